@@ -1,0 +1,170 @@
+/* daft_exprt_b200 — C-ABI of the Blackwell-native (sm_100a) Daft-Exprt mel-prediction path.
+ *
+ * This is the drop-in boundary.  The reference (ubisoft/ubisoft-laforge-daft-exprt) has NO native code and
+ * no FFI: every hot-path FLOP is a torch.nn call inside `src/daft_exprt/model.py` / `loss.py`.  Each entry point below
+ * therefore cites the reference Python call site(s) it replaces; the host-side binding a maintainer adds is the ctypes stub
+ * shown in INTEGRATION.md (and implemented in ubisoft-laforge-daft-exprt_b200/cabi.py).
+ *
+ * Conventions
+ *   - plain C: raw device pointers + sizes, no torch types; all pointers are BORROWED (caller allocates every output and
+ *     every workspace; the library never allocates persistent device memory and never frees caller memory);
+ *   - activations are channels-last fp32 `[B, S, C]` (row = one phoneme / mel frame); lengths / ids are int64 device arrays,
+ *     exactly the tensors `DaftExprt.parse_batch` (model.py:727-753) produces;
+ *   - every call is asynchronous on `stream` (a `cudaStream_t` passed as void*; pass torch's current stream) and re-entrant
+ *     per stream; no host synchronisation inside;
+ *   - return 0 on success, negative on error (DX_ERR_*); `dx_last_error()` returns a thread-local message; no exceptions
+ *     cross the ABI;
+ *   - dropout: `p == 0` disables; masks are regenerated from (seed, element index) in backward, never stored.
+ */
+#ifndef DAFT_EXPRT_B200_H
+#define DAFT_EXPRT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DX_ABI_VERSION 1
+#define DX_GEMM_FP32_CUDA_CORES 0 /* exact fp32 (parity mode) */
+#define DX_GEMM_TCGEN05_TF32 1    /* tcgen05.mma kind::tf32, TMEM accumulators, TMA-fed (default on sm_100) */
+
+const char* dx_last_error(void);
+int dx_abi_version(void);
+/* 0 when the current device is sm_100 (B200); negative otherwise */
+int dx_device_check(void);
+int dx_set_gemm_backend(int backend);
+int dx_get_gemm_backend(void);
+
+/* ---- Conv1d / Linear as channels-last GEMMs --------------------------------------------------------------------------
+ * replaces nn.Conv1d inside ConvNorm1D (model.py:82,86-94) and nn.Linear inside LinearNorm (model.py:63,66-72), incl. the
+ * in/out projections of nn.MultiheadAttention (model.py:165).  Weights are consumed in a packed, cached layout. */
+/* w [Cout][Cin][KW] (the parameter) -> fwd [KW][Cout][Cin] and dgrad [KW][Cin][Cout] with taps flipped (either may be NULL) */
+int dx_pack_conv_weight(const float* w, float* fwd, float* dgrad, int Cout, int Cin, int KW, int round_tf32, void* stream);
+/* y[b,s,n] = epi(alpha * sum_{tap,c} x[b, s+tap-(KW-1)/2, c] * w[tap][n][c] + bias[n]); zero padding at s<0, s>=S only.
+ * epi: relu, then multiply by (relu_src > 0) when relu_src != NULL (ReLU backward fused into a dgrad), then + add_src
+ * (same layout as y; residual / gradient accumulation) when != NULL, then optional tf32 rounding of the stored value.  backend < 0 selects the global default. */
+int dx_conv_gemm(const float* x, const float* w_packed, const float* bias, const float* relu_src, const float* add_src, float* y, int B, int S,
+                 int Cin, int Cout, int KW, int ldx, int ldy, float alpha, int relu, int round_tf32, int backend, void* stream);
+size_t dx_conv_wgrad_workspace(int B, int S, int Cin, int Cout, int KW, int backend);
+/* dw[co][ci][tap] = alpha * sum_{b,s} dy[b,s,co] * x[b, s+tap-pad, ci]  (parameter layout);  dbias[co] = alpha * sum dy */
+int dx_conv_wgrad(const float* x, const float* dy, float* dw, float* dbias, void* workspace, size_t workspace_bytes, int B,
+                  int S, int Cin, int Cout, int KW, int ldx, float alpha, int backend, void* stream);
+int dx_colsum(const float* dy, float* db, int rows, int C, float alpha, void* stream);
+int dx_relu_bwd(const float* dy, const float* y, float* dx, size_t n, void* stream);
+int dx_scale_copy(const float* x, float* y, float alpha, size_t n, void* stream);
+
+/* ---- multi-head self-attention core (flash style, S x S never materialised) ------------------------------------------
+ * replaces nn.MultiheadAttention's scaled-dot-product part as called at model.py:182-186 (key_padding_mask from lengths).
+ * qkv [B,S,3*H*dh] = in-projection output (q|k|v); ctx [B,S,H*dh]; lse [B,H,S]; padded query rows are written as 0. */
+int dx_attention_fwd(const float* qkv, const int64_t* lens, float* ctx, float* lse, int B, int S, int H, int dh,
+                     float dropout_p, uint64_t seed, void* stream);
+/* delta: scratch [B,H,S]; dqkv [B,S,3*H*dh] is fully written */
+int dx_attention_bwd(const float* qkv, const int64_t* lens, const float* ctx, const float* lse, const float* dctx, float* dqkv,
+                     float* delta, int B, int S, int H, int dh, float dropout_p, uint64_t seed, void* stream);
+
+/* ---- residual + LayerNorm + FiLM + padding mask ----------------------------------------------------------------------
+ * v = dropout_in(a) + res;  y = mask(film_gamma * dropout_out(LN(v)*w + b) + film_beta)
+ * replaces model.py:189-191,259 (attention epilogue), :226-235,262 (conv-FF epilogue + FiLM), the LayerNorm+Dropout pairs
+ * of the pre-net (:347-348,354-355,361-362) and of the prosody predictor (:534-535,541-542,559-566).
+ * film: gamma at film[b*film_stride + c], beta at film[b*film_stride + D + c] (NULL = no FiLM); lens NULL = no mask.
+ * D in {128, 256, 1024}.  Saves xhat [B,S,D] and rstd [B*S] for backward. */
+int dx_ln_fwd(const float* a, const float* res, const float* ln_w, const float* ln_b, const float* film, int film_stride,
+              const int64_t* lens, float* y, float* xhat, float* rstd, int B, int S, int D, float p_in, uint64_t seed_in,
+              float p_out, uint64_t seed_out, void* stream);
+/* relu_src (nullable, [B,S,D]): dv/da are multiplied by (relu_src > 0) — the ReLU that feeds the LN in the pre-net/predictor.
+ * dv = grad wrt v (== grad wrt res); da (nullable) = grad wrt a when p_in > 0; dln_w/dln_b [D]; dfilm [B,2D] nullable */
+int dx_ln_bwd(const float* dy, const float* xhat, const float* rstd, const float* ln_w, const float* ln_b, const float* film,
+              int film_stride, const int64_t* lens, const float* relu_src, float* dv, float* da, float* dln_w, float* dln_b, float* dfilm, int B,
+              int S, int D, float p_in, uint64_t seed_in, float p_out, uint64_t seed_out, void* stream);
+
+/* ---- embeddings, positional encoding, masks ---------------------------------------------------------------------------
+ * pe: the reference's sinusoid table (model.py:123-130), rows >= max(S) needed.  replaces model.py:497-504. */
+int dx_embed_pe_fwd(const int64_t* symbols, const int64_t* lens, const float* emb, const float* pe, float* y, int B, int L,
+                    int D, int n_symbols, void* stream);
+int dx_embed_pe_bwd(const int64_t* symbols, const int64_t* lens, const float* dy, float* demb, int B, int L, int D,
+                    int n_symbols, void* stream);
+/* y = mask * (x + PE + Conv1d(1->D,k3)(energy) + Conv1d(1->D,k3)(pitch)); energy == NULL -> y = mask * (x + PE).
+ * replaces model.py:400-414 (prosody encoder input) and model.py:696-701 (frame decoder input). */
+int dx_frame_input_fwd(const float* x, const float* energy, const float* pitch, const float* we, const float* be,
+                       const float* wp, const float* bp, const float* pe, const int64_t* lens, float* y, int B, int T, int D,
+                       void* stream);
+int dx_frame_input_bwd(const float* dy, const float* energy, const float* pitch, const int64_t* lens, float* dx, float* dwe,
+                       float* dbe, float* dwp, float* dbp, int B, int T, int D, void* stream);
+/* pooled[b,:] = sum_s x[b,s,:] / len[b]   (model.py:419) */
+int dx_meanpool_fwd(const float* x, const int64_t* lens, float* pooled, int B, int S, int D, void* stream);
+int dx_meanpool_bwd(const float* dpooled, const int64_t* lens, float* dx, int B, int S, int D, void* stream);
+/* h = pooled + spk_embedding[speaker_ids]   (model.py:423-424) */
+int dx_add_speaker_fwd(const float* pooled, const int64_t* spk, const float* spk_emb, float* h, int B, int D, int n_spk,
+                       void* stream);
+int dx_add_speaker_bwd(const float* dh, const int64_t* spk, float* dspk_emb, int B, int D, int n_spk, void* stream);
+/* FiLM split + scalar post-multipliers (model.py:430-461).  graw/braw [B,NF]; post [2,NB] or NULL; film [B, 2*NF] laid out
+ * module after module as [nb_blocks][gamma(ch) | beta(ch)].  n_modules <= 4. */
+int dx_film_assemble_fwd(const float* graw, const float* braw, const float* post, float* film, int B, int n_modules,
+                         const int* nb_blocks, const int* channels, void* stream);
+int dx_film_assemble_bwd(const float* dfilm, const float* graw, const float* braw, const float* post, float* dgraw,
+                         float* dbraw, float* dpost, int B, int n_modules, const int* nb_blocks, const int* channels,
+                         void* stream);
+/* out[j][b*S+s] = mask * (x[b,s,:] . w[j,:] + bias[j]), j < NO <= 4  (predictor head, model.py:566-573) */
+int dx_narrow_linear_fwd(const float* x, const float* w, const float* bias, const int64_t* lens, float* out, int B, int S,
+                         int C, int NO, void* stream);
+int dx_narrow_linear_bwd(const float* dout, const float* x, const float* w, const int64_t* lens, float* dx, float* dw,
+                         float* db, int B, int S, int C, int NO, void* stream);
+/* mel[b,m,t] = mask * y[b,t,m]   (model.py:707-708) */
+int dx_mask_transpose_fwd(const float* y, const int64_t* lens, float* mel, int B, int T, int M, void* stream);
+int dx_mask_transpose_bwd(const float* dmel, const int64_t* lens, float* dy, int B, int T, int M, void* stream);
+
+/* ---- Gaussian upsampling = duration-driven phoneme -> frame expansion (north_star's "LengthRegulator") ---------------
+ * replaces GaussianUpsamplingModule.forward, model.py:608-662.
+ * prep: xp = x + conv3(energy) + conv3(pitch); z = (xp + conv3(dur_f)).rw + rb; sigma = softplus(z) (padded -> 1);
+ *       csum = inclusive int64 prefix sum of dur_i (BIT-EXACT), total[b] = sum, mu = float(d)/2 + float(csum - d). */
+int dx_gauss_prep(const float* x, const float* dur_f, const int64_t* dur_i, const float* energy, const float* pitch,
+                  const int64_t* lens, const float* wd, const float* bd, const float* we, const float* be, const float* wp,
+                  const float* bp, const float* rw, const float* rb, float* xp, float* z, float* sigma, float* mu,
+                  int64_t* csum, int64_t* total, int B, int L, int D, void* stream);
+/* up[b,t,:] = sum_i w[i,t] xp[b,i,:];  weights [B,L,T] = the reference's `alignments` output */
+int dx_gauss_upsample_fwd(const float* xp, const float* mu, const float* sigma, const int64_t* lens, float* up, float* weights,
+                          int B, int L, int T, int D, void* stream);
+/* scratch: B*L + 2*B*T floats.  dx [B,L,D] = grad wrt x; parameter grads in the parameters' own layouts. */
+int dx_gauss_upsample_bwd(const float* dup, const float* dweights, const float* up, const float* weights, const float* xp,
+                          const float* z, const float* mu, const float* sigma, const float* dur_f, const float* energy,
+                          const float* pitch, const int64_t* lens, const float* wd, const float* bd, const float* rw, float* dx,
+                          float* dwd, float* dbd, float* dwe, float* dbe, float* dwp, float* dbp, float* drw, float* drb,
+                          float* scratch, int B, int L, int T, int D, void* stream);
+
+/* ---- loss: replaces DaftExprtLoss.forward, loss.py:30-106 ------------------------------------------------------------
+ * out[8] = {speaker, post_mult, duration, energy, pitch, mel_l1, mel_l2, total} (already weighted); acc: scratch [B,8]. */
+int dx_loss_fwd(const float* spk_logits, const int64_t* spk_ids, const float* post, const float* dur_p, const float* energy_p,
+                const float* pitch_p, const float* dur_t, const float* energy_t, const float* pitch_t, const float* mel_p,
+                const float* mel_t, const int64_t* in_lens, const int64_t* out_lens, int B, int L, int T, int M, int NS, int NP,
+                float w_adv, float w_post, float w_dur, float w_energy, float w_pitch, float w_mel, float* acc, float* out,
+                void* stream);
+int dx_loss_bwd(const float* gout, const float* spk_logits, const int64_t* spk_ids, const float* post, const float* dur_p,
+                const float* energy_p, const float* pitch_p, const float* dur_t, const float* energy_t, const float* pitch_t,
+                const float* mel_p, const float* mel_t, const int64_t* in_lens, const int64_t* out_lens, int B, int L, int T,
+                int M, int NS, int NP, float w_adv, float w_post, float w_dur, float w_energy, float w_pitch, float w_mel,
+                float* dspk_logits, float* dpost, float* ddur, float* denergy, float* dpitch, float* dmel, void* stream);
+
+/* ---- inference-time controls ------------------------------------------------------------------------------------------
+ * replaces DaftExprt.get_int_durations (model.py:789-812) + duration_to_integer (extract_features.py:69-111): BIT-EXACT.
+ * dur_out = thresholded float durations, dur_int [B,L], totals[b] = sum, err[b] != 0 where the reference would raise. */
+int dx_int_durations(const float* dur_pred, const float* dur_factors, const int64_t* lens, float* dur_out, int64_t* dur_int,
+                     int64_t* totals, int* err, int B, int L, int sampling_rate, int filter_length, int hop_length,
+                     int centered, void* stream);
+/* model.py:895-899 */
+int dx_inference_adjust(float* energy, float* pitch, const float* energy_factors, const int64_t* dur_int, int B, int L,
+                        void* stream);
+/* model.py:814-834; stats [n_speakers][2] = {mean, std} float32 */
+int dx_pitch_shift(float* pitch, const float* factors, const int64_t* spk, const float* stats, int B, int L, void* stream);
+/* model.py:836-864 */
+int dx_pitch_multiply(float* pitch, const float* factors, int B, int L, void* stream);
+
+/* ---- optimiser: fused Adam over a flat buffer (train.py:299-301,401) ---------------------------------------------------*/
+int dx_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAFT_EXPRT_B200_H */

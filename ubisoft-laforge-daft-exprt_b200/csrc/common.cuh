@@ -1,0 +1,78 @@
+// Shared device/host helpers for the daft_exprt_b200 CUDA kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#define DX_OK 0
+#define DX_ERR_ARG -1
+#define DX_ERR_CUDA -2
+#define DX_ERR_UNSUPPORTED -3
+
+namespace dx {
+
+void set_last_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define DX_REQUIRE(cond, ...)                          \
+    do {                                               \
+        if (!(cond)) {                                 \
+            dx::set_last_error(__VA_ARGS__);           \
+            return DX_ERR_ARG;                         \
+        }                                              \
+    } while (0)
+
+#define DX_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            dx::set_last_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return DX_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+__host__ __device__ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+// 1-D grid for a grid-stride loop: ceil(n / per) blocks, at least 1, capped at a few waves of the 148 SMs
+static inline int grid_1d(size_t n, int per = 256, int cap = 148 * 16) {
+    size_t g = (n + per - 1) / per;
+    if (g < 1) g = 1;
+    if (g > (size_t)cap) g = cap;
+    return (int)g;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// round-to-nearest fp32 -> tf32 (kept in an fp32 container); tcgen05 kind::tf32 ignores the low 13 mantissa bits,
+// so operands that only feed tensor-core GEMMs are pre-rounded to avoid a truncation bias.
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// Stateless counter-based uniform in [0,1): the same (seed, index) gives the same value in forward and backward,
+// so dropout masks are never stored.
+__device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned long long idx) {
+    unsigned long long x = seed + idx * 0x9E3779B97F4A7C15ull;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return (float)(x >> 40) * (1.0f / 16777216.0f);
+}
+__device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned long long idx, float p, float inv_keep) {
+    return hash_uniform(seed, idx) >= p ? inv_keep : 0.f;
+}
+#endif
+
+}  // namespace dx

@@ -1,0 +1,232 @@
+// Fused residual + LayerNorm + FiLM + padding-mask kernels (forward / backward), one warp per row.
+//
+//   v = dropout_in(a) + res ;  y = mask( gamma_film * dropout_out(LN(v) * w + b) + beta_film )
+//
+// Covers the three LayerNorm sites of the hot path:
+//   * attention epilogue        LN(dropout(out_proj) + x), zero padded rows        reference model.py:189-191, :259
+//   * conv feed-forward epilogue gamma * LN(dropout(conv2) + x) + beta, zero padded model.py:226-235, :262
+//   * pre-net / predictor        dropout(LN(relu(conv)))  (ReLU is done in the GEMM epilogue)  model.py:341-363, :528-543
+// HBM-bound: algorithmic bytes per row = (2 reads + 2 writes) * D * 4.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dx {
+
+template <int VPT>  // values per lane, D = 32 * VPT
+__global__ void __launch_bounds__(256) ln_fwd_kernel(LnArgs p) {
+    constexpr int D = 32 * VPT, NV = VPT / 4;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int R = p.B * p.S;
+    if (row >= R) return;
+    const int b = row / p.S, s = row - b * p.S;
+    const bool masked = p.lens && s >= (int)p.lens[b];
+    float* yrow = p.y + (size_t)row * D;
+    float* hrow = p.xhat + (size_t)row * D;
+    if (masked) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = (j * 32 + lane) * 4;
+            *reinterpret_cast<float4*>(yrow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(hrow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (lane == 0) p.rstd[row] = 0.f;
+        return;
+    }
+    float v[VPT];
+    const float* arow = p.a + (size_t)row * D;
+    const float inv_keep_in = p.p_in > 0.f ? 1.f / (1.f - p.p_in) : 1.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = (j * 32 + lane) * 4;
+        const float4 t = *reinterpret_cast<const float4*>(arow + c);
+        v[j * 4 + 0] = t.x; v[j * 4 + 1] = t.y; v[j * 4 + 2] = t.z; v[j * 4 + 3] = t.w;
+        if (p.p_in > 0.f) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[j * 4 + e] *= dropout_scale(p.seed_in, (unsigned long long)row * D + c + e, p.p_in, inv_keep_in);
+        }
+        if (p.res) {
+            const float4 r = *reinterpret_cast<const float4*>(p.res + (size_t)row * D + c);
+            v[j * 4 + 0] += r.x; v[j * 4 + 1] += r.y; v[j * 4 + 2] += r.z; v[j * 4 + 3] += r.w;
+        }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) sum += v[i];
+    const float mean = warp_sum(sum) * (1.f / D);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) { const float d = v[i] - mean; sq += d * d; }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.f / D) + 1e-5f);
+    if (lane == 0) p.rstd[row] = rstd;
+    const float inv_keep_out = p.p_out > 0.f ? 1.f / (1.f - p.p_out) : 1.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = (j * 32 + lane) * 4;
+        const float4 w = *reinterpret_cast<const float4*>(p.ln_w + c);
+        const float4 bb = *reinterpret_cast<const float4*>(p.ln_b + c);
+        const float wv[4] = {w.x, w.y, w.z, w.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+        float h[4], o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            h[e] = (v[j * 4 + e] - mean) * rstd;
+            o[e] = h[e] * wv[e] + bv[e];
+        }
+        if (p.p_out > 0.f) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] *= dropout_scale(p.seed_out, (unsigned long long)row * D + c + e, p.p_out, inv_keep_out);
+        }
+        if (p.film) {
+            const float4 g = *reinterpret_cast<const float4*>(p.film + (size_t)b * p.film_stride + c);
+            const float4 be = *reinterpret_cast<const float4*>(p.film + (size_t)b * p.film_stride + D + c);
+            o[0] = g.x * o[0] + be.x; o[1] = g.y * o[1] + be.y; o[2] = g.z * o[2] + be.z; o[3] = g.w * o[3] + be.w;
+        }
+        *reinterpret_cast<float4*>(hrow + c) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(yrow + c) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// grad wrt v:  g = dy * mask * drop_out * film_gamma * w ;  dv = rstd * (g - mean(g) - xhat * mean(g * xhat))
+template <int VPT>
+__global__ void __launch_bounds__(256) ln_bwd_dx_kernel(LnArgs p) {
+    constexpr int D = 32 * VPT, NV = VPT / 4;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int R = p.B * p.S;
+    if (row >= R) return;
+    const int b = row / p.S, s = row - b * p.S;
+    const bool masked = p.lens && s >= (int)p.lens[b];
+    float* dvrow = p.dv + (size_t)row * D;
+    float* darow = p.da ? p.da + (size_t)row * D : nullptr;
+    if (masked) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = (j * 32 + lane) * 4;
+            *reinterpret_cast<float4*>(dvrow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (darow) *reinterpret_cast<float4*>(darow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        return;
+    }
+    const float inv_keep_out = p.p_out > 0.f ? 1.f / (1.f - p.p_out) : 1.f;
+    const float inv_keep_in = p.p_in > 0.f ? 1.f / (1.f - p.p_in) : 1.f;
+    float g[VPT], h[VPT];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = (j * 32 + lane) * 4;
+        const float4 d = *reinterpret_cast<const float4*>(p.dy + (size_t)row * D + c);
+        const float4 hh = *reinterpret_cast<const float4*>(p.xhat + (size_t)row * D + c);
+        const float4 w = *reinterpret_cast<const float4*>(p.ln_w + c);
+        float dv[4] = {d.x, d.y, d.z, d.w};
+        const float wv[4] = {w.x, w.y, w.z, w.w};
+        h[j * 4 + 0] = hh.x; h[j * 4 + 1] = hh.y; h[j * 4 + 2] = hh.z; h[j * 4 + 3] = hh.w;
+        if (p.p_out > 0.f) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dv[e] *= dropout_scale(p.seed_out, (unsigned long long)row * D + c + e, p.p_out, inv_keep_out);
+        }
+        if (p.film) {
+            const float4 fg = *reinterpret_cast<const float4*>(p.film + (size_t)b * p.film_stride + c);
+            dv[0] *= fg.x; dv[1] *= fg.y; dv[2] *= fg.z; dv[3] *= fg.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            g[j * 4 + e] = dv[e] * wv[e];
+            s1 += g[j * 4 + e];
+            s2 += g[j * 4 + e] * h[j * 4 + e];
+        }
+    }
+    const float c1 = warp_sum(s1) * (1.f / D), c2 = warp_sum(s2) * (1.f / D);
+    const float rstd = p.rstd[row];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = (j * 32 + lane) * 4;
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = rstd * (g[j * 4 + e] - c1 - h[j * 4 + e] * c2);
+        if (p.relu_src) {
+            const float4 rs = *reinterpret_cast<const float4*>(p.relu_src + (size_t)row * D + c);
+            o[0] = rs.x > 0.f ? o[0] : 0.f; o[1] = rs.y > 0.f ? o[1] : 0.f; o[2] = rs.z > 0.f ? o[2] : 0.f; o[3] = rs.w > 0.f ? o[3] : 0.f;
+        }
+        *reinterpret_cast<float4*>(dvrow + c) = make_float4(o[0], o[1], o[2], o[3]);
+        if (darow) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] *= dropout_scale(p.seed_in, (unsigned long long)row * D + c + e, p.p_in, inv_keep_in);
+            *reinterpret_cast<float4*>(darow + c) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+// Column reductions: dln_w[c] += sum_r q*xhat, dln_b[c] += sum_r q  with q = dy*mask*drop_out*film_gamma;
+// dfilm_gamma[b][c] += sum_s e*drop_out(xhat*w+b), dfilm_beta[b][c] += sum_s e  with e = dy*mask.
+// Block = 32 columns x 8 row lanes over a row chunk inside one utterance; cross-block accumulation with fp32 atomics.
+__global__ void __launch_bounds__(256) ln_bwd_param_kernel(LnArgs p, int rows_per_chunk) {
+    __shared__ float sm[4][8][33];
+    const int D = p.D;
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl, b = blockIdx.z;
+    const int len = p.lens ? min((int)p.lens[b], p.S) : p.S;
+    const int s0 = blockIdx.y * rows_per_chunk, s1 = min(len, s0 + rows_per_chunk);
+    const float inv_keep_out = p.p_out > 0.f ? 1.f / (1.f - p.p_out) : 1.f;
+    float aw = 0.f, ab = 0.f, ag = 0.f, abe = 0.f;
+    if (c < D) {
+        const float w = p.ln_w[c], bb = p.ln_b[c];
+        const float fg = p.film ? p.film[(size_t)b * p.film_stride + c] : 1.f;
+        for (int s = s0 + rl; s < s1; s += 8) {
+            const size_t i = ((size_t)b * p.S + s) * D + c;
+            const float e = p.dy[i];
+            const float dm = p.p_out > 0.f ? dropout_scale(p.seed_out, i, p.p_out, inv_keep_out) : 1.f;
+            const float h = p.xhat[i];
+            ag += e * dm * (h * w + bb);
+            abe += e;
+            const float q = e * fg * dm;
+            aw += q * h;
+            ab += q;
+        }
+    }
+    sm[0][rl][cl] = aw; sm[1][rl][cl] = ab; sm[2][rl][cl] = ag; sm[3][rl][cl] = abe;
+    __syncthreads();
+    if (rl < 4 && c < D) {
+        float tot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tot += sm[rl][k][cl];
+        if (rl == 0) atomicAdd(p.dln_w + c, tot);
+        else if (rl == 1) atomicAdd(p.dln_b + c, tot);
+        else if (p.dfilm) atomicAdd(p.dfilm + (size_t)b * 2 * D + (rl == 2 ? 0 : D) + c, tot);
+    }
+}
+
+int ln_fwd(const LnArgs& a, cudaStream_t st) {
+    const int R = a.B * a.S;
+    const int blocks = ceil_div(R, 8);
+    switch (a.D) {
+        case 128: ln_fwd_kernel<4><<<blocks, 256, 0, st>>>(a); break;
+        case 256: ln_fwd_kernel<8><<<blocks, 256, 0, st>>>(a); break;
+        case 1024: ln_fwd_kernel<32><<<blocks, 256, 0, st>>>(a); break;
+        default: set_last_error("ln_fwd: unsupported width D=%d (128, 256, 1024)", a.D); return DX_ERR_UNSUPPORTED;
+    }
+    return check_launch("ln_fwd");
+}
+
+int ln_bwd(const LnArgs& a, cudaStream_t st) {
+    const int R = a.B * a.S;
+    const int blocks = ceil_div(R, 8);
+    switch (a.D) {
+        case 128: ln_bwd_dx_kernel<4><<<blocks, 256, 0, st>>>(a); break;
+        case 256: ln_bwd_dx_kernel<8><<<blocks, 256, 0, st>>>(a); break;
+        case 1024: ln_bwd_dx_kernel<32><<<blocks, 256, 0, st>>>(a); break;
+        default: set_last_error("ln_bwd: unsupported width D=%d (128, 256, 1024)", a.D); return DX_ERR_UNSUPPORTED;
+    }
+    int rc = check_launch("ln_bwd_dx");
+    if (rc) return rc;
+    DX_CUDA(cudaMemsetAsync(a.dln_w, 0, (size_t)a.D * sizeof(float), st));
+    DX_CUDA(cudaMemsetAsync(a.dln_b, 0, (size_t)a.D * sizeof(float), st));
+    if (a.dfilm) DX_CUDA(cudaMemsetAsync(a.dfilm, 0, (size_t)a.B * 2 * a.D * sizeof(float), st));
+    const int col_blocks = ceil_div(a.D, 32);
+    int chunks = max(1, min(ceil_div(a.S, 64), ceil_div(148 * 4, col_blocks * a.B)));
+    const int rpc = ceil_div(a.S, chunks);
+    dim3 grid(col_blocks, ceil_div(a.S, rpc), a.B);
+    ln_bwd_param_kernel<<<grid, 256, 0, st>>>(a, rpc);
+    return check_launch("ln_bwd_param");
+}
+
+}  // namespace dx

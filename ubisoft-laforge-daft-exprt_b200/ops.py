@@ -1,0 +1,595 @@
+"""Autograd functions of the Daft-Exprt hot path: every forward/backward here is a sequence of C-ABI calls into
+libdaftexprt_b200.so (hand-written sm_100a CUDA).  PyTorch provides device memory, streams and the autograd tape only.
+
+Granularity = one Function per sub-layer of the reference (`model.py`), so that the tape has ~40 nodes per step and
+the fusions live below the ABI:
+  AttentionSubLayer   MultiHeadAttention.forward + masked_fill            model.py:171-193, :258-259
+  ConvFFSubLayer      PositionWiseConvFF.forward + masked_fill            model.py:220-237, :261-262
+  PreNet              ProsodyEncoder.convs                                model.py:341-363, :408-409
+  FrameInput          + energy/pitch embeddings + PE + mask               model.py:400-414 / :696-701
+  MeanPoolSpeaker     time pooling + speaker embedding                    model.py:419-424
+  FilmHead            gammas/betas predictors + post-multipliers          model.py:427-461
+  Linear              LinearNorm (+ReLU), gradient reversal folded in     model.py:27-38, :276-283
+  EmbedPE             symbols embedding + PE + mask                       model.py:497-504
+  Predictor           LocalProsodyPredictor.forward                       model.py:549-575
+  GaussUpsample       GaussianUpsamplingModule.forward                    model.py:608-662
+  MelProjection       Linear(128->80) + mask + transpose                  model.py:706-708
+  Loss                DaftExprtLoss.forward                               loss.py:30-106
+"""
+import ctypes
+import threading
+
+import torch
+
+from . import cabi
+
+_state = threading.local()
+_weights_epoch = 0
+_pack_cache = {}
+_seed_counter = [0]
+_backend = [cabi.DX_GEMM_FP32_CUDA_CORES]
+launch_count = [0]   # number of C-ABI compute calls issued (each launches >= 1 of our kernels)
+
+
+def lib():
+    return cabi.load()
+
+
+def set_backend(name):
+    """'fp32' = exact CUDA-core GEMMs (parity mode); 'tf32' = tcgen05 tensor-core GEMMs (tf32 multiply, fp32 accumulate)."""
+    be = {'fp32': cabi.DX_GEMM_FP32_CUDA_CORES, 'tf32': cabi.DX_GEMM_TCGEN05_TF32}[name]
+    cabi.check(lib().dx_set_gemm_backend(be), 'dx_set_gemm_backend')
+    _backend[0] = be
+    invalidate_packed_weights()
+
+
+def get_backend():
+    return 'tf32' if _backend[0] == cabi.DX_GEMM_TCGEN05_TF32 else 'fp32'
+
+
+def invalidate_packed_weights():
+    """Call after parameters were modified through raw pointers (e.g. dx_adam_step), which does not bump tensor versions."""
+    global _weights_epoch
+    _weights_epoch += 1
+    _pack_cache.clear()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _call(name, *args):
+    launch_count[0] += 1
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise RuntimeError(f'{name} failed (rc={rc}): {cabi.last_error()}')
+
+
+def next_seed():
+    _seed_counter[0] += 1
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + _seed_counter[0] * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+
+
+def _check_input(t, dtype=torch.float32):
+    if t.device.type != 'cuda':
+        raise RuntimeError('daft_exprt_b200 ops need CUDA tensors: there is no CPU fallback')
+    if t.dtype != dtype:
+        raise RuntimeError(f'expected {dtype}, got {t.dtype}')
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# packed weights (derived, cached, version-checked; the parameters keep the reference's own layout)
+# ----------------------------------------------------------------------------------------------------------------------
+def packed(weight):
+    """weight [Cout, Cin, KW] or [Cout, Cin] -> (fwd [KW, Cout, Cin], dgrad [KW, Cin, Cout] taps flipped)."""
+    w = weight.detach()
+    key = id(weight)
+    ver = (w.data_ptr(), w._version, _weights_epoch, _backend[0])
+    hit = _pack_cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1], hit[2]
+    w = _check_input(w)
+    cout, cin = w.shape[0], w.shape[1]
+    kw = w.shape[2] if w.dim() == 3 else 1
+    fwd = torch.empty(kw, cout, cin, device=w.device, dtype=torch.float32)
+    dgrad = torch.empty(kw, cin, cout, device=w.device, dtype=torch.float32)
+    rnd = 1 if _backend[0] == cabi.DX_GEMM_TCGEN05_TF32 else 0
+    _call('dx_pack_conv_weight', _p(w), _p(fwd), _p(dgrad), cout, cin, kw, rnd, _st())
+    _pack_cache[key] = (ver, fwd, dgrad)
+    return fwd, dgrad
+
+
+def conv_gemm(x, wp, bias, B, S, relu=False, relu_src=None, add_src=None, alpha=1.0, round_out=False, ldx=None):
+    """x [B,S,Cin] (row stride ldx) · packed weight [KW,Cout,Cin] -> [B,S,Cout]"""
+    kw, cout, cin = wp.shape
+    y = torch.empty(B, S, cout, device=wp.device, dtype=torch.float32)
+    rnd = 1 if (round_out and _backend[0] == cabi.DX_GEMM_TCGEN05_TF32) else 0
+    _call('dx_conv_gemm', _p(x), _p(wp), _p(bias), _p(relu_src), _p(add_src), _p(y), B, S, cin, cout, kw,
+          cin if ldx is None else ldx, cout, float(alpha), int(relu), rnd, -1, _st())
+    return y
+
+
+def linear_rows(x2d, wp, bias, **kw):
+    """Linear over a [R, Cin] matrix (KW == 1: rows are independent, so the batch structure is irrelevant)."""
+    R = x2d.shape[0]
+    return conv_gemm(x2d, wp, bias, 1, R, **kw).view(R, -1)
+
+
+def conv_wgrad(x, dy, B, S, cin, cout, kw, shape, want_bias=True, ldx=None, alpha=1.0):
+    """-> (dw in the parameter's own layout `shape`, dbias [Cout] or None)"""
+    dw = torch.empty(tuple(shape), device=dy.device, dtype=torch.float32)
+    db = torch.empty(cout, device=dy.device, dtype=torch.float32) if want_bias else None
+    nbytes = lib().dx_conv_wgrad_workspace(B, S, cin, cout, kw, -1)
+    ws = torch.empty(max(nbytes, 16) // 4 + 4, device=dy.device, dtype=torch.float32)
+    _call('dx_conv_wgrad', _p(x), _p(dy), _p(dw), _p(db), _p(ws), ws.numel() * 4, B, S, cin, cout, kw,
+          cin if ldx is None else ldx, float(alpha), -1, _st())
+    return dw, db
+
+
+def ln_fwd(a, res, ln_w, ln_b, film, film_stride, lens, B, S, D, p_in=0.0, seed_in=0, p_out=0.0, seed_out=0):
+    y = torch.empty(B, S, D, device=a.device, dtype=torch.float32)
+    xhat = torch.empty(B, S, D, device=a.device, dtype=torch.float32)
+    rstd = torch.empty(B * S, device=a.device, dtype=torch.float32)
+    _call('dx_ln_fwd', _p(a), _p(res), _p(ln_w), _p(ln_b), _p(film), film_stride, _p(lens), _p(y), _p(xhat), _p(rstd),
+          B, S, D, float(p_in), seed_in, float(p_out), seed_out, _st())
+    return y, xhat, rstd
+
+
+def ln_bwd(dy, xhat, rstd, ln_w, ln_b, film, film_stride, lens, B, S, D, relu_src=None, p_in=0.0, seed_in=0, p_out=0.0,
+           seed_out=0, want_film=False):
+    dv = torch.empty(B, S, D, device=dy.device, dtype=torch.float32)
+    da = torch.empty(B, S, D, device=dy.device, dtype=torch.float32) if p_in > 0 else None
+    dw = torch.empty(D, device=dy.device, dtype=torch.float32)
+    db = torch.empty(D, device=dy.device, dtype=torch.float32)
+    dfilm = torch.empty(B, 2 * D, device=dy.device, dtype=torch.float32) if want_film else None
+    _call('dx_ln_bwd', _p(dy), _p(xhat), _p(rstd), _p(ln_w), _p(ln_b), _p(film), film_stride, _p(lens), _p(relu_src),
+          _p(dv), _p(da), _p(dw), _p(db), _p(dfilm), B, S, D, float(p_in), seed_in, float(p_out), seed_out, _st())
+    return dv, (da if da is not None else dv), dw, db, dfilm
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class AttentionSubLayer(torch.autograd.Function):
+    """y = mask(LN(dropout(out_proj(SDPA(in_proj(x)))) + x))"""
+
+    @staticmethod
+    def forward(ctx, x, lens, in_w, in_b, out_w, out_b, ln_w, ln_b, nb_heads, p_drop):
+        x = _check_input(x)
+        B, S, D = x.shape
+        dh = D // nb_heads
+        in_wp, in_wd = packed(in_w)
+        out_wp, out_wd = packed(out_w)
+        qkv = conv_gemm(x, in_wp, in_b, 1, B * S).view(B, S, 3 * D)
+        att = torch.empty(B, S, D, device=x.device, dtype=torch.float32)
+        lse = torch.empty(B, nb_heads, S, device=x.device, dtype=torch.float32)
+        seed_attn, seed_out = (next_seed(), next_seed()) if p_drop > 0 else (0, 0)
+        _call('dx_attention_fwd', _p(qkv), _p(lens), _p(att), _p(lse), B, S, nb_heads, dh, float(p_drop), seed_attn, _st())
+        proj = conv_gemm(att, out_wp, out_b, 1, B * S)
+        y, xhat, rstd = ln_fwd(proj, x, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p_drop, seed_in=seed_out)
+        ctx.save_for_backward(x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b, in_wd, out_wd)
+        ctx.cfg = (B, S, D, nb_heads, dh, float(p_drop), seed_attn, seed_out, in_w.shape, out_w.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b, in_wd, out_wd = ctx.saved_tensors
+        B, S, D, H, dh, p, seed_attn, seed_out, in_shape, out_shape = ctx.cfg
+        dy = _check_input(dy)
+        dv, dproj, dln_w, dln_b, _ = ln_bwd(dy, xhat, rstd, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p, seed_in=seed_out)
+        datt = conv_gemm(dproj, out_wd, None, 1, B * S)
+        d_out_w, d_out_b = conv_wgrad(att, dproj, 1, B * S, D, D, 1, out_shape)
+        dqkv = torch.empty(B, S, 3 * D, device=dy.device, dtype=torch.float32)
+        delta = torch.empty(B, H, S, device=dy.device, dtype=torch.float32)
+        _call('dx_attention_bwd', _p(qkv), _p(lens), _p(att), _p(lse), _p(datt), _p(dqkv), _p(delta), B, S, H, dh, p,
+              seed_attn, _st())
+        dx = conv_gemm(dqkv, in_wd, None, 1, B * S, add_src=dv).view(B, S, D)
+        d_in_w, d_in_b = conv_wgrad(x, dqkv, 1, B * S, D, 3 * D, 1, in_shape)
+        return dx, None, d_in_w, d_in_b, d_out_w, d_out_b, dln_w, dln_b, None, None
+
+
+class ConvFFSubLayer(torch.autograd.Function):
+    """y = mask(gamma * LN(dropout(conv2(relu(conv1(x)))) + x) + beta);  film = (tensor [B, stride], column offset) or None"""
+
+    @staticmethod
+    def forward(ctx, x, lens, w1, b1, w2, b2, ln_w, ln_b, film, p_drop):
+        x = _check_input(x)
+        B, S, D = x.shape
+        w1p, w1d = packed(w1)
+        w2p, w2d = packed(w2)
+        C = w1.shape[0]
+        h = conv_gemm(x, w1p, b1, B, S, relu=True, round_out=True)
+        o = conv_gemm(h, w2p, b2, B, S)
+        seed = next_seed() if p_drop > 0 else 0
+        if film is not None:
+            film = _check_input(film)
+            assert film.shape[1] == 2 * D   # reference model.py:232
+        y, xhat, rstd = ln_fwd(o, x, ln_w, ln_b, film, 2 * D, lens, B, S, D, p_in=p_drop, seed_in=seed)
+        ctx.save_for_backward(x, lens, h, xhat, rstd, ln_w, ln_b, film, w1d, w2d)
+        ctx.cfg = (B, S, D, C, float(p_drop), seed, w1.shape, w2.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, lens, h, xhat, rstd, ln_w, ln_b, film, w1d, w2d = ctx.saved_tensors
+        B, S, D, C, p, seed, w1_shape, w2_shape = ctx.cfg
+        dy = _check_input(dy)
+        dv, do, dln_w, dln_b, dfilm = ln_bwd(dy, xhat, rstd, ln_w, ln_b, film, 2 * D, lens, B, S, D, p_in=p, seed_in=seed,
+                                             want_film=film is not None)
+        dh = conv_gemm(do, w2d, None, B, S, relu_src=h, round_out=True)
+        dw2, db2 = conv_wgrad(h, do, B, S, C, D, w2_shape[2], w2_shape)
+        dx = conv_gemm(dh, w1d, None, B, S, add_src=dv)
+        dw1, db1 = conv_wgrad(x, dh, B, S, D, C, w1_shape[2], w1_shape)
+        return dx, None, dw1, db1, dw2, db2, dln_w, dln_b, dfilm, None
+
+
+class PreNet(torch.autograd.Function):
+    """3 x (Conv1d k3 -> ReLU -> LayerNorm -> Dropout) on the reference mel-spec [B, M, T] -> [B, T, D]"""
+
+    @staticmethod
+    def forward(ctx, mel, w0, b0, g0, e0, w1, b1, g1, e1, w2, b2, g2, e2, p_drop):
+        mel = _check_input(mel)
+        B, M, T = mel.shape
+        full = torch.full((B,), T, device=mel.device, dtype=torch.int64)
+        x = torch.empty(B, T, M, device=mel.device, dtype=torch.float32)
+        _call('dx_mask_transpose_bwd', _p(mel), _p(full), _p(x), B, T, M, _st())   # plain [B,M,T] -> [B,T,M]
+        saved, cur = [x], x
+        seeds = []
+        for w, b, g, e in ((w0, b0, g0, e0), (w1, b1, g1, e1), (w2, b2, g2, e2)):
+            wp, wd = packed(w)
+            a = conv_gemm(cur, wp, b, B, T, relu=True)
+            seed = next_seed() if p_drop > 0 else 0
+            y, xhat, rstd = ln_fwd(a, None, g, e, None, 0, None, B, T, w.shape[0], p_out=p_drop, seed_out=seed)
+            saved += [a, xhat, rstd, g, e, wd]
+            seeds.append(seed)
+            cur = y
+            saved.append(y)
+        ctx.save_for_backward(*saved)
+        ctx.cfg = (B, T, M, float(p_drop), seeds, (w0.shape, w1.shape, w2.shape))
+        return cur
+
+    @staticmethod
+    def backward(ctx, dy):
+        saved = ctx.saved_tensors
+        B, T, M, p, seeds, shapes = ctx.cfg
+        x = saved[0]
+        layers = [saved[1 + 7 * i: 8 + 7 * i] for i in range(3)]   # a, xhat, rstd, g, e, wd, y
+        grads = [None] * 12
+        d = _check_input(dy)
+        for i in (2, 1, 0):
+            a, xhat, rstd, g, e, wd, _y = layers[i]
+            cout, cin, kw = shapes[i]
+            inp = x if i == 0 else layers[i - 1][6]
+            dpre, _, dg, de, _ = ln_bwd(d, xhat, rstd, g, e, None, 0, None, B, T, cout, relu_src=a, p_out=p, seed_out=seeds[i])
+            dw, db = conv_wgrad(inp, dpre, B, T, cin, cout, kw, shapes[i])
+            grads[4 * i: 4 * i + 4] = [dw, db, dg, de]
+            if i > 0:
+                d = conv_gemm(dpre, wd, None, B, T)
+        return (None, *grads, None)
+
+
+class FrameInput(torch.autograd.Function):
+    """y = mask * (x + PE [+ conv3(energy) + conv3(pitch)])"""
+
+    @staticmethod
+    def forward(ctx, x, lens, pe, energy, pitch, we, be, wp, bp):
+        x = _check_input(x)
+        B, T, D = x.shape
+        y = torch.empty_like(x)
+        has = energy is not None
+        if has:
+            energy, pitch = _check_input(energy), _check_input(pitch)
+        _call('dx_frame_input_fwd', _p(x), _p(energy), _p(pitch), _p(we), _p(be), _p(wp), _p(bp), _p(pe), _p(lens), _p(y),
+              B, T, D, _st())
+        ctx.save_for_backward(lens, energy, pitch)
+        ctx.cfg = (B, T, D, has)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lens, energy, pitch = ctx.saved_tensors
+        B, T, D, has = ctx.cfg
+        dy = _check_input(dy)
+        dx = torch.empty_like(dy)
+        dwe = dbe = dwp = dbp = None
+        if has:
+            dwe = torch.empty(D, 1, 3, device=dy.device, dtype=torch.float32)
+            dwp = torch.empty(D, 1, 3, device=dy.device, dtype=torch.float32)
+            dbe = torch.empty(D, device=dy.device, dtype=torch.float32)
+            dbp = torch.empty(D, device=dy.device, dtype=torch.float32)
+        _call('dx_frame_input_bwd', _p(dy), _p(energy), _p(pitch), _p(lens), _p(dx), _p(dwe), _p(dbe), _p(dwp), _p(dbp),
+              B, T, D, _st())
+        return dx, None, None, None, None, dwe, dbe, dwp, dbp
+
+
+class MeanPoolSpeaker(torch.autograd.Function):
+    """pooled = sum_t x / len ;  h = pooled + spk_embedding[ids]   -> (pooled, h)"""
+
+    @staticmethod
+    def forward(ctx, x, lens, spk_ids, spk_emb):
+        x = _check_input(x)
+        B, S, D = x.shape
+        pooled = torch.empty(B, D, device=x.device, dtype=torch.float32)
+        h = torch.empty(B, D, device=x.device, dtype=torch.float32)
+        _call('dx_meanpool_fwd', _p(x), _p(lens), _p(pooled), B, S, D, _st())
+        _call('dx_add_speaker_fwd', _p(pooled), _p(spk_ids), _p(spk_emb), _p(h), B, D, spk_emb.shape[0], _st())
+        ctx.save_for_backward(lens, spk_ids)
+        ctx.cfg = (B, S, D, spk_emb.shape[0])
+        return pooled, h
+
+    @staticmethod
+    def backward(ctx, dpooled, dh):
+        lens, spk_ids = ctx.saved_tensors
+        B, S, D, n_spk = ctx.cfg
+        dh = _check_input(dh)
+        demb = torch.empty(n_spk, D, device=dh.device, dtype=torch.float32)
+        _call('dx_add_speaker_bwd', _p(dh), _p(spk_ids), _p(demb), B, D, n_spk, _st())
+        tot = (dh + dpooled).contiguous()   # [B, D] host-side plumbing: both consumers of `pooled` feed one gradient
+        dx = torch.empty(B, S, D, device=dh.device, dtype=torch.float32)
+        _call('dx_meanpool_bwd', _p(tot), _p(lens), _p(dx), B, S, D, _st())
+        return dx, None, None, demb
+
+
+class FilmHead(torch.autograd.Function):
+    """gammas/betas = Linear(h); split per module/block, scalar post-multipliers, gamma in the delta regime.
+    Returns one contiguous [B, 2*ch] tensor per FiLM-ed block (module order: encoder blocks, predictor, decoder blocks)."""
+
+    @staticmethod
+    def forward(ctx, h, gw, gb, bw, bb, post, nb_blocks, channels):
+        h = _check_input(h)
+        B = h.shape[0]
+        gwp, gwd = packed(gw)
+        bwp, bwd = packed(bw)
+        graw = linear_rows(h, gwp, gb)
+        braw = linear_rows(h, bwp, bb)
+        NF = graw.shape[1]
+        film = torch.empty(B, 2 * NF, device=h.device, dtype=torch.float32)
+        nb_arr = (ctypes.c_int * len(nb_blocks))(*nb_blocks)
+        ch_arr = (ctypes.c_int * len(channels))(*channels)
+        _call('dx_film_assemble_fwd', _p(graw), _p(braw), _p(post), _p(film), B, len(nb_blocks), ctypes.addressof(nb_arr),
+              ctypes.addressof(ch_arr), _st())
+        outs, col = [], 0
+        for nb, ch in zip(nb_blocks, channels):
+            for _ in range(nb):
+                outs.append(film[:, col: col + 2 * ch].contiguous())
+                col += 2 * ch
+        ctx.save_for_backward(h, graw, braw, post, gwd, bwd)
+        ctx.cfg = (B, NF, tuple(nb_blocks), tuple(channels), gw.shape, bw.shape)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        h, graw, braw, post, gwd, bwd = ctx.saved_tensors
+        B, NF, nb_blocks, channels, gshape, bshape = ctx.cfg
+        parts, k = [], 0
+        for nb, ch in zip(nb_blocks, channels):
+            for _ in range(nb):
+                d = douts[k]
+                parts.append(d if d is not None else torch.zeros(B, 2 * ch, device=h.device, dtype=torch.float32))
+                k += 1
+        dfilm = torch.cat(parts, dim=1).contiguous()
+        dgraw = torch.empty_like(graw)
+        dbraw = torch.empty_like(braw)
+        dpost = torch.empty_like(post) if post is not None else None
+        nb_arr = (ctypes.c_int * len(nb_blocks))(*nb_blocks)
+        ch_arr = (ctypes.c_int * len(channels))(*channels)
+        _call('dx_film_assemble_bwd', _p(dfilm), _p(graw), _p(braw), _p(post), _p(dgraw), _p(dbraw), _p(dpost), B,
+              len(nb_blocks), ctypes.addressof(nb_arr), ctypes.addressof(ch_arr), _st())
+        D = h.shape[1]
+        dh1 = linear_rows(dgraw, gwd, None)
+        dh = linear_rows(dbraw, bwd, None, add_src=dh1)
+        dgw, dgb = conv_wgrad(h, dgraw, 1, B, D, NF, 1, gshape)
+        dbw, dbb = conv_wgrad(h, dbraw, 1, B, D, NF, 1, bshape)
+        return dh, dgw, dgb, dbw, dbb, dpost, None, None
+
+
+class Linear(torch.autograd.Function):
+    """y = relu?(x W^T + b); the input gradient is multiplied by `grad_in_scale` (gradient reversal: -lambda)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, relu, grad_in_scale):
+        x = _check_input(x)
+        wp, wd = packed(w)
+        y = linear_rows(x, wp, b, relu=relu)
+        ctx.save_for_backward(x, y if relu else None, wd)
+        ctx.cfg = (relu, float(grad_in_scale), w.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, wd = ctx.saved_tensors
+        relu, scale, wshape = ctx.cfg
+        dy = _check_input(dy)
+        R, cout, cin = x.shape[0], wshape[0], wshape[1]
+        if relu:
+            dpre = torch.empty_like(dy)
+            _call('dx_relu_bwd', _p(dy), _p(y), _p(dpre), dy.numel(), _st())
+            dy = dpre
+        dx = linear_rows(dy, wd, None, alpha=scale)
+        dw, db = conv_wgrad(x, dy, 1, R, cin, cout, 1, wshape)
+        return dx, dw, db, None, None
+
+
+class EmbedPE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, symbols, lens, emb, pe):
+        B, L = symbols.shape
+        D = emb.shape[1]
+        y = torch.empty(B, L, D, device=emb.device, dtype=torch.float32)
+        symbols = _check_input(symbols, torch.int64)
+        _call('dx_embed_pe_fwd', _p(symbols), _p(lens), _p(emb), _p(pe), _p(y), B, L, D, emb.shape[0], _st())
+        ctx.save_for_backward(symbols, lens)
+        ctx.cfg = (B, L, D, emb.shape[0])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        symbols, lens = ctx.saved_tensors
+        B, L, D, n = ctx.cfg
+        dy = _check_input(dy)
+        demb = torch.empty(n, D, device=dy.device, dtype=torch.float32)
+        _call('dx_embed_pe_bwd', _p(symbols), _p(lens), _p(dy), _p(demb), B, L, D, n, _st())
+        return None, None, demb, None
+
+
+class Predictor(torch.autograd.Function):
+    """conv(128->256,k3)+ReLU -> LN -> drop -> conv(256->256,k3)+ReLU -> LN -> drop -> FiLM -> mask -> Linear(256->3) -> mask.
+    Returns preds [3, B, L] (duration, energy, pitch planes)."""
+
+    @staticmethod
+    def forward(ctx, x, lens, film, w0, b0, g0, e0, w1, b1, g1, e1, pw, pb, p_drop):
+        x = _check_input(x)
+        B, L, D = x.shape
+        C = w0.shape[0]
+        w0p, w0d = packed(w0)
+        w1p, w1d = packed(w1)
+        film = _check_input(film)
+        assert film.shape[1] == 2 * C   # reference model.py:561
+        s0, s1 = (next_seed(), next_seed()) if p_drop > 0 else (0, 0)
+        a0 = conv_gemm(x, w0p, b0, B, L, relu=True)
+        y0, xh0, rs0 = ln_fwd(a0, None, g0, e0, None, 0, None, B, L, C, p_out=p_drop, seed_out=s0)
+        a1 = conv_gemm(y0, w1p, b1, B, L, relu=True)
+        y1, xh1, rs1 = ln_fwd(a1, None, g1, e1, film, 2 * C, lens, B, L, C, p_out=p_drop, seed_out=s1)
+        NO = pw.shape[0]
+        out = torch.empty(NO, B, L, device=x.device, dtype=torch.float32)
+        _call('dx_narrow_linear_fwd', _p(y1), _p(pw), _p(pb), _p(lens), _p(out), B, L, C, NO, _st())
+        ctx.save_for_backward(x, lens, film, a0, y0, xh0, rs0, a1, y1, xh1, rs1, g0, e0, g1, e1, pw, w0d, w1d)
+        ctx.cfg = (B, L, D, C, NO, float(p_drop), s0, s1, w0.shape, w1.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, lens, film, a0, y0, xh0, rs0, a1, y1, xh1, rs1, g0, e0, g1, e1, pw, w0d, w1d = ctx.saved_tensors
+        B, L, D, C, NO, p, s0, s1, w0s, w1s = ctx.cfg
+        dout = _check_input(dout)
+        dy1 = torch.empty(B, L, C, device=dout.device, dtype=torch.float32)
+        dpw = torch.empty(NO, C, device=dout.device, dtype=torch.float32)
+        dpb = torch.empty(NO, device=dout.device, dtype=torch.float32)
+        _call('dx_narrow_linear_bwd', _p(dout), _p(y1), _p(pw), _p(lens), _p(dy1), _p(dpw), _p(dpb), B, L, C, NO, _st())
+        dpre1, _, dg1, de1, dfilm = ln_bwd(dy1, xh1, rs1, g1, e1, film, 2 * C, lens, B, L, C, relu_src=a1, p_out=p,
+                                           seed_out=s1, want_film=True)
+        dy0 = conv_gemm(dpre1, w1d, None, B, L)
+        dw1, db1 = conv_wgrad(y0, dpre1, B, L, C, C, w1s[2], w1s)
+        dpre0, _, dg0, de0, _ = ln_bwd(dy0, xh0, rs0, g0, e0, None, 0, None, B, L, C, relu_src=a0, p_out=p, seed_out=s0)
+        dx = conv_gemm(dpre0, w0d, None, B, L)
+        dw0, db0 = conv_wgrad(x, dpre0, B, L, D, C, w0s[2], w0s)
+        return dx, None, dfilm, dw0, db0, dg0, de0, dw1, db1, dg1, de1, dpw, dpb, None
+
+
+class GaussUpsample(torch.autograd.Function):
+    """-> (x_upsamp [B,T,D], weights [B,L,T], csum [B,L] int64, totals [B] int64)"""
+
+    @staticmethod
+    def forward(ctx, x, dur_f, dur_i, energy, pitch, lens, wd, bd, we, be, wp, bp, rw, rb, T):
+        ctx.set_materialize_grads(False)
+        x = _check_input(x)
+        B, L, D = x.shape
+        dev = x.device
+        dur_f, energy, pitch = _check_input(dur_f), _check_input(energy), _check_input(pitch)
+        dur_i = _check_input(dur_i, torch.int64)
+        xp = torch.empty(B, L, D, device=dev, dtype=torch.float32)
+        z = torch.empty(B, L, device=dev, dtype=torch.float32)
+        sigma = torch.empty(B, L, device=dev, dtype=torch.float32)
+        mu = torch.empty(B, L, device=dev, dtype=torch.float32)
+        csum = torch.empty(B, L, device=dev, dtype=torch.int64)
+        total = torch.empty(B, device=dev, dtype=torch.int64)
+        _call('dx_gauss_prep', _p(x), _p(dur_f), _p(dur_i), _p(energy), _p(pitch), _p(lens), _p(wd), _p(bd), _p(we), _p(be),
+              _p(wp), _p(bp), _p(rw), _p(rb), _p(xp), _p(z), _p(sigma), _p(mu), _p(csum), _p(total), B, L, D, _st())
+        if T is None:   # inference: T_max = max(sum(durations_int)) needs one read-back (the reference syncs here too)
+            T = int(total.max().item())
+        up = torch.empty(B, T, D, device=dev, dtype=torch.float32)
+        weights = torch.empty(B, L, T, device=dev, dtype=torch.float32)
+        _call('dx_gauss_upsample_fwd', _p(xp), _p(mu), _p(sigma), _p(lens), _p(up), _p(weights), B, L, T, D, _st())
+        ctx.save_for_backward(up, weights, xp, z, mu, sigma, dur_f, energy, pitch, lens, wd, bd, rw)
+        ctx.cfg = (B, L, T, D)
+        ctx.mark_non_differentiable(csum, total)
+        return up, weights, csum, total
+
+    @staticmethod
+    def backward(ctx, dup, dweights, _dc, _dt):
+        up, weights, xp, z, mu, sigma, dur_f, energy, pitch, lens, wd, bd, rw = ctx.saved_tensors
+        B, L, T, D = ctx.cfg
+        dev = up.device
+        dup = _check_input(dup) if dup is not None else torch.zeros_like(up)
+        dweights = _check_input(dweights) if dweights is not None else None
+        dx = torch.empty(B, L, D, device=dev, dtype=torch.float32)
+        g = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        dwd, dwe, dwp = g(D, 1, 3), g(D, 1, 3), g(D, 1, 3)
+        dbd, dbe, dbp = g(D), g(D), g(D)
+        drw, drb = g(1, D), g(1)
+        scratch = g(B * L + 2 * B * T)
+        _call('dx_gauss_upsample_bwd', _p(dup), _p(dweights), _p(up), _p(weights), _p(xp), _p(z), _p(mu), _p(sigma),
+              _p(dur_f), _p(energy), _p(pitch), _p(lens), _p(wd), _p(bd), _p(rw), _p(dx), _p(dwd), _p(dbd), _p(dwe), _p(dbe),
+              _p(dwp), _p(dbp), _p(drw), _p(drb), _p(scratch), B, L, T, D, _st())
+        return dx, None, None, None, None, None, dwd, dbd, dwe, dbe, dwp, dbp, drw, drb, None
+
+
+class MelProjection(torch.autograd.Function):
+    """mel [B, M, T] = transpose(mask * (x W^T + b))"""
+
+    @staticmethod
+    def forward(ctx, x, lens, w, b):
+        x = _check_input(x)
+        B, T, D = x.shape
+        M = w.shape[0]
+        wp, wd = packed(w)
+        y = conv_gemm(x, wp, b, 1, B * T)
+        mel = torch.empty(B, M, T, device=x.device, dtype=torch.float32)
+        _call('dx_mask_transpose_fwd', _p(y), _p(lens), _p(mel), B, T, M, _st())
+        ctx.save_for_backward(x, lens, wd)
+        ctx.cfg = (B, T, D, M, w.shape)
+        return mel
+
+    @staticmethod
+    def backward(ctx, dmel):
+        x, lens, wd = ctx.saved_tensors
+        B, T, D, M, wshape = ctx.cfg
+        dmel = _check_input(dmel)
+        dy = torch.empty(B, T, M, device=dmel.device, dtype=torch.float32)
+        _call('dx_mask_transpose_bwd', _p(dmel), _p(lens), _p(dy), B, T, M, _st())
+        dx = conv_gemm(dy, wd, None, 1, B * T).view(B, T, D)
+        dw, db = conv_wgrad(x, dy, 1, B * T, D, M, 1, wshape)
+        return dx, None, dw, db
+
+
+class Loss(torch.autograd.Function):
+    """-> out[8] = {speaker, post_mult, duration, energy, pitch, mel_l1, mel_l2, total}; only out[7] is differentiable."""
+
+    @staticmethod
+    def forward(ctx, spk_logits, post, dur_p, energy_p, pitch_p, mel_p, spk_ids, dur_t, energy_t, pitch_t, mel_t, in_lens,
+                out_lens, weights):
+        spk_logits, dur_p, energy_p, pitch_p, mel_p = (_check_input(t) for t in (spk_logits, dur_p, energy_p, pitch_p, mel_p))
+        dur_t, energy_t, pitch_t, mel_t = (_check_input(t) for t in (dur_t, energy_t, pitch_t, mel_t))
+        post_c = _check_input(post) if post is not None else None
+        B, NS = spk_logits.shape
+        L = dur_p.shape[1]
+        M, T = mel_p.shape[1], mel_p.shape[2]
+        NP = post_c.numel() if post_c is not None else 0
+        acc = torch.empty(B, 8, device=mel_p.device, dtype=torch.float32)
+        out = torch.empty(8, device=mel_p.device, dtype=torch.float32)
+        w = tuple(float(v) for v in weights)
+        _call('dx_loss_fwd', _p(spk_logits), _p(spk_ids), _p(post_c), _p(dur_p), _p(energy_p), _p(pitch_p), _p(dur_t),
+              _p(energy_t), _p(pitch_t), _p(mel_p), _p(mel_t), _p(in_lens), _p(out_lens), B, L, T, M, NS, NP, *w, _p(acc),
+              _p(out), _st())
+        ctx.save_for_backward(spk_logits, spk_ids, post_c, dur_p, energy_p, pitch_p, dur_t, energy_t, pitch_t, mel_p, mel_t,
+                              in_lens, out_lens)
+        ctx.cfg = (B, L, T, M, NS, NP, w, post.shape if post is not None else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (spk_logits, spk_ids, post, dur_p, energy_p, pitch_p, dur_t, energy_t, pitch_t, mel_p, mel_t, in_lens,
+         out_lens) = ctx.saved_tensors
+        B, L, T, M, NS, NP, w, post_shape = ctx.cfg
+        dev = mel_p.device
+        gout = _check_input(dout)[7:8].contiguous()   # d(total); the 7 individual terms are reporting-only (loss.py:102-104)
+        g = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        dlog, ddur, den, dpi, dmel = g(B, NS), g(B, L), g(B, L), g(B, L), g(B, M, T)
+        dpost = g(*post_shape) if post is not None else None
+        _call('dx_loss_bwd', _p(gout), _p(spk_logits), _p(spk_ids), _p(post), _p(dur_p), _p(energy_p), _p(pitch_p), _p(dur_t),
+              _p(energy_t), _p(pitch_t), _p(mel_p), _p(mel_t), _p(in_lens), _p(out_lens), B, L, T, M, NS, NP, *w, _p(dlog),
+              _p(dpost), _p(ddur), _p(den), _p(dpi), _p(dmel), _st())
+        return dlog, dpost, ddur, den, dpi, dmel, None, None, None, None, None, None, None, None
