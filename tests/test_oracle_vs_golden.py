@@ -50,7 +50,7 @@ def test_forward_loss_grads_match_reference_golden(case):
         assert g is not None, n
         ref_norm = float(fx['grad_norms'][i])
         assert abs(g.double().norm().item() - ref_norm) <= 1e-4 * max(ref_norm, 1e-8), n
-        assert abs(grad_projection(n, g) - float(fx['grad_projs'][i])) <= 2e-4 * max(ref_norm * np.sqrt(g.numel()), 1e-8), n
+        assert abs(grad_projection(n, g) - float(fx['grad_projs'][i])) <= 2e-4 * max(4 * ref_norm, 1e-8), n
         if 'grad:' + n in fx.files:
             assert scale_rel_err(g, fx['grad:' + n]) < 5e-4, n   # fp32 reduction-order noise over B*T rows
 

@@ -1,0 +1,370 @@
+"""GPU parity tests (-m gpu): the CUDA path (through the C-ABI) against the oracle and the committed golden fixtures.
+
+Tolerances (north_star: "mel/loss outputs match the reference within 1e-3 relative fp32"; integers bit-exact):
+  * fp32 backend (CUDA-core GEMMs, exact fp32 math):  scale-relative error  max|a-b| / max|b|  <= 1e-4  on dense outputs,
+    loss terms relative 1e-4, gradients 1e-3 (fp32 reduction-order noise over B*T rows);
+  * tf32 backend (tcgen05 tensor cores, tf32 multiply + fp32 accumulate): dense outputs <= 1e-3 relative-L2 and 3e-3
+    scale-relative, loss 1e-3, gradients 2e-2 relative-L2 — the measured values are printed by the tests.
+  * integer outputs (prefix sums, output lengths, T_max, get_int_durations): torch.equal.
+"""
+import numpy as np
+import pytest
+import torch
+
+import daft_exprt_oracle as oracle
+from daft_exprt_b200 import synthetic
+from helpers import (GOLDEN_CASES, GOLDEN_DIR, case_inference_inputs, case_inputs, fake_stats, grad_projection, l2_rel_err,
+                     load_golden, scale_rel_err, targets_of)
+
+pytestmark = pytest.mark.gpu
+
+BACKENDS = ('fp32', 'tf32')
+TOL = {  # (dense scale-rel, dense l2-rel, loss rel, grad l2-rel)
+    'fp32': (1e-4, 1e-4, 1e-4, 1e-3),
+    'tf32': (3e-3, 1e-3, 1e-3, 2e-2),
+}
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'the gpu tests need a CUDA device'
+    from daft_exprt_b200 import cabi
+    cabi.check(cabi.load().dx_device_check(), 'dx_device_check')
+    return torch.device('cuda', 0)
+
+
+def build_model(n_ids, dev, nudge=False, train=False):
+    from daft_exprt_b200.hparams import default_hparams
+    from daft_exprt_b200.model import DaftExprt
+    hp = default_hparams(n_speakers=n_ids + 1, stats=fake_stats(n_ids))
+    model = DaftExprt(hp)
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    sd = synthetic.synthetic_state_dict(shapes, 1234)
+    if nudge:
+        sd = synthetic.nudge_for_inference(sd)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    model.train(train)
+    return model, hp, sd
+
+
+def to_dev(inputs, dev):
+    return tuple(t.to(dev) for t in inputs)
+
+
+def set_backend(name):
+    from daft_exprt_b200 import ops
+    ops.set_backend(name)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# unit level: each C-ABI primitive against plain torch fp32/fp64 on the same inputs
+# ----------------------------------------------------------------------------------------------------------------------
+GEMM_SHAPES = [  # B, S, Cin, Cout, KW
+    (3, 37, 128, 1024, 3), (2, 131, 1024, 128, 3), (1, 300, 128, 384, 1), (2, 50, 80, 1024, 3), (1, 257, 128, 80, 1),
+    (1, 33, 128, 11, 1), (1, 33, 11, 128, 1), (2, 40, 256, 256, 3), (1, 6, 128, 1280, 1), (4, 1000, 128, 128, 1),
+]
+
+
+@pytest.mark.parametrize('backend', BACKENDS)
+@pytest.mark.parametrize('shape', GEMM_SHAPES)
+def test_conv_gemm_forward_dgrad_wgrad(dev, backend, shape):
+    from daft_exprt_b200 import ops
+    set_backend(backend)
+    B, S, Cin, Cout, KW = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(B, S, Cin, generator=g)
+    w = torch.randn(Cout, Cin, KW, generator=g) / np.sqrt(Cin * KW)
+    b = torch.randn(Cout, generator=g)
+    dy = torch.randn(B, S, Cout, generator=g)
+    xd, wd_, bd, dyd = x.to(dev), w.to(dev), b.to(dev), dy.to(dev)
+    wp, wdg = ops.packed(wd_)
+    y = ops.conv_gemm(xd, wp, bd, B, S, relu=True)
+    ref = torch.relu(torch.nn.functional.conv1d(x.double().transpose(1, 2), w.double(), b.double(), padding=(KW - 1) // 2)).transpose(1, 2)
+    tol = 2e-5 if backend == 'fp32' else 2e-3
+    assert scale_rel_err(y, ref) < tol, f'forward {shape}'
+    # dgrad with fused ReLU mask and residual add
+    add = torch.randn(B, S, Cin, generator=g)
+    mask_src = torch.randn(B, S, Cin, generator=g)
+    dx = ops.conv_gemm(dyd, wdg, None, B, S, relu_src=mask_src.to(dev), add_src=add.to(dev), alpha=0.5)
+    xr = x.double().clone().requires_grad_(True)
+    yr = torch.nn.functional.conv1d(xr.transpose(1, 2), w.double(), None, padding=(KW - 1) // 2).transpose(1, 2)
+    yr.backward(dy.double())
+    ref_dx = 0.5 * xr.grad * (mask_src > 0).double() + add.double()
+    assert scale_rel_err(dx, ref_dx) < tol, f'dgrad {shape}'
+    # wgrad + bias grad
+    dw, db = ops.conv_wgrad(xd, dyd, B, S, Cin, Cout, KW, (Cout, Cin, KW))
+    wr = w.double().clone().requires_grad_(True)
+    br = b.double().clone().requires_grad_(True)
+    yr = torch.nn.functional.conv1d(x.double().transpose(1, 2), wr, br, padding=(KW - 1) // 2).transpose(1, 2)
+    yr.backward(dy.double())
+    assert scale_rel_err(dw, wr.grad) < tol, f'wgrad {shape}'
+    assert scale_rel_err(db, br.grad) < 2e-5, f'bias grad {shape}'
+
+
+@pytest.mark.parametrize('cfg', [(3, 70, 2, 64), (2, 150, 8, 16), (4, 64, 2, 64), (1, 257, 8, 16), (2, 40, 4, 32)])
+def test_attention_forward_backward(dev, cfg):
+    from daft_exprt_b200 import ops
+    B, S, H, dh = cfg
+    D = H * dh
+    g = torch.Generator().manual_seed(B * S + H)
+    qkv = torch.randn(B, S, 3 * D, generator=g)
+    lens = torch.randint(max(1, S // 3), S + 1, (B,), generator=g)
+    lens[0] = S
+    dctx = torch.randn(B, S, D, generator=g)
+    valid = oracle.valid_mask(lens, S)
+    dctx = dctx * valid[:, :, None]
+    # reference in fp64
+    q64 = qkv.double().clone().requires_grad_(True)
+    q, k, v = q64.split(D, dim=2)
+    hd = lambda t: t.reshape(B, S, H, dh).permute(0, 2, 1, 3)
+    sc = (hd(q) / np.sqrt(dh)) @ hd(k).transpose(-1, -2)
+    sc = sc.masked_fill(~valid[:, None, None, :], float('-inf'))
+    ctx_ref = (torch.softmax(sc, -1) @ hd(v)).permute(0, 2, 1, 3).reshape(B, S, D) * valid[:, :, None]
+    ctx_ref.backward(dctx.double())
+    qd, ld = qkv.to(dev), lens.to(dev)
+    ctx = torch.empty(B, S, D, device=dev)
+    lse = torch.empty(B, H, S, device=dev)
+    ops._call('dx_attention_fwd', qd.data_ptr(), ld.data_ptr(), ctx.data_ptr(), lse.data_ptr(), B, S, H, dh, 0.0, 0, ops._st())
+    assert scale_rel_err(ctx, ctx_ref.detach()) < 2e-5
+    dqkv = torch.empty(B, S, 3 * D, device=dev)
+    delta = torch.empty(B, H, S, device=dev)
+    ops._call('dx_attention_bwd', qd.data_ptr(), ld.data_ptr(), ctx.data_ptr(), lse.data_ptr(), dctx.to(dev).data_ptr(),
+              dqkv.data_ptr(), delta.data_ptr(), B, S, H, dh, 0.0, 0, ops._st())
+    ref_g = q64.grad * 1.0
+    # gradients wrt padded rows of q/k/v are exactly zero in both
+    assert scale_rel_err(dqkv, ref_g) < 5e-5
+
+
+@pytest.mark.parametrize('D', [128, 256, 1024])
+def test_layernorm_film_mask_forward_backward(dev, D):
+    from daft_exprt_b200 import ops
+    B, S = 3, 45
+    g = torch.Generator().manual_seed(D)
+    a, res = torch.randn(B, S, D, generator=g), torch.randn(B, S, D, generator=g)
+    w, b = 1 + 0.1 * torch.randn(D, generator=g), 0.1 * torch.randn(D, generator=g)
+    film = torch.randn(B, 2 * D, generator=g)
+    lens = torch.tensor([S, S // 2, 7])
+    dy = torch.randn(B, S, D, generator=g)
+    t64 = [t.double().clone().requires_grad_(True) for t in (a, res, w, b, film)]
+    keep = oracle.valid_mask(lens, S)[:, :, None].double()
+    yref = torch.nn.functional.layer_norm(t64[0] + t64[1], (D,), t64[2], t64[3])
+    yref = (t64[4][:, None, :D] * yref + t64[4][:, None, D:]) * keep
+    yref.backward(dy.double())
+    ad, rd, wd_, bd, fd, ld, dyd = (t.to(dev) for t in (a, res, w, b, film, lens, dy))
+    y, xhat, rstd = ops.ln_fwd(ad, rd, wd_, bd, fd, 2 * D, ld, B, S, D)
+    assert scale_rel_err(y, yref.detach()) < 2e-5
+    dv, da, dw, db, dfilm = ops.ln_bwd(dyd, xhat, rstd, wd_, bd, fd, 2 * D, ld, B, S, D, want_film=True)
+    assert scale_rel_err(dv, t64[0].grad) < 5e-5
+    assert scale_rel_err(dw, t64[2].grad) < 5e-5
+    assert scale_rel_err(db, t64[3].grad) < 5e-5
+    assert scale_rel_err(dfilm, t64[4].grad) < 5e-5
+
+
+def test_gaussian_upsampling_integer_contract_and_values(dev):
+    """prefix sums / totals / T_max bit-exact; upsampled values and alignments vs the oracle; gradients vs oracle autograd."""
+    from daft_exprt_b200.hparams import default_hparams
+    from daft_exprt_b200.model import GaussianUpsamplingModule
+    hp = default_hparams(12)
+    inputs = synthetic.make_batch(5, 61, 333, 11, seed=3)
+    symbols, dur_f, dur_i, en, pi, in_len = inputs[:6]
+    mod = GaussianUpsamplingModule(hp)
+    shapes = {'gaussian_upsampling.' + k: tuple(v.shape) for k, v in mod.state_dict().items()}
+    sd = synthetic.synthetic_state_dict(shapes, 7)
+    mod.load_state_dict({k[len('gaussian_upsampling.'):]: v for k, v in sd.items()})
+    mod = mod.to(dev)
+    x = torch.randn(5, 61, 128, generator=torch.Generator().manual_seed(1)) * oracle.valid_mask(in_len, 61)[:, :, None]
+    xd = x.to(dev).requires_grad_(True)
+    from daft_exprt_b200 import ops
+    r = mod.projection[0].linear_layer
+    d, e, f = mod.duration_projection.conv, mod.energy_projection.conv, mod.pitch_projection.conv
+    up, w, csum, totals = ops.GaussUpsample.apply(xd, dur_f.to(dev), dur_i.to(dev), en.to(dev), pi.to(dev), in_len.to(dev),
+                                                  d.weight, d.bias, e.weight, e.bias, f.weight, f.bias, r.weight, r.bias, None)
+    assert torch.equal(csum.cpu(), torch.cumsum(dur_i, dim=1))            # bit-exact int64 prefix sum (model.py:642)
+    assert torch.equal(totals.cpu(), dur_i.sum(dim=1))                    # output_lengths (model.py:912)
+    assert up.shape[1] == int(torch.cumsum(dur_i, dim=1).max())           # T_max (model.py:649)
+    sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    x64 = x.double().requires_grad_(True)
+    up_ref, w_ref = oracle.gaussian_upsampling(sd64, x64, dur_f.double(), dur_i, en.double(), pi.double(), in_len)
+    assert scale_rel_err(up, up_ref.detach()) < 2e-5
+    assert scale_rel_err(w, w_ref.detach()) < 2e-5
+    gup = torch.randn(up_ref.shape, generator=torch.Generator().manual_seed(2))
+    up_ref.backward(gup.double())
+    up.backward(gup.to(dev))
+    assert scale_rel_err(xd.grad, x64.grad) < 1e-4
+    for name, prm in (('duration_projection.conv.weight', d.weight), ('duration_projection.conv.bias', d.bias),
+                      ('energy_projection.conv.weight', e.weight), ('pitch_projection.conv.bias', f.bias),
+                      ('projection.0.linear_layer.weight', r.weight), ('projection.0.linear_layer.bias', r.bias)):
+        assert scale_rel_err(prm.grad, sd64['gaussian_upsampling.' + name].grad) < 2e-4, name
+
+
+def test_int_durations_bit_exact_known_answers(dev):
+    """get_int_durations / duration_to_integer (model.py:789-812, extract_features.py:69-111): KAT from the reference."""
+    from daft_exprt_b200.hparams import default_hparams
+    from daft_exprt_b200.model import DaftExprt
+    kat = np.load(f'{GOLDEN_DIR}/int_durations_kat.npz')
+    hp = default_hparams(2)
+    model = DaftExprt.__new__(DaftExprt)
+    torch.nn.Module.__init__(model)
+    d = torch.from_numpy(kat['durations']).to(dev)
+    out, dint = DaftExprt.get_int_durations(model, d, hp)
+    assert torch.equal(dint.cpu(), torch.from_numpy(kat['durations_int']))
+    totals, err = model._last_int_dur_status
+    assert int(err.max()) == 0
+    assert torch.equal(totals.cpu(), torch.from_numpy(kat['durations_int']).sum(1))
+    # random stress against the oracle's Python restatement (which is pinned on the same KAT)
+    rng = np.random.RandomState(5)
+    rows = (rng.rand(48, 90) * 0.2).astype(np.float32)
+    rows[rng.rand(48, 90) < 0.2] = 0.
+    _, ref = oracle.get_int_durations(torch.from_numpy(rows), oracle.OracleHParams())
+    _, got = DaftExprt.get_int_durations(model, torch.from_numpy(rows).to(dev), hp)
+    assert torch.equal(got.cpu(), ref)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# model level: DaftExprt + DaftExprtLoss against the reference's golden vectors and the oracle
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('backend', BACKENDS)
+@pytest.mark.parametrize('case', GOLDEN_CASES)
+def test_forward_loss_backward_match_reference_golden(dev, case, backend):
+    from daft_exprt_b200.loss import DaftExprtLoss
+    set_backend(backend)
+    t_dense, t_l2, t_loss, t_grad = TOL[backend]
+    fx = load_golden(case)
+    inputs, n_ids = case_inputs(fx)
+    model, hp, _ = build_model(n_ids, dev)
+    crit = DaftExprtLoss(0, hp)
+    din = to_dev(inputs, dev)
+    out = model(din)
+    spk, film, enc, dec, align = out
+    assert torch.equal(dec[1].cpu(), torch.from_numpy(fx['output_lengths']))
+    assert tuple(align.shape) == fx['alignments'].shape
+    report = {}
+    for name, got in (('speaker_preds', spk), ('encoder_film', film[1]), ('prosody_pred_film', film[2]), ('decoder_film', film[3]),
+                      ('duration_preds', enc[0]), ('energy_preds', enc[1]), ('pitch_preds', enc[2]), ('mel_spec_preds', dec[0])):
+        report[name] = (scale_rel_err(got.detach(), fx[name]), l2_rel_err(got.detach(), fx[name]))
+    print(f'[{backend}/{case}] (scale-rel, l2-rel):', {k: (f'{a:.1e}', f'{b:.1e}') for k, (a, b) in report.items()})
+    for name, (a, b) in report.items():
+        assert a < t_dense and b < t_l2, (name, a, b)
+    assert scale_rel_err(align.detach(), fx['alignments'].astype(np.float32)) < 2e-3   # fixture stored in fp16
+    total, terms = crit(out, targets_of(din), int(fx['meta_iteration']))
+    assert abs(total.item() - float(fx['loss_total'])) <= t_loss * abs(float(fx['loss_total']))
+    for k, v in terms.items():
+        ref = float(fx['loss_' + k])
+        assert abs(v - ref) <= t_loss * max(abs(ref), 1e-6), (k, v, ref)
+    total.backward()
+    names = [str(n) for n in fx['grad_names']]
+    params = dict(model.named_parameters())
+    worst = []
+    for i, n in enumerate(names):
+        g = params[n].grad
+        assert g is not None, f'no gradient for {n} (DDP needs every parameter to receive one, train.py:293)'
+        ref_norm = float(fx['grad_norms'][i])
+        e_norm = abs(g.double().norm().item() - ref_norm) / max(ref_norm, 1e-12)
+        e_proj = abs(grad_projection(n, g) - float(fx['grad_projs'][i])) / max(4 * ref_norm, 1e-12)   # N(0,1) probe: std = |g - ref|
+        e_full = scale_rel_err(g, fx['grad:' + n]) if 'grad:' + n in fx.files else 0.0
+        worst.append((max(e_norm, e_proj, e_full), n, e_norm, e_proj, e_full))
+    worst.sort(reverse=True)
+    print(f'[{backend}/{case}] worst gradient errors:', [(n, f'{a:.1e}') for a, n, *_ in worst[:5]])
+    for a, n, e_norm, e_proj, e_full in worst:
+        assert e_norm < t_grad and e_proj < t_grad and e_full < max(t_grad, 2e-3), (n, e_norm, e_proj, e_full)
+
+
+@pytest.mark.parametrize('backend', BACKENDS)
+def test_all_gradients_match_oracle_autograd(dev, backend):
+    """Every one of the 193 gradient tensors, element-wise, against the oracle's autograd on CPU (small ragged batch with
+    zero-duration symbols, 11 speakers)."""
+    from daft_exprt_b200.loss import DaftExprtLoss
+    set_backend(backend)
+    n_ids = 11
+    inputs = synthetic.make_batch(4, 29, 97, n_ids, seed=21)
+    model, hp, sd = build_model(n_ids, dev)
+    crit = DaftExprtLoss(0, hp)
+    din = to_dev(inputs, dev)
+    total, _ = crit(model(din), targets_of(din), 4000)
+    total.backward()
+    sd_o = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ohp = oracle.OracleHParams(n_speakers=n_ids + 1)
+    total_o, _ = oracle.loss(ohp, oracle.forward(sd_o, ohp, inputs), targets_of(inputs), 4000)
+    total_o.backward()
+    tol = 1e-3 if backend == 'fp32' else 3e-2
+    assert abs(total.item() - total_o.item()) < (1e-4 if backend == 'fp32' else 1e-3) * abs(total_o.item())
+    bad = []
+    for n, p in model.named_parameters():
+        e = scale_rel_err(p.grad, sd_o[n].grad)
+        if not e < tol:
+            bad.append((n, e))
+    assert not bad, bad[:10]
+
+
+@pytest.mark.parametrize('case', GOLDEN_CASES)
+@pytest.mark.parametrize('transform', ['add', 'multiply'])
+def test_inference_matches_reference_golden(dev, case, transform):
+    set_backend('fp32')
+    fx = load_golden(case)
+    n_ids = int(fx['meta_n_speaker_ids'])
+    model, hp, _ = build_model(n_ids, dev, nudge=True)
+    with torch.no_grad():
+        enc, dec, w = model.inference(to_dev(case_inference_inputs(fx, transform), dev), transform, hp)
+    assert torch.equal(enc[1].cpu(), torch.from_numpy(fx[f'inf_{transform}_durations_int']))      # bit-exact
+    assert torch.equal(dec[1].cpu(), torch.from_numpy(fx[f'inf_{transform}_output_lengths']))
+    for name, got in (('duration_preds', enc[0]), ('energy_preds', enc[2]), ('pitch_preds', enc[3]), ('mel_spec_preds', dec[0])):
+        assert scale_rel_err(got, fx[f'inf_{transform}_{name}']) < 2e-4, name
+
+
+def test_state_dict_roundtrip_and_unknown_transform(dev):
+    model, hp, sd = build_model(3, dev)
+    got = model.state_dict()
+    assert list(got.keys()) == list(sd.keys())
+    assert all(torch.equal(got[k].cpu(), sd[k]) for k in sd)
+    with pytest.raises(NotImplementedError):
+        model.inference(to_dev(synthetic.make_inference_batch(2, 10, 30, 3), dev), 'bogus', hp)
+
+
+def test_cpu_tensors_fail_loudly(dev):
+    model, hp, _ = build_model(3, dev)
+    with pytest.raises(RuntimeError):
+        model(synthetic.make_batch(2, 10, 40, 3, seed=1))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# full BASELINE size: size-independent properties (the oracle is too slow / too big there)
+# ----------------------------------------------------------------------------------------------------------------------
+def test_full_size_properties(dev):
+    """B=32, L<=200, T<=1000 (BASELINE configs[1]): integer contract, padding invariants, alignment normalisation,
+    batch-composition independence of the LONGEST utterance, determinism, train-mode dropout sanity."""
+    from daft_exprt_b200.loss import DaftExprtLoss
+    set_backend('tf32')
+    n_ids = 11
+    inputs = synthetic.make_batch(32, 200, 1000, n_ids, seed=0)
+    model, hp, _ = build_model(n_ids, dev)
+    crit = DaftExprtLoss(0, hp)
+    din = to_dev(inputs, dev)
+    out = model(din)
+    spk, film, enc, dec, align = out
+    mel, out_len = dec
+    assert torch.equal(out_len.cpu(), inputs[2].sum(1))
+    assert mel.shape == (32, 80, 1000) and align.shape == (32, 200, 1000)
+    tmask = oracle.valid_mask(inputs[9], 1000).to(dev)
+    lmask = oracle.valid_mask(inputs[5], 200).to(dev)
+    assert float(mel.abs().masked_select(~tmask[:, None, :].expand_as(mel)).max()) == 0.0       # padded frames are exactly 0
+    assert float(enc[0].abs().masked_select(~lmask).max()) == 0.0
+    assert float(align.masked_select(~lmask[:, :, None].expand_as(align)).abs().max()) == 0.0     # padded phonemes carry no weight
+    colsum = align.sum(dim=1)
+    assert float((colsum.masked_select(tmask) - 1).abs().max()) < 1e-4                            # weights normalised over phonemes
+    assert torch.isfinite(mel).all() and torch.isfinite(align).all()
+    total, terms = crit(out, targets_of(din), 1000)
+    total.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+    # the longest utterance does not depend on who else is in the batch
+    solo = tuple(t[:1].clone() for t in din)
+    mel_solo = model(solo)[3][0]
+    assert scale_rel_err(mel_solo[0], mel[0].detach()) < 5e-3
+    # determinism of the forward (no atomics on the forward path)
+    mel2 = model(din)[3][0]
+    assert torch.equal(mel2, mel)
+    # train mode: dropout changes the output, keeps padding at zero and everything finite
+    model.train()
+    mel_t = model(din)[3][0]
+    assert not torch.equal(mel_t, mel) and torch.isfinite(mel_t).all()
+    assert float(mel_t.abs().masked_select(~tmask[:, None, :].expand_as(mel_t)).max()) == 0.0

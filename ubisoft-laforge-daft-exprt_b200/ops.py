@@ -18,6 +18,7 @@ the fusions live below the ABI:
 """
 import ctypes
 import threading
+import weakref
 
 import torch
 
@@ -91,7 +92,7 @@ def packed(weight):
     key = id(weight)
     ver = (w.data_ptr(), w._version, _weights_epoch, _backend[0])
     hit = _pack_cache.get(key)
-    if hit is not None and hit[0] == ver:
+    if hit is not None and hit[0] == ver and hit[3]() is weight:   # id() can be recycled: check object identity too
         return hit[1], hit[2]
     w = _check_input(w)
     cout, cin = w.shape[0], w.shape[1]
@@ -100,7 +101,7 @@ def packed(weight):
     dgrad = torch.empty(kw, cin, cout, device=w.device, dtype=torch.float32)
     rnd = 1 if _backend[0] == cabi.DX_GEMM_TCGEN05_TF32 else 0
     _call('dx_pack_conv_weight', _p(w), _p(fwd), _p(dgrad), cout, cin, kw, rnd, _st())
-    _pack_cache[key] = (ver, fwd, dgrad)
+    _pack_cache[key] = (ver, fwd, dgrad, weakref.ref(weight))
     return fwd, dgrad
 
 
