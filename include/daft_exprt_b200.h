@@ -28,10 +28,13 @@ extern "C" {
 
 #define DX_ABI_VERSION 1
 #define DX_GEMM_FP32_CUDA_CORES 0 /* exact fp32 (parity mode) */
-#define DX_GEMM_TCGEN05_TF32 1    /* tcgen05.mma kind::tf32, TMEM accumulators, TMA-fed (default on sm_100) */
+#define DX_GEMM_TCGEN05_TF32 1    /* tcgen05.mma kind::tf32 on fp32 tiles: one pass, ~1e-3 per GEMM (forward/dgrad; wgrad runs bf16x3) */
+#define DX_GEMM_TCGEN05_BF16X3 2  /* tcgen05.mma kind::f16 on bf16 hi/lo operand planes, 3 passes, fp32-grade results (default) */
 
 const char* dx_last_error(void);
 int dx_abi_version(void);
+/* number of CUDA kernels this library has launched so far in this process */
+uint64_t dx_launch_count(void);
 /* 0 when the current device is sm_100 (B200); negative otherwise */
 int dx_device_check(void);
 int dx_set_gemm_backend(int backend);
@@ -45,8 +48,13 @@ int dx_pack_conv_weight(const float* w, float* fwd, float* dgrad, int Cout, int 
 /* y[b,s,n] = epi(alpha * sum_{tap,c} x[b, s+tap-(KW-1)/2, c] * w[tap][n][c] + bias[n]); zero padding at s<0, s>=S only.
  * epi: relu, then multiply by (relu_src > 0) when relu_src != NULL (ReLU backward fused into a dgrad), then + add_src
  * (same layout as y; residual / gradient accumulation) when != NULL, then optional tf32 rounding of the stored value.  backend < 0 selects the global default. */
-int dx_conv_gemm(const float* x, const float* w_packed, const float* bias, const float* relu_src, const float* add_src, float* y, int B, int S,
-                 int Cin, int Cout, int KW, int ldx, int ldy, float alpha, int relu, int round_tf32, int backend, void* stream);
+/* w_planes (nullable): cached bf16 hi|lo planes of w_packed made by dx_split_weight_planes (2 * KW*Cout*Cin bf16);
+ * workspace: dx_conv_gemm_workspace(...) bytes (operand planes of the bf16x3 tensor-core path; 0 for the fp32 backend). */
+int dx_conv_gemm(const float* x, const float* w_packed, const void* w_planes, const float* bias, const float* relu_src,
+                 const float* add_src, float* y, void* workspace, size_t workspace_bytes, int B, int S, int Cin, int Cout, int KW,
+                 int ldx, int ldy, float alpha, int relu, int round_tf32, int backend, void* stream);
+size_t dx_conv_gemm_workspace(int B, int S, int Cin, int Cout, int KW, int have_w_planes, int backend);
+int dx_split_weight_planes(const float* w_packed, void* planes, size_t n, void* stream);
 size_t dx_conv_wgrad_workspace(int B, int S, int Cin, int Cout, int KW, int backend);
 /* dw[co][ci][tap] = alpha * sum_{b,s} dy[b,s,co] * x[b, s+tap-pad, ci]  (parameter layout);  dbias[co] = alpha * sum dy */
 int dx_conv_wgrad(const float* x, const float* dy, float* dw, float* dbias, void* workspace, size_t workspace_bytes, int B,

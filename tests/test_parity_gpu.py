@@ -3,8 +3,10 @@
 Tolerances (north_star: "mel/loss outputs match the reference within 1e-3 relative fp32"; integers bit-exact):
   * fp32 backend (CUDA-core GEMMs, exact fp32 math):  scale-relative error  max|a-b| / max|b|  <= 1e-4  on dense outputs,
     loss terms relative 1e-4, gradients 1e-3 (fp32 reduction-order noise over B*T rows);
-  * tf32 backend (tcgen05 tensor cores, tf32 multiply + fp32 accumulate): dense outputs <= 1e-3 relative-L2 and 3e-3
-    scale-relative, loss 1e-3, gradients 2e-2 relative-L2 — the measured values are printed by the tests.
+  * bf16x3 backend (DEFAULT; tcgen05 tensor cores on bf16 hi/lo operand planes, fp32 accumulate in TMEM): dense outputs
+    <= 1e-3 scale-relative and 2e-4 relative-L2, loss terms 1e-4, gradients 2e-3;
+  * tf32 backend (single-pass tcgen05 kind::tf32): a reduced-precision mode that does NOT meet the 1e-3 bar on mel (measured
+    ~1e-2 scale-relative, printed by the tests); kept for comparison only, never used for a parity claim.
   * integer outputs (prefix sums, output lengths, T_max, get_int_durations): torch.equal.
 """
 import numpy as np
@@ -18,10 +20,11 @@ from helpers import (GOLDEN_CASES, GOLDEN_DIR, case_inference_inputs, case_input
 
 pytestmark = pytest.mark.gpu
 
-BACKENDS = ('fp32', 'tf32')
+BACKENDS = ('fp32', 'bf16x3', 'tf32')
 TOL = {  # (dense scale-rel, dense l2-rel, loss rel, grad l2-rel)
     'fp32': (1e-4, 1e-4, 1e-4, 1e-3),
-    'tf32': (3e-3, 1e-3, 1e-3, 2e-2),
+    'bf16x3': (1e-3, 2e-4, 1e-4, 2e-3),
+    'tf32': (5e-2, 5e-3, 2e-3, 1e-1),     # reduced-precision mode: reported, outside the 1e-3 parity bar by design
 }
 
 
@@ -81,7 +84,7 @@ def test_conv_gemm_forward_dgrad_wgrad(dev, backend, shape):
     wp, wdg = ops.packed(wd_)
     y = ops.conv_gemm(xd, wp, bd, B, S, relu=True)
     ref = torch.relu(torch.nn.functional.conv1d(x.double().transpose(1, 2), w.double(), b.double(), padding=(KW - 1) // 2)).transpose(1, 2)
-    tol = 2e-5 if backend == 'fp32' else 2e-3
+    tol = {'fp32': 2e-5, 'bf16x3': 5e-5, 'tf32': 3e-3}[backend]
     assert scale_rel_err(y, ref) < tol, f'forward {shape}'
     # dgrad with fused ReLU mask and residual add
     add = torch.randn(B, S, Cin, generator=g)
@@ -283,12 +286,14 @@ def test_all_gradients_match_oracle_autograd(dev, backend):
     din = to_dev(inputs, dev)
     total, _ = crit(model(din), targets_of(din), 4000)
     total.backward()
-    sd_o = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    # fp64 oracle as the arbiter: fp32 autograd on CPU carries ~1e-3 cancellation noise of its own on the deepest gradients
+    sd_o = {k: v.double().requires_grad_(True) for k, v in sd.items()}
     ohp = oracle.OracleHParams(n_speakers=n_ids + 1)
-    total_o, _ = oracle.loss(ohp, oracle.forward(sd_o, ohp, inputs), targets_of(inputs), 4000)
+    in64 = tuple(t.double() if t.is_floating_point() else t for t in inputs)
+    total_o, _ = oracle.loss(ohp, oracle.forward(sd_o, ohp, in64), targets_of(in64), 4000)
     total_o.backward()
-    tol = 1e-3 if backend == 'fp32' else 3e-2
-    assert abs(total.item() - total_o.item()) < (1e-4 if backend == 'fp32' else 1e-3) * abs(total_o.item())
+    tol = {'fp32': 1e-3, 'bf16x3': 3e-3, 'tf32': 2e-1}[backend]
+    assert abs(total.item() - total_o.item()) < {'fp32': 1e-4, 'bf16x3': 1e-4, 'tf32': 2e-3}[backend] * abs(total_o.item())
     bad = []
     for n, p in model.named_parameters():
         e = scale_rel_err(p.grad, sd_o[n].grad)
@@ -334,7 +339,7 @@ def test_full_size_properties(dev):
     """B=32, L<=200, T<=1000 (BASELINE configs[1]): integer contract, padding invariants, alignment normalisation,
     batch-composition independence of the LONGEST utterance, determinism, train-mode dropout sanity."""
     from daft_exprt_b200.loss import DaftExprtLoss
-    set_backend('tf32')
+    set_backend('bf16x3')
     n_ids = 11
     inputs = synthetic.make_batch(32, 200, 1000, n_ids, seed=0)
     model, hp, _ = build_model(n_ids, dev)
@@ -359,7 +364,7 @@ def test_full_size_properties(dev):
     # the longest utterance does not depend on who else is in the batch
     solo = tuple(t[:1].clone() for t in din)
     mel_solo = model(solo)[3][0]
-    assert scale_rel_err(mel_solo[0], mel[0].detach()) < 5e-3
+    assert scale_rel_err(mel_solo[0], mel[0].detach()) < 1e-3
     # determinism of the forward (no atomics on the forward path)
     mel2 = model(din)[3][0]
     assert torch.equal(mel2, mel)

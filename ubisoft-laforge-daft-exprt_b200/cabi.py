@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libdaftexprt_b200.so')
 
 DX_GEMM_FP32_CUDA_CORES = 0
 DX_GEMM_TCGEN05_TF32 = 1
+DX_GEMM_TCGEN05_BF16X3 = 2
 
 _lib = None
 _protos = None
@@ -33,9 +34,9 @@ def parse_header(path=HEADER):
     text = open(path).read()
     text = re.sub(r'/\*.*?\*/', ' ', text, flags=re.S)
     protos = {}
-    for m in re.finditer(r'(const char\*|int|size_t)\s+(dx_\w+)\s*\(([^;{]*?)\)\s*;', text, flags=re.S):
+    for m in re.finditer(r'(const char\*|int|size_t|uint64_t)\s+(dx_\w+)\s*\(([^;{]*?)\)\s*;', text, flags=re.S):
         ret, name, args = m.group(1), m.group(2), ' '.join(m.group(3).split())
-        restype = {'const char*': ctypes.c_char_p, 'int': ctypes.c_int, 'size_t': ctypes.c_size_t}[ret]
+        restype = {'const char*': ctypes.c_char_p, 'int': ctypes.c_int, 'size_t': ctypes.c_size_t, 'uint64_t': ctypes.c_uint64}[ret]
         argtypes = [] if args in ('', 'void') else [_ctype_of(a) for a in args.split(',')]
         protos[name] = (restype, argtypes)
     return protos

@@ -10,6 +10,7 @@ namespace dx {
 
 static thread_local char g_err[1024] = "";
 static int g_backend = DX_GEMM_FP32_CUDA_CORES;
+static unsigned long long g_launches = 0;   // kernels launched by this library (every launch goes through check_launch)
 
 void set_last_error(const char* fmt, ...) {
     va_list ap;
@@ -19,6 +20,7 @@ void set_last_error(const char* fmt, ...) {
 }
 
 int check_launch(const char* what) {
+    ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_last_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -37,6 +39,7 @@ extern "C" {
 
 const char* dx_last_error(void) { return g_err; }
 int dx_abi_version(void) { return DX_ABI_VERSION; }
+uint64_t dx_launch_count(void) { return g_launches; }
 
 int dx_device_check(void) {
     int dev = 0;
@@ -51,8 +54,10 @@ int dx_device_check(void) {
 }
 
 int dx_set_gemm_backend(int backend) {
-    DX_REQUIRE(backend == DX_GEMM_FP32_CUDA_CORES || backend == DX_GEMM_TCGEN05_TF32, "unknown GEMM backend %d", backend);
+    DX_REQUIRE(backend == DX_GEMM_FP32_CUDA_CORES || backend == DX_GEMM_TCGEN05_TF32 || backend == DX_GEMM_TCGEN05_BF16X3,
+               "unknown GEMM backend %d", backend);
     g_backend = backend;
+    set_tc_precision(backend == DX_GEMM_TCGEN05_TF32);
     return DX_OK;
 }
 int dx_get_gemm_backend(void) { return g_backend; }
@@ -61,15 +66,37 @@ int dx_pack_conv_weight(const float* w, float* fwd, float* dgrad, int Cout, int 
     return pack_conv_weight(w, fwd, dgrad, Cout, Cin, KW, round_tf32, ST(stream));
 }
 
-int dx_conv_gemm(const float* x, const float* w_packed, const float* bias, const float* relu_src, const float* add_src, float* y, int B, int S,
-                 int Cin, int Cout, int KW, int ldx, int ldy, float alpha, int relu, int round_tf32, int backend, void* stream) {
+static ConvGemmArgs gemm_args(const float* x, const float* w_packed, const void* w_planes, const float* bias,
+                              const float* relu_src, const float* add_src, float* y, void* ws, size_t wsb, int B, int S, int Cin,
+                              int Cout, int KW, int ldx, int ldy, float alpha, int relu, int round_tf32) {
     ConvGemmArgs a;
     a.x = x; a.w = w_packed; a.bias = bias; a.relu_src = relu_src; a.add_src = add_src; a.y = y;
     a.B = B; a.S = S; a.Cin = Cin; a.Cout = Cout; a.KW = KW; a.ldx = ldx; a.ldy = ldy;
     a.alpha = alpha; a.relu = relu; a.round_tf32 = round_tf32;
+    a.w_planes = w_planes; a.workspace = ws; a.workspace_bytes = wsb;
+    return a;
+}
+
+int dx_split_weight_planes(const float* w_packed, void* planes, size_t n, void* stream) {
+    return split_weight_planes(w_packed, planes, n, ST(stream));
+}
+
+size_t dx_conv_gemm_workspace(int B, int S, int Cin, int Cout, int KW, int have_w_planes, int backend) {
+    const int be = backend < 0 ? g_backend : backend;
+    if (be == DX_GEMM_FP32_CUDA_CORES) return 0;
+    ConvGemmArgs a = gemm_args(nullptr, nullptr, have_w_planes ? (const void*)16 : nullptr, nullptr, nullptr, nullptr, nullptr,
+                               nullptr, 0, B, S, Cin, Cout, KW, Cin, Cout, 1.f, 0, 0);
+    return conv_gemm_tc_workspace(a);
+}
+
+int dx_conv_gemm(const float* x, const float* w_packed, const void* w_planes, const float* bias, const float* relu_src,
+                 const float* add_src, float* y, void* workspace, size_t workspace_bytes, int B, int S, int Cin, int Cout, int KW,
+                 int ldx, int ldy, float alpha, int relu, int round_tf32, int backend, void* stream) {
+    ConvGemmArgs a = gemm_args(x, w_packed, w_planes, bias, relu_src, add_src, y, workspace, workspace_bytes, B, S, Cin, Cout, KW,
+                               ldx, ldy, alpha, relu, round_tf32);
     DX_REQUIRE(B > 0 && S > 0 && Cin > 0 && Cout > 0 && (KW == 1 || KW == 3), "dx_conv_gemm: bad shape B=%d S=%d Cin=%d Cout=%d KW=%d", B, S, Cin, Cout, KW);
     const int be = backend < 0 ? g_backend : backend;
-    if (be == DX_GEMM_TCGEN05_TF32 && conv_gemm_tc_supported(a)) return conv_gemm_tc(a, ST(stream));
+    if (be != DX_GEMM_FP32_CUDA_CORES && conv_gemm_tc_supported(a)) return conv_gemm_tc(a, ST(stream));
     return conv_gemm_simt(a, ST(stream));
 }
 
@@ -85,7 +112,7 @@ size_t dx_conv_wgrad_workspace(int B, int S, int Cin, int Cout, int KW, int back
     ConvWgradArgs a = wgrad_args(nullptr, nullptr, nullptr, nullptr, nullptr, 0, B, S, Cin, Cout, KW, Cin, 1.f);
     size_t need = conv_wgrad_simt_workspace(a, nullptr);
     const int be = backend < 0 ? g_backend : backend;
-    if (be == DX_GEMM_TCGEN05_TF32 && conv_wgrad_tc_supported(a)) {
+    if (be != DX_GEMM_FP32_CUDA_CORES && conv_wgrad_tc_supported(a)) {
         const size_t t = conv_wgrad_tc_workspace(a);
         if (t > need) need = t;
     }
@@ -96,7 +123,7 @@ int dx_conv_wgrad(const float* x, const float* dy, float* dw, float* dbias, void
                   int S, int Cin, int Cout, int KW, int ldx, float alpha, int backend, void* stream) {
     ConvWgradArgs a = wgrad_args(x, dy, dw, dbias, workspace, workspace_bytes, B, S, Cin, Cout, KW, ldx, alpha);
     const int be = backend < 0 ? g_backend : backend;
-    if (be == DX_GEMM_TCGEN05_TF32 && conv_wgrad_tc_supported(a)) return conv_wgrad_tc(a, ST(stream));
+    if (be != DX_GEMM_FP32_CUDA_CORES && conv_wgrad_tc_supported(a)) return conv_wgrad_tc(a, ST(stream));
     return conv_wgrad_simt(a, ST(stream));
 }
 

@@ -1,10 +1,620 @@
-// placeholder, replaced below
+// tcgen05 / TMEM / TMA implementation of the channels-last Conv1d / Linear GEMMs (forward, dgrad, wgrad) for sm_100a.
+//
+//   forward/dgrad:  y[b, s, n] = epi( alpha * sum_{tap < KW} sum_{c < Cin} x[b, s + tap - pad, c] * w[tap][n][c] + bias[n] )
+//   wgrad:          part[split][tap][co][ci] = sum_{b in split} sum_s dy[b, s, co] * x[b, s + tap - pad, ci]
+//
+// im2col-free: the KW taps are KW shifted K-slices of the same activation tensor.  Operand tiles are fetched by 3-D TMA
+// tensor maps whose s-coordinate is simply offset by (tap - pad); rows that fall outside [0, S) are zero-filled by the TMA
+// unit, which IS the convolution's zero padding (it can never bleed into the neighbouring utterance because the batch
+// index is its own tensor dimension).
+//
+// Precision modes (the reference computes in fp32 and parity is the first gate):
+//   BF16X3  every fp32 operand is split as hi + lo (two bf16 planes, |x - hi - lo| <= 2^-17 |x|) and the product is formed as
+//           hi*hi + lo*hi + hi*lo by three `tcgen05.mma kind::f16` per K-step with fp32 accumulation in TMEM: fp32-grade
+//           results (~1e-5) at 3 bf16 tensor-core passes.  Default.
+//   TF32    fp32 tiles are consumed directly by `tcgen05.mma kind::tf32` (10-bit mantissa): one pass at half the bf16 rate,
+//           ~1e-3 per GEMM.  Forward/dgrad only.
+//
+// CTA = 192 threads, persistent over 128 x 128 output tiles, one CTA per SM:
+//   warp 0    TMA producer: ring of K-stages (128-byte rows, SWIZZLE_128B), mbarrier complete_tx
+//   warp 1    MMA issuer (one thread): UMMA M128 N128, tcgen05.commit frees the stage; two TMEM accumulators (2 x 128
+//             columns) so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns) -> registers -> bias / ReLU / ReLU-mask / residual add ->
+//             128B-swizzled smem staging -> TMA store (clips partial tiles)
+#include <cuda.h>
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "kernels.h"
+
 namespace dx {
-bool conv_gemm_tc_supported(const ConvGemmArgs&) { return false; }
-int conv_gemm_tc(const ConvGemmArgs&, cudaStream_t) { set_last_error("tcgen05 path not built"); return DX_ERR_UNSUPPORTED; }
-bool conv_wgrad_tc_supported(const ConvWgradArgs&) { return false; }
-int conv_wgrad_tc(const ConvWgradArgs&, cudaStream_t) { set_last_error("tcgen05 path not built"); return DX_ERR_UNSUPPORTED; }
-size_t conv_wgrad_tc_workspace(const ConvWgradArgs&) { return 0; }
+
+namespace {
+
+enum { PREC_TF32 = 0, PREC_BF16X3 = 1 };
+enum { MODE_CONV = 0, MODE_WGRAD = 1 };
+
+constexpr int TM = 128, TN = 128;
+constexpr int TILE_BYTES = 128 * 128;                 // one operand tile: 128 rows x 128 bytes
+constexpr int OUT_BYTES = TM * 32 * 4;                // one 128 x 32 fp32 staging chunk
+constexpr int TMEM_COLS = 256;
+
+template <int PREC> struct Cfg;
+template <> struct Cfg<PREC_TF32>   { static constexpr int TKB = 32, PLANES = 1, NSTAGE = 5; };
+template <> struct Cfg<PREC_BF16X3> { static constexpr int TKB = 64, PLANES = 2, NSTAGE = 3; };
+template <int PREC> constexpr int stage_bytes() { return 2 * Cfg<PREC>::PLANES * TILE_BYTES; }
+template <int PREC> constexpr int smem_bytes() { return Cfg<PREC>::NSTAGE * stage_bytes<PREC>() + 2 * OUT_BYTES + 256 + 1024; }
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile in shared memory, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 B apart (SBO); LBO unused.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: fp32 accumulate, both operands K-major, M x N tile; fmt 1 = bf16 (kind::f16), 2 = tf32 (kind::tf32)
+__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+template <int PREC>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (PREC == PREC_TF32) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+        "%25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcParams {
+    const float* bias;
+    const float* relu_src;
+    const float* add_src;
+    int B, S, Cin, Cout, KW, ldy;
+    int tiles_m_per_b, tiles_n, num_tiles, k_chunks;   // CONV: tiles over (b, s) x n;  WGRAD: tiles_m = co tiles, tiles_n = ci tiles
+    int nsplit;                                         // WGRAD: batch ranges
+    float alpha;
+    int relu, round_tf32;
+};
+
+struct TileCoord {
+    int a0, a1, a2;   // first-stage A coordinates (coordinate 0 advances with the K chunk)
+    int b0, b1, b2;
+    int o0, o1, o2;   // output coordinates of column chunk 0
+    int tap, k_begin, k_end;   // K iterations [k_begin, k_end): k -> (outer = k / k_chunks, chunk = k % k_chunks)
+};
+
+template <int MODE>
+__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int tile) {
+    TileCoord t;
+    if constexpr (MODE == MODE_CONV) {
+        const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
+        const int b = tm / p.tiles_m_per_b, s0 = (tm % p.tiles_m_per_b) * TM, n0 = tn * TN;
+        t.a0 = 0; t.a1 = s0; t.a2 = b;
+        t.b0 = 0; t.b1 = n0; t.b2 = 0;
+        t.o0 = n0; t.o1 = s0; t.o2 = b;
+        t.tap = 0; t.k_begin = 0; t.k_end = p.KW * p.k_chunks;   // outer = tap
+    } else {
+        // tile = ((split * KW + tap) * tiles_m + tco) * tiles_n + tci
+        const int tci = tile % p.tiles_n;
+        int r = tile / p.tiles_n;
+        const int tco = r % p.tiles_m_per_b;
+        r /= p.tiles_m_per_b;
+        const int tap = r % p.KW, split = r / p.KW;
+        t.a0 = 0; t.a1 = 0; t.a2 = tco * TM;
+        t.b0 = 0; t.b1 = 0; t.b2 = tci * TN;
+        t.o0 = tci * TN; t.o1 = tco * TM; t.o2 = split * p.KW + tap;
+        t.tap = tap;
+        const long long total_k = (long long)p.B * p.k_chunks;                 // outer = utterance
+        t.k_begin = (int)((split * total_k) / p.nsplit);
+        t.k_end = (int)(((split + 1) * total_k) / p.nsplit);
+    }
+    return t;
+}
+
+template <int PREC, int MODE>
+__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
+                                                         const __grid_constant__ CUtensorMap map_a_lo,
+                                                         const __grid_constant__ CUtensorMap map_b_hi,
+                                                         const __grid_constant__ CUtensorMap map_b_lo,
+                                                         const __grid_constant__ CUtensorMap map_y, TcParams p) {
+    constexpr int NSTAGE = Cfg<PREC>::NSTAGE, PLANES = Cfg<PREC>::PLANES, TKB = Cfg<PREC>::TKB;
+    constexpr int STAGE_BYTES = stage_bytes<PREC>();
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t sOut = base + NSTAGE * STAGE_BYTES;
+    const uint32_t bars = sOut + 2 * OUT_BYTES;
+    const uint32_t full0 = bars, empty0 = bars + 8 * NSTAGE, tfull0 = bars + 16 * NSTAGE, tempty0 = tfull0 + 16;
+    const uint32_t tmem_slot = tempty0 + 16;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pad = (p.KW - 1) / 2;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const TileCoord t = tile_coord<MODE>(p, tile);
+                for (int k = t.k_begin; k < t.k_end; ++k) {
+                    {
+                        const int o = k / p.k_chunks, kc = k - o * p.k_chunks;
+                        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                        const uint32_t bar = full0 + 8 * stage;
+                        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + PLANES * TILE_BYTES;
+                        mbar_expect_tx(bar, STAGE_BYTES);
+                        int a0, a1, a2, b0, b1, b2;
+                        if constexpr (MODE == MODE_CONV) {      // o = tap
+                            a0 = kc * TKB; a1 = t.a1 + o - pad; a2 = t.a2;
+                            b0 = kc * TKB; b1 = t.b1; b2 = o;
+                        } else {                                // o = utterance inside this split
+                            a0 = kc * TKB; a1 = o; a2 = t.a2;
+                            b0 = kc * TKB + t.tap - pad; b1 = o; b2 = t.b2;
+                        }
+                        tma_load_3d(sa, &map_a_hi, bar, a0, a1, a2);
+                        tma_load_3d(sb, &map_b_hi, bar, b0, b1, b2);
+                        if constexpr (PLANES == 2) {
+                            tma_load_3d(sa + TILE_BYTES, &map_a_lo, bar, a0, a1, a2);
+                            tma_load_3d(sb + TILE_BYTES, &map_b_lo, bar, b0, b1, b2);
+                        }
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(PREC == PREC_TF32 ? 2 : 1, TM, TN);
+            int stage = 0, phase = 0, it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const TileCoord t = tile_coord<MODE>(p, tile);
+                const int k_iters = t.k_end - t.k_begin;
+                const int acc = it & 1, acc_phase = (it >> 1) & 1;
+                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);     // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * TN;
+                for (int k = 0; k < k_iters; ++k) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + PLANES * TILE_BYTES;
+                    const uint64_t a_hi = umma_desc_k_sw128(sa), b_hi = umma_desc_k_sw128(sb);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {   // 32 bytes of K per instruction (+2 in 16-byte descriptor units)
+                        umma<PREC>(tmem_d, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (k | kk) != 0);
+                        if constexpr (PLANES == 2) {
+                            const uint64_t a_lo = umma_desc_k_sw128(sa + TILE_BYTES), b_lo = umma_desc_k_sw128(sb + TILE_BYTES);
+                            umma<PREC>(tmem_d, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1u);
+                            umma<PREC>(tmem_d, a_hi + 2 * kk, b_lo + 2 * kk, idesc, 1u);
+                        }
+                    }
+                    umma_commit(empty0 + 8 * stage);          // frees the smem stage when these MMAs retire
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull0 + 8 * acc);                // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // epilogue: warp w may only touch TMEM lanes [32*(w%4), +32); thread <-> output row
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const int et = threadIdx.x - 64;          // 0..127
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const TileCoord t = tile_coord<MODE>(p, tile);
+            const int acc = it & 1, acc_phase = (it >> 1) & 1;
+            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            tc_fence_after();
+            const int s = t.o1 + row;
+            const bool row_ok = MODE == MODE_CONV && s < p.S;
+            const size_t grow = (size_t)t.o2 * p.S + s;
+#pragma unroll 1
+            for (int j = 0; j < TN / 32; ++j) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN + j * 32, v);
+                if (j == TN / 32 - 1) {   // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                }
+                const int nb = t.o0 + j * 32;
+                float o[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float f = __uint_as_float(v[i]);
+                    if constexpr (MODE == MODE_CONV) {
+                        const int n = nb + i;
+                        f *= p.alpha;
+                        if (n < p.Cout) {
+                            if (p.bias) f += __ldg(p.bias + n);
+                            if (p.relu) f = fmaxf(f, 0.f);
+                            if (row_ok) {
+                                if (p.relu_src) f = __ldg(p.relu_src + grow * p.Cout + n) > 0.f ? f : 0.f;
+                                if (p.add_src) f += __ldg(p.add_src + grow * p.ldy + n);
+                            }
+                            if (p.round_tf32) f = round_tf32(f);
+                        }
+                    }
+                    o[i] = f;
+                }
+                // staging buffer (j & 1): the TMA store that last read it (2 chunks ago) must have finished reading
+                if (et == 0) tma_store_wait_read<1>();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const uint32_t obuf = sOut + (j & 1) * OUT_BYTES + row * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {   // 16-byte chunk c of this row lands at chunk (c ^ (row & 7)): SWIZZLE_128B
+                    const uint32_t dst = obuf + ((c ^ (row & 7)) << 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o[4 * c]), "f"(o[4 * c + 1]),
+                                 "f"(o[4 * c + 2]), "f"(o[4 * c + 3]) : "memory");
+                }
+                fence_async_smem();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    tma_store_3d(&map_y, sOut + (j & 1) * OUT_BYTES, nb, t.o1, t.o2);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (et == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- operand planes: fp32 [B, S, ld] -> bf16 hi/lo, row-major [B*S][C] and/or transposed [C][B][Sp] -------------------
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// grid (ceil(S/64), ceil(C/64), B), 256 threads; one 64(s) x 64(c) tile per block
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ src, int ld, int S, int C, int Sp,
+                                                           __nv_bfloat16* __restrict__ row_hi, __nv_bfloat16* __restrict__ row_lo,
+                                                           __nv_bfloat16* __restrict__ t_hi, __nv_bfloat16* __restrict__ t_lo, int B) {
+    __shared__ __nv_bfloat16 th[64][72], tl[64][72];   // [c][s], padded rows (144 B: 16-byte aligned chunks)
+    const int b = blockIdx.z, s0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = t + 256 * i, r = idx >> 4, cq = (idx & 15) * 4;
+        const int s = s0 + r, c = c0 + cq;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s < S && c < C) v = *reinterpret_cast<const float4*>(src + ((size_t)b * S + s) * ld + c);   // C % 4 == 0
+        __nv_bfloat16 h[4], l[4];
+        split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+        if (row_hi && s < S && c < C) {
+            const size_t o = ((size_t)b * S + s) * C + c;
+            *reinterpret_cast<uint2*>(row_hi + o) = *reinterpret_cast<uint2*>(h);
+            *reinterpret_cast<uint2*>(row_lo + o) = *reinterpret_cast<uint2*>(l);
+        }
+        if (t_hi) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { th[cq + e][r] = h[e]; tl[cq + e][r] = l[e]; }
+        }
+    }
+    if (!t_hi) return;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int idx = t + 256 * i, c = idx >> 3, sq = (idx & 7) * 8;   // 64 c-rows x 8 chunks of 8 bf16 (16 bytes)
+        if (c0 + c < C && s0 + sq < Sp) {
+            const size_t o = ((size_t)(c0 + c) * B + b) * Sp + s0 + sq;
+            *reinterpret_cast<uint4*>(t_hi + o) = *reinterpret_cast<uint4*>(&th[c][sq]);
+            *reinterpret_cast<uint4*>(t_lo + o) = *reinterpret_cast<uint4*>(&tl[c][sq]);
+        }
+    }
+}
+
+// weight planes: fp32 packed [KW][N][K] -> bf16 hi/lo (same layout)
+__global__ void split_flat_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                  size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        __nv_bfloat16 h, l;
+        split_bf16(src[i], h, l);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
+// ---- host side: tensor maps -------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+// 3-D tensor (d0 contiguous), box (b0, b1, b2), SWIZZLE_128B, zero OOB fill.  esz = 4 (fp32) or 2 (bf16).
+int make_map_3d(CUtensorMap* map, const void* ptr, int esz, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
+    EncodeTiledFn enc = get_encode();
+    DX_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {b0, b1, b2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                     const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) esz=%d dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u,%u)",
+               (int)r, esz, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+               (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes, b0, b1, b2);
+    return DX_OK;
+}
+
+int g_num_sms = 0;
+int g_prec = PREC_BF16X3;
+
+int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <int PREC, int MODE>
+int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const CUtensorMap& my,
+           const TcParams& p, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        DX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<PREC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<PREC>()));
+        configured = true;
+    }
+    const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    gemm_tc_kernel<PREC, MODE><<<grid, 192, smem_bytes<PREC>(), st>>>(ah, al, bh, bl, my, p);
+    return check_launch("gemm_tc");
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+inline int round8(int x) { return (x + 7) & ~7; }
+
+}  // namespace
+
+void set_tc_precision(int tf32) { g_prec = tf32 ? PREC_TF32 : PREC_BF16X3; }
+
+int split_weight_planes(const float* w, void* planes, size_t n, cudaStream_t st) {
+    __nv_bfloat16* hi = (__nv_bfloat16*)planes;
+    split_flat_kernel<<<grid_1d(n), 256, 0, st>>>(w, hi, hi + n, n);
+    return check_launch("split_flat");
+}
+
+bool conv_gemm_tc_supported(const ConvGemmArgs& a) {
+    if (a.Cin % 8 != 0 || a.Cout % 4 != 0 || a.ldx % 4 != 0 || a.ldy % 4 != 0) return false;   // 16-byte global strides
+    if (((uintptr_t)a.x | (uintptr_t)a.w | (uintptr_t)a.y) & 15) return false;
+    if (a.Cin < 16 || a.Cout < 16) return false;
+    return get_encode() != nullptr;
+}
+
+// workspace: bf16 hi/lo planes of x ([B*S][Cin]) and of the packed weight ([KW][Cout][Cin]) when running BF16X3
+size_t conv_gemm_tc_workspace(const ConvGemmArgs& a) {
+    if (g_prec == PREC_TF32) return 0;
+    const size_t xe = (size_t)a.B * a.S * a.Cin, we = (size_t)a.KW * a.Cout * a.Cin;
+    return 2 * align256(xe * 2) + (a.w_planes ? 0 : 2 * align256(we * 2)) + 256;
+}
+
+int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
+    TcParams p;
+    p.bias = a.bias; p.relu_src = a.relu_src; p.add_src = a.add_src;
+    p.B = a.B; p.S = a.S; p.Cin = a.Cin; p.Cout = a.Cout; p.KW = a.KW; p.ldy = a.ldy;
+    p.tiles_m_per_b = ceil_div(a.S, TM);
+    p.tiles_n = ceil_div(a.Cout, TN);
+    p.num_tiles = p.tiles_m_per_b * a.B * p.tiles_n;
+    p.nsplit = 1;
+    p.alpha = a.alpha; p.relu = a.relu; p.round_tf32 = a.round_tf32;
+    CUtensorMap mxh, mxl, mwh, mwl, my;
+    int rc;
+    if ((rc = make_map_3d(&my, a.y, 4, a.Cout, a.S, a.B, (uint64_t)a.ldy * 4, (uint64_t)a.S * a.ldy * 4, 32, TM, 1))) return rc;
+    if (g_prec == PREC_TF32) {
+        p.k_chunks = ceil_div(a.Cin, Cfg<PREC_TF32>::TKB);
+        if ((rc = make_map_3d(&mxh, a.x, 4, a.Cin, a.S, a.B, (uint64_t)a.ldx * 4, (uint64_t)a.S * a.ldx * 4, 32, TM, 1))) return rc;
+        if ((rc = make_map_3d(&mwh, a.w, 4, a.Cin, a.Cout, a.KW, (uint64_t)a.Cin * 4, (uint64_t)a.Cout * a.Cin * 4, 32, TN, 1))) return rc;
+        return launch<PREC_TF32, MODE_CONV>(mxh, mxh, mwh, mwh, my, p, st);
+    }
+    const size_t need = conv_gemm_tc_workspace(a);
+    DX_REQUIRE(a.workspace && a.workspace_bytes >= need, "conv_gemm_tc: workspace %zu < %zu bytes", a.workspace_bytes, need);
+    const size_t xe = (size_t)a.B * a.S * a.Cin, we = (size_t)a.KW * a.Cout * a.Cin;
+    uint8_t* ws = (uint8_t*)(((uintptr_t)a.workspace + 255) & ~(uintptr_t)255);
+    __nv_bfloat16* xh = (__nv_bfloat16*)ws;
+    __nv_bfloat16* xl = (__nv_bfloat16*)(ws + align256(xe * 2));
+    const __nv_bfloat16* wh = (const __nv_bfloat16*)(ws + 2 * align256(xe * 2));
+    const __nv_bfloat16* wl = (const __nv_bfloat16*)(ws + 2 * align256(xe * 2) + align256(we * 2));
+    {
+        dim3 grid(ceil_div(a.S, 64), ceil_div(a.Cin, 64), a.B);
+        split_planes_kernel<<<grid, 256, 0, st>>>(a.x, a.ldx, a.S, a.Cin, 0, xh, xl, nullptr, nullptr, a.B);
+        if ((rc = check_launch("split_planes"))) return rc;
+        if (a.w_planes) {   // cached by the caller: hi plane followed by lo plane
+            wh = (const __nv_bfloat16*)a.w_planes;
+            wl = wh + we;
+        } else {
+            split_flat_kernel<<<grid_1d(we), 256, 0, st>>>(a.w, (__nv_bfloat16*)wh, (__nv_bfloat16*)wl, we);
+            if ((rc = check_launch("split_flat"))) return rc;
+        }
+    }
+    p.k_chunks = ceil_div(a.Cin, Cfg<PREC_BF16X3>::TKB);
+    const uint64_t xs1 = (uint64_t)a.Cin * 2, xs2 = (uint64_t)a.S * a.Cin * 2;
+    const uint64_t ws1 = (uint64_t)a.Cin * 2, ws2 = (uint64_t)a.Cout * a.Cin * 2;
+    if ((rc = make_map_3d(&mxh, xh, 2, a.Cin, a.S, a.B, xs1, xs2, 64, TM, 1))) return rc;
+    if ((rc = make_map_3d(&mxl, xl, 2, a.Cin, a.S, a.B, xs1, xs2, 64, TM, 1))) return rc;
+    if ((rc = make_map_3d(&mwh, wh, 2, a.Cin, a.Cout, a.KW, ws1, ws2, 64, TN, 1))) return rc;
+    if ((rc = make_map_3d(&mwl, wl, 2, a.Cin, a.Cout, a.KW, ws1, ws2, 64, TN, 1))) return rc;
+    return launch<PREC_BF16X3, MODE_CONV>(mxh, mxl, mwh, mwl, my, p, st);
+}
+
+// ---- wgrad -----------------------------------------------------------------------------------------------------------
+bool conv_wgrad_tc_supported(const ConvWgradArgs& a) {
+    if (a.Cin % 4 != 0 || a.Cout % 4 != 0 || a.ldx % 4 != 0) return false;
+    if (a.Cin < 16 || a.Cout < 16) return false;
+    if (((uintptr_t)a.x | (uintptr_t)a.dy) & 15) return false;
+    return get_encode() != nullptr;
+}
+
+static int wgrad_nsplit(const ConvWgradArgs& a) {
+    const int tiles = ceil_div(a.Cout, TM) * ceil_div(a.Cin, TN) * a.KW;
+    const int sms = 148;
+    int best = 1;
+    double best_eff = 0.0;
+    const int total_k = a.B * ceil_div(a.S, 64);
+    for (int ns = 1; ns <= total_k / 4 && ns <= 64; ++ns) {
+        const int ctas = tiles * ns, waves = ceil_div(ctas, sms);
+        const double eff = (double)ctas / ((double)waves * sms);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = ns; }
+        if (eff >= 0.9 && ctas >= sms) { best = ns; break; }
+    }
+    return best;
+}
+
+size_t conv_wgrad_tc_workspace(const ConvWgradArgs& a) {
+    const int Sp = round8(a.S);
+    const size_t dyT = (size_t)a.Cout * a.B * Sp, xT = (size_t)a.Cin * a.B * Sp;
+    const size_t part = (size_t)wgrad_nsplit(a) * a.KW * a.Cout * a.Cin * 4;
+    return 2 * align256(dyT * 2) + 2 * align256(xT * 2) + align256(part) + 256;
+}
+
+__global__ void wgrad_reduce_tc_kernel(const float* __restrict__ part, float* __restrict__ dw, int nsplit, int KW, int Cout,
+                                       int Cin, float alpha) {
+    // part[(split*KW + tap)][co][ci]  ->  dw[co][ci][tap]
+    const size_t per = (size_t)KW * Cout * Cin;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < per; i += (size_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < nsplit; ++k) s += part[(size_t)k * per + i];
+        const int ci = (int)(i % Cin);
+        const size_t q = i / Cin;
+        const int co = (int)(q % Cout), tap = (int)(q / Cout);
+        dw[((size_t)co * Cin + ci) * KW + tap] = alpha * s;
+    }
+}
+
+int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
+    const size_t need = conv_wgrad_tc_workspace(a);
+    DX_REQUIRE(a.workspace && a.workspace_bytes >= need, "conv_wgrad_tc: workspace %zu < %zu bytes", a.workspace_bytes, need);
+    const int Sp = round8(a.S);
+    const int nsplit = wgrad_nsplit(a);
+    const size_t dyT = (size_t)a.Cout * a.B * Sp, xT = (size_t)a.Cin * a.B * Sp;
+    uint8_t* ws = (uint8_t*)(((uintptr_t)a.workspace + 255) & ~(uintptr_t)255);
+    __nv_bfloat16* dh = (__nv_bfloat16*)ws;
+    __nv_bfloat16* dl = (__nv_bfloat16*)(ws + align256(dyT * 2));
+    __nv_bfloat16* xh = (__nv_bfloat16*)(ws + 2 * align256(dyT * 2));
+    __nv_bfloat16* xl = (__nv_bfloat16*)(ws + 2 * align256(dyT * 2) + align256(xT * 2));
+    float* part = (float*)(ws + 2 * align256(dyT * 2) + 2 * align256(xT * 2));
+    int rc;
+    {
+        dim3 g1(ceil_div(a.S, 64), ceil_div(a.Cout, 64), a.B);
+        split_planes_kernel<<<g1, 256, 0, st>>>(a.dy, a.Cout, a.S, a.Cout, Sp, nullptr, nullptr, dh, dl, a.B);
+        if ((rc = check_launch("split_planes(dy^T)"))) return rc;
+        dim3 g2(ceil_div(a.S, 64), ceil_div(a.Cin, 64), a.B);
+        split_planes_kernel<<<g2, 256, 0, st>>>(a.x, a.ldx, a.S, a.Cin, Sp, nullptr, nullptr, xh, xl, a.B);
+        if ((rc = check_launch("split_planes(x^T)"))) return rc;
+    }
+    TcParams p;
+    p.bias = nullptr; p.relu_src = nullptr; p.add_src = nullptr;
+    p.B = a.B; p.S = a.S; p.Cin = a.Cin; p.Cout = a.Cout; p.KW = a.KW; p.ldy = a.Cin;
+    p.tiles_m_per_b = ceil_div(a.Cout, TM);
+    p.tiles_n = ceil_div(a.Cin, TN);
+    p.nsplit = nsplit;
+    p.num_tiles = p.tiles_m_per_b * p.tiles_n * a.KW * nsplit;
+    p.k_chunks = ceil_div(a.S, Cfg<PREC_BF16X3>::TKB);
+    p.alpha = 1.f; p.relu = 0; p.round_tf32 = 0;
+    CUtensorMap mah, mal, mbh, mbl, my;
+    const uint64_t s1 = (uint64_t)Sp * 2, s2 = (uint64_t)a.B * Sp * 2;
+    if ((rc = make_map_3d(&mah, dh, 2, a.S, a.B, a.Cout, s1, s2, 64, 1, TM))) return rc;
+    if ((rc = make_map_3d(&mal, dl, 2, a.S, a.B, a.Cout, s1, s2, 64, 1, TM))) return rc;
+    if ((rc = make_map_3d(&mbh, xh, 2, a.S, a.B, a.Cin, s1, s2, 64, 1, TN))) return rc;
+    if ((rc = make_map_3d(&mbl, xl, 2, a.S, a.B, a.Cin, s1, s2, 64, 1, TN))) return rc;
+    if ((rc = make_map_3d(&my, part, 4, a.Cin, a.Cout, (uint64_t)nsplit * a.KW, (uint64_t)a.Cin * 4, (uint64_t)a.Cout * a.Cin * 4, 32, TM, 1)))
+        return rc;
+    if ((rc = launch<PREC_BF16X3, MODE_WGRAD>(mah, mal, mbh, mbl, my, p, st))) return rc;
+    const size_t per = (size_t)a.KW * a.Cout * a.Cin;
+    wgrad_reduce_tc_kernel<<<grid_1d(per, 256, 148 * 8), 256, 0, st>>>(part, a.dw, nsplit, a.KW, a.Cout, a.Cin, a.alpha);
+    if ((rc = check_launch("wgrad_reduce_tc"))) return rc;
+    if (a.dbias) return colsum(a.dy, a.dbias, a.B * a.S, a.Cout, a.alpha, st);
+    return DX_OK;
+}
+
+}  // namespace dx

@@ -21,6 +21,9 @@ struct ConvGemmArgs {
     float alpha;
     int relu;
     int round_tf32;
+    const void* w_planes;   // optional cached bf16 hi|lo planes of w (tensor-core bf16x3 path), else nullptr
+    void* workspace;        // tensor-core bf16x3 path: operand planes (see conv_gemm_tc_workspace)
+    size_t workspace_bytes;
 };
 
 // dw[co][ci][tap] = alpha * sum_{b,s} dy[b,s,co] * x[b, s + tap - pad, ci];  dbias[co] = alpha * sum dy[b,s,co]
@@ -43,6 +46,9 @@ int colsum(const float* dy, float* db, int R, int C, float alpha, cudaStream_t s
 int pack_conv_weight(const float* w, float* fwd, float* dgrad, int Cout, int Cin, int KW, int round, cudaStream_t st);
 
 // tcgen05 / TMEM / TMA path (gemm_tcgen05.cu)
+void set_tc_precision(int tf32);
+int split_weight_planes(const float* w, void* planes, size_t n, cudaStream_t st);
+size_t conv_gemm_tc_workspace(const ConvGemmArgs& a);
 bool conv_gemm_tc_supported(const ConvGemmArgs& a);
 int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st);
 bool conv_wgrad_tc_supported(const ConvWgradArgs& a);

@@ -36,16 +36,22 @@ def lib():
     return cabi.load()
 
 
+BACKENDS = {'fp32': cabi.DX_GEMM_FP32_CUDA_CORES, 'tf32': cabi.DX_GEMM_TCGEN05_TF32, 'bf16x3': cabi.DX_GEMM_TCGEN05_BF16X3}
+
+
 def set_backend(name):
-    """'fp32' = exact CUDA-core GEMMs (parity mode); 'tf32' = tcgen05 tensor-core GEMMs (tf32 multiply, fp32 accumulate)."""
-    be = {'fp32': cabi.DX_GEMM_FP32_CUDA_CORES, 'tf32': cabi.DX_GEMM_TCGEN05_TF32}[name]
+    """GEMM backend for Conv1d/Linear forward, dgrad and wgrad:
+    'bf16x3' tcgen05 tensor cores on bf16 hi/lo operand planes, 3 passes, fp32-grade results (default);
+    'tf32'   tcgen05 kind::tf32 on fp32 tiles, one pass, ~1e-3 per GEMM (wgrad still runs bf16x3);
+    'fp32'   exact fp32 on CUDA cores (strict parity mode)."""
+    be = BACKENDS[name]
     cabi.check(lib().dx_set_gemm_backend(be), 'dx_set_gemm_backend')
     _backend[0] = be
     invalidate_packed_weights()
 
 
 def get_backend():
-    return 'tf32' if _backend[0] == cabi.DX_GEMM_TCGEN05_TF32 else 'fp32'
+    return {v: k for k, v in BACKENDS.items()}[_backend[0]]
 
 
 def invalidate_packed_weights():
@@ -86,8 +92,24 @@ def _check_input(t, dtype=torch.float32):
 # ----------------------------------------------------------------------------------------------------------------------
 # packed weights (derived, cached, version-checked; the parameters keep the reference's own layout)
 # ----------------------------------------------------------------------------------------------------------------------
+class PackedWeight:
+    """fp32 packed layout [KW, N, K] + (bf16x3 backend) cached bf16 hi|lo planes of the same layout."""
+    __slots__ = ('w', 'planes', 'shape')
+
+    def __init__(self, w, planes):
+        self.w, self.planes, self.shape = w, planes, tuple(w.shape)
+
+
+def _make_packed(t):
+    planes = None
+    if _backend[0] == cabi.DX_GEMM_TCGEN05_BF16X3:
+        planes = torch.empty(2 * t.numel(), device=t.device, dtype=torch.bfloat16)
+        _call('dx_split_weight_planes', _p(t), _p(planes), t.numel(), _st())
+    return PackedWeight(t, planes)
+
+
 def packed(weight):
-    """weight [Cout, Cin, KW] or [Cout, Cin] -> (fwd [KW, Cout, Cin], dgrad [KW, Cin, Cout] taps flipped)."""
+    """weight [Cout, Cin, KW] or [Cout, Cin] -> (fwd [KW, Cout, Cin], dgrad [KW, Cin, Cout] taps flipped) PackedWeights."""
     w = weight.detach()
     key = id(weight)
     ver = (w.data_ptr(), w._version, _weights_epoch, _backend[0])
@@ -101,6 +123,7 @@ def packed(weight):
     dgrad = torch.empty(kw, cin, cout, device=w.device, dtype=torch.float32)
     rnd = 1 if _backend[0] == cabi.DX_GEMM_TCGEN05_TF32 else 0
     _call('dx_pack_conv_weight', _p(w), _p(fwd), _p(dgrad), cout, cin, kw, rnd, _st())
+    fwd, dgrad = _make_packed(fwd), _make_packed(dgrad)
     _pack_cache[key] = (ver, fwd, dgrad, weakref.ref(weight))
     return fwd, dgrad
 
@@ -108,10 +131,14 @@ def packed(weight):
 def conv_gemm(x, wp, bias, B, S, relu=False, relu_src=None, add_src=None, alpha=1.0, round_out=False, ldx=None):
     """x [B,S,Cin] (row stride ldx) · packed weight [KW,Cout,Cin] -> [B,S,Cout]"""
     kw, cout, cin = wp.shape
-    y = torch.empty(B, S, cout, device=wp.device, dtype=torch.float32)
+    dev = wp.w.device
+    y = torch.empty(B, S, cout, device=dev, dtype=torch.float32)
     rnd = 1 if (round_out and _backend[0] == cabi.DX_GEMM_TCGEN05_TF32) else 0
-    _call('dx_conv_gemm', _p(x), _p(wp), _p(bias), _p(relu_src), _p(add_src), _p(y), B, S, cin, cout, kw,
-          cin if ldx is None else ldx, cout, float(alpha), int(relu), rnd, -1, _st())
+    nbytes = lib().dx_conv_gemm_workspace(B, S, cin, cout, kw, int(wp.planes is not None), -1)
+    ws = torch.empty(nbytes + 256, device=dev, dtype=torch.uint8) if nbytes else None
+    _call('dx_conv_gemm', _p(x), _p(wp.w), _p(wp.planes), _p(bias), _p(relu_src), _p(add_src), _p(y), _p(ws),
+          ws.numel() if ws is not None else 0, B, S, cin, cout, kw, cin if ldx is None else ldx, cout, float(alpha),
+          int(relu), rnd, -1, _st())
     return y
 
 
@@ -171,24 +198,26 @@ class AttentionSubLayer(torch.autograd.Function):
         _call('dx_attention_fwd', _p(qkv), _p(lens), _p(att), _p(lse), B, S, nb_heads, dh, float(p_drop), seed_attn, _st())
         proj = conv_gemm(att, out_wp, out_b, 1, B * S)
         y, xhat, rstd = ln_fwd(proj, x, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p_drop, seed_in=seed_out)
-        ctx.save_for_backward(x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b, in_wd, out_wd)
+        ctx.save_for_backward(x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b)
+        ctx.packed = (in_wd, out_wd)
         ctx.cfg = (B, S, D, nb_heads, dh, float(p_drop), seed_attn, seed_out, in_w.shape, out_w.shape)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b, in_wd, out_wd = ctx.saved_tensors
+        x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b = ctx.saved_tensors
+        in_wd, out_wd = ctx.packed
         B, S, D, H, dh, p, seed_attn, seed_out, in_shape, out_shape = ctx.cfg
         dy = _check_input(dy)
         dv, dproj, dln_w, dln_b, _ = ln_bwd(dy, xhat, rstd, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p, seed_in=seed_out)
         datt = conv_gemm(dproj, out_wd, None, 1, B * S)
-        d_out_w, d_out_b = conv_wgrad(att, dproj, 1, B * S, D, D, 1, out_shape)
+        d_out_w, d_out_b = conv_wgrad(att, dproj, B, S, D, D, 1, out_shape)
         dqkv = torch.empty(B, S, 3 * D, device=dy.device, dtype=torch.float32)
         delta = torch.empty(B, H, S, device=dy.device, dtype=torch.float32)
         _call('dx_attention_bwd', _p(qkv), _p(lens), _p(att), _p(lse), _p(datt), _p(dqkv), _p(delta), B, S, H, dh, p,
               seed_attn, _st())
         dx = conv_gemm(dqkv, in_wd, None, 1, B * S, add_src=dv).view(B, S, D)
-        d_in_w, d_in_b = conv_wgrad(x, dqkv, 1, B * S, D, 3 * D, 1, in_shape)
+        d_in_w, d_in_b = conv_wgrad(x, dqkv, B, S, D, 3 * D, 1, in_shape)
         return dx, None, d_in_w, d_in_b, d_out_w, d_out_b, dln_w, dln_b, None, None
 
 
@@ -209,13 +238,15 @@ class ConvFFSubLayer(torch.autograd.Function):
             film = _check_input(film)
             assert film.shape[1] == 2 * D   # reference model.py:232
         y, xhat, rstd = ln_fwd(o, x, ln_w, ln_b, film, 2 * D, lens, B, S, D, p_in=p_drop, seed_in=seed)
-        ctx.save_for_backward(x, lens, h, xhat, rstd, ln_w, ln_b, film, w1d, w2d)
+        ctx.save_for_backward(x, lens, h, xhat, rstd, ln_w, ln_b, film)
+        ctx.packed = (w1d, w2d)
         ctx.cfg = (B, S, D, C, float(p_drop), seed, w1.shape, w2.shape)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, lens, h, xhat, rstd, ln_w, ln_b, film, w1d, w2d = ctx.saved_tensors
+        x, lens, h, xhat, rstd, ln_w, ln_b, film = ctx.saved_tensors
+        w1d, w2d = ctx.packed
         B, S, D, C, p, seed, w1_shape, w2_shape = ctx.cfg
         dy = _check_input(dy)
         dv, do, dln_w, dln_b, dfilm = ln_bwd(dy, xhat, rstd, ln_w, ln_b, film, 2 * D, lens, B, S, D, p_in=p, seed_in=seed,
@@ -238,17 +269,19 @@ class PreNet(torch.autograd.Function):
         x = torch.empty(B, T, M, device=mel.device, dtype=torch.float32)
         _call('dx_mask_transpose_bwd', _p(mel), _p(full), _p(x), B, T, M, _st())   # plain [B,M,T] -> [B,T,M]
         saved, cur = [x], x
-        seeds = []
+        seeds, wds = [], []
         for w, b, g, e in ((w0, b0, g0, e0), (w1, b1, g1, e1), (w2, b2, g2, e2)):
             wp, wd = packed(w)
             a = conv_gemm(cur, wp, b, B, T, relu=True)
             seed = next_seed() if p_drop > 0 else 0
             y, xhat, rstd = ln_fwd(a, None, g, e, None, 0, None, B, T, w.shape[0], p_out=p_drop, seed_out=seed)
-            saved += [a, xhat, rstd, g, e, wd]
+            saved += [a, xhat, rstd, g, e]
             seeds.append(seed)
+            wds.append(wd)
             cur = y
             saved.append(y)
         ctx.save_for_backward(*saved)
+        ctx.packed = wds
         ctx.cfg = (B, T, M, float(p_drop), seeds, (w0.shape, w1.shape, w2.shape))
         return cur
 
@@ -257,13 +290,14 @@ class PreNet(torch.autograd.Function):
         saved = ctx.saved_tensors
         B, T, M, p, seeds, shapes = ctx.cfg
         x = saved[0]
-        layers = [saved[1 + 7 * i: 8 + 7 * i] for i in range(3)]   # a, xhat, rstd, g, e, wd, y
+        layers = [saved[1 + 6 * i: 7 + 6 * i] for i in range(3)]   # a, xhat, rstd, g, e, y
         grads = [None] * 12
         d = _check_input(dy)
         for i in (2, 1, 0):
-            a, xhat, rstd, g, e, wd, _y = layers[i]
+            a, xhat, rstd, g, e, _y = layers[i]
+            wd = ctx.packed[i]
             cout, cin, kw = shapes[i]
-            inp = x if i == 0 else layers[i - 1][6]
+            inp = x if i == 0 else layers[i - 1][5]
             dpre, _, dg, de, _ = ln_bwd(d, xhat, rstd, g, e, None, 0, None, B, T, cout, relu_src=a, p_out=p, seed_out=seeds[i])
             dw, db = conv_wgrad(inp, dpre, B, T, cin, cout, kw, shapes[i])
             grads[4 * i: 4 * i + 4] = [dw, db, dg, de]
@@ -357,13 +391,15 @@ class FilmHead(torch.autograd.Function):
             for _ in range(nb):
                 outs.append(film[:, col: col + 2 * ch].contiguous())
                 col += 2 * ch
-        ctx.save_for_backward(h, graw, braw, post, gwd, bwd)
+        ctx.save_for_backward(h, graw, braw, post)
+        ctx.packed = (gwd, bwd)
         ctx.cfg = (B, NF, tuple(nb_blocks), tuple(channels), gw.shape, bw.shape)
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *douts):
-        h, graw, braw, post, gwd, bwd = ctx.saved_tensors
+        h, graw, braw, post = ctx.saved_tensors
+        gwd, bwd = ctx.packed
         B, NF, nb_blocks, channels, gshape, bshape = ctx.cfg
         parts, k = [], 0
         for nb, ch in zip(nb_blocks, channels):
@@ -395,13 +431,15 @@ class Linear(torch.autograd.Function):
         x = _check_input(x)
         wp, wd = packed(w)
         y = linear_rows(x, wp, b, relu=relu)
-        ctx.save_for_backward(x, y if relu else None, wd)
+        ctx.save_for_backward(x, y if relu else None)
+        ctx.packed = wd
         ctx.cfg = (relu, float(grad_in_scale), w.shape)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, wd = ctx.saved_tensors
+        x, y = ctx.saved_tensors
+        wd = ctx.packed
         relu, scale, wshape = ctx.cfg
         dy = _check_input(dy)
         R, cout, cin = x.shape[0], wshape[0], wshape[1]
@@ -457,13 +495,15 @@ class Predictor(torch.autograd.Function):
         NO = pw.shape[0]
         out = torch.empty(NO, B, L, device=x.device, dtype=torch.float32)
         _call('dx_narrow_linear_fwd', _p(y1), _p(pw), _p(pb), _p(lens), _p(out), B, L, C, NO, _st())
-        ctx.save_for_backward(x, lens, film, a0, y0, xh0, rs0, a1, y1, xh1, rs1, g0, e0, g1, e1, pw, w0d, w1d)
+        ctx.save_for_backward(x, lens, film, a0, y0, xh0, rs0, a1, y1, xh1, rs1, g0, e0, g1, e1, pw)
+        ctx.packed = (w0d, w1d)
         ctx.cfg = (B, L, D, C, NO, float(p_drop), s0, s1, w0.shape, w1.shape)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, lens, film, a0, y0, xh0, rs0, a1, y1, xh1, rs1, g0, e0, g1, e1, pw, w0d, w1d = ctx.saved_tensors
+        x, lens, film, a0, y0, xh0, rs0, a1, y1, xh1, rs1, g0, e0, g1, e1, pw = ctx.saved_tensors
+        w0d, w1d = ctx.packed
         B, L, D, C, NO, p, s0, s1, w0s, w1s = ctx.cfg
         dout = _check_input(dout)
         dy1 = torch.empty(B, L, C, device=dout.device, dtype=torch.float32)
@@ -540,19 +580,21 @@ class MelProjection(torch.autograd.Function):
         y = conv_gemm(x, wp, b, 1, B * T)
         mel = torch.empty(B, M, T, device=x.device, dtype=torch.float32)
         _call('dx_mask_transpose_fwd', _p(y), _p(lens), _p(mel), B, T, M, _st())
-        ctx.save_for_backward(x, lens, wd)
+        ctx.save_for_backward(x, lens)
+        ctx.packed = wd
         ctx.cfg = (B, T, D, M, w.shape)
         return mel
 
     @staticmethod
     def backward(ctx, dmel):
-        x, lens, wd = ctx.saved_tensors
+        x, lens = ctx.saved_tensors
+        wd = ctx.packed
         B, T, D, M, wshape = ctx.cfg
         dmel = _check_input(dmel)
         dy = torch.empty(B, T, M, device=dmel.device, dtype=torch.float32)
         _call('dx_mask_transpose_bwd', _p(dmel), _p(lens), _p(dy), B, T, M, _st())
         dx = conv_gemm(dy, wd, None, 1, B * T).view(B, T, D)
-        dw, db = conv_wgrad(x, dy, 1, B * T, D, M, 1, wshape)
+        dw, db = conv_wgrad(x, dy, B, T, D, M, 1, wshape)
         return dx, None, dw, db
 
 

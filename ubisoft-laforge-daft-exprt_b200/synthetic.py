@@ -49,10 +49,13 @@ def make_batch(batch_size, max_symbols, max_frames, n_speaker_ids, seed=0, n_mel
             over -= take
             i -= 1
         dur_int[b, :n] = d
-    # force the first (longest-input) row to define T_max == T exactly
+    # force the first (longest-input) row to define T_max == T exactly: spread the shortfall over its voiced symbols
     short = T - int(dur_int[0].sum())
     nz = np.nonzero(dur_int[0, :lens[0]])[0]
-    dur_int[0, nz[-1] if len(nz) else 0] += short
+    if len(nz) == 0:
+        nz = np.array([0])
+    dur_int[0, nz] += short // len(nz)
+    dur_int[0, nz[:short % len(nz)]] += 1
     out_lens = dur_int.sum(axis=1)
     # the reference requires T_max = max(output_lengths); keep the batch sorted by input length only
     dur_float = (dur_int.astype(np.float64) * HOP_LENGTH / SAMPLING_RATE).astype(np.float32)
