@@ -33,7 +33,7 @@ def _worker(rank, world, port, ret):
     model(x).pow(2).mean().backward()
     assert sync.grads_attached()                        # autograd accumulated into the flat buffer in place
     sync.all_reduce_mean()
-    ret[rank] = (sync.flat.clone(), torch.cat([p.data.reshape(-1) for p in model.parameters()]))
+    ret[rank] = (torch.cat([p.grad.reshape(-1) for p in model.parameters()]), torch.cat([p.data.reshape(-1) for p in model.parameters()]))
     dist.destroy_process_group()
 
 

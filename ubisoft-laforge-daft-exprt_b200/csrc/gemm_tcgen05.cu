@@ -1,7 +1,8 @@
 // tcgen05 / TMEM / TMA implementation of the channels-last Conv1d / Linear GEMMs (forward, dgrad, wgrad) for sm_100a.
 //
 //   forward/dgrad:  y[b, s, n] = epi( alpha * sum_{tap < KW} sum_{c < Cin} x[b, s + tap - pad, c] * w[tap][n][c] + bias[n] )
-//   wgrad:          part[split][tap][co][ci] = sum_{b in split} sum_s dy[b, s, co] * x[b, s + tap - pad, ci]
+//   wgrad:          part[split][tap][co][ci] = sum_{(b, s) in split} dy[b, s, co] * x[b, s + tap - pad, ci]
+//                   (same bf16 row planes as forward/dgrad, consumed as MN-major UMMA operands: K = rows)
 //
 // im2col-free: the KW taps are KW shifted K-slices of the same activation tensor.  Operand tiles are fetched by 3-D TMA
 // tensor maps whose s-coordinate is simply offset by (tap - pad); rows that fall outside [0, S) are zero-filled by the TMA
@@ -23,6 +24,7 @@
 //             128B-swizzled smem staging -> TMA store (clips partial tiles)
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -89,9 +91,16 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor: fp32 accumulate, both operands K-major, M x N tile; fmt 1 = bf16 (kind::f16), 2 = tf32 (kind::tf32)
-__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
-    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major operand tile (K = rows): 64-element (128-byte) MN chunks, each chunk = [K rows][128 B] with SWIZZLE_128B;
+// LBO = distance between MN chunks (8192 B: one 64-row TMA box), SBO = distance between 8-row K groups (1024 B).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: fp32 accumulate, M x N tile; fmt 1 = bf16 (kind::f16), 2 = tf32 (kind::tf32); mn_major = 1 when
+// both operands are MN-major (wgrad), 0 when both are K-major
+__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N, int mn_major = 0) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)mn_major << 15) | ((uint32_t)mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 template <int PREC>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -132,6 +141,7 @@ struct TcParams {
     int nsplit;                                         // WGRAD: batch ranges
     float alpha;
     int relu, round_tf32;
+    int debug;   // bring-up bisection mask (DX_TC_DEBUG): 1 no MMA, 2 no TMA loads, 4 no TMEM loads, 8 no TMA store, 16 no TMEM alloc
 };
 
 struct TileCoord {
@@ -194,8 +204,12 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (p.debug & 16) {
+            if (lane == 0) *tmem_slot_ptr = 0u;
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -213,20 +227,31 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
                         const uint32_t bar = full0 + 8 * stage;
                         const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + PLANES * TILE_BYTES;
+                        if (p.debug & 2) { mbar_arrive(bar); if (++stage == NSTAGE) { stage = 0; phase ^= 1; } continue; }
                         mbar_expect_tx(bar, STAGE_BYTES);
                         int a0, a1, a2, b0, b1, b2;
                         if constexpr (MODE == MODE_CONV) {      // o = tap
                             a0 = kc * TKB; a1 = t.a1 + o - pad; a2 = t.a2;
                             b0 = kc * TKB; b1 = t.b1; b2 = o;
-                        } else {                                // o = utterance inside this split
-                            a0 = kc * TKB; a1 = o; a2 = t.a2;
-                            b0 = kc * TKB + t.tap - pad; b1 = o; b2 = t.b2;
+                        } else {                                // o = utterance; K = 64 rows of s; operands are (c, s, b) boxes
+                            a0 = t.a2; a1 = kc * TKB; a2 = o;
+                            b0 = t.b2; b1 = kc * TKB + t.tap - pad; b2 = o;
                         }
-                        tma_load_3d(sa, &map_a_hi, bar, a0, a1, a2);
-                        tma_load_3d(sb, &map_b_hi, bar, b0, b1, b2);
-                        if constexpr (PLANES == 2) {
-                            tma_load_3d(sa + TILE_BYTES, &map_a_lo, bar, a0, a1, a2);
-                            tma_load_3d(sb + TILE_BYTES, &map_b_lo, bar, b0, b1, b2);
+                        if constexpr (MODE == MODE_CONV) {
+                            tma_load_3d(sa, &map_a_hi, bar, a0, a1, a2);
+                            tma_load_3d(sb, &map_b_hi, bar, b0, b1, b2);
+                            if constexpr (PLANES == 2) {
+                                tma_load_3d(sa + TILE_BYTES, &map_a_lo, bar, a0, a1, a2);
+                                tma_load_3d(sb + TILE_BYTES, &map_b_lo, bar, b0, b1, b2);
+                            }
+                        } else {                                // two 64-column MN chunks per 128-wide tile
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                tma_load_3d(sa + j * 8192, &map_a_hi, bar, a0 + 64 * j, a1, a2);
+                                tma_load_3d(sb + j * 8192, &map_b_hi, bar, b0 + 64 * j, b1, b2);
+                                tma_load_3d(sa + TILE_BYTES + j * 8192, &map_a_lo, bar, a0 + 64 * j, a1, a2);
+                                tma_load_3d(sb + TILE_BYTES + j * 8192, &map_b_lo, bar, b0 + 64 * j, b1, b2);
+                            }
                         }
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                     }
@@ -235,7 +260,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(PREC == PREC_TF32 ? 2 : 1, TM, TN);
+            constexpr uint32_t idesc = umma_idesc(PREC == PREC_TF32 ? 2 : 1, TM, TN, MODE == MODE_WGRAD ? 1 : 0);
+            // descriptor step per K=16 (bf16) / K=8 (tf32) instruction, in 16-byte units:
+            //   K-major: 32 bytes along the 128-byte row;  MN-major: 16 rows of 128 bytes
+            constexpr uint32_t kstep = MODE == MODE_WGRAD ? (16 * 128) >> 4 : 2;
             int stage = 0, phase = 0, it = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 const TileCoord t = tile_coord<MODE>(p, tile);
@@ -248,20 +276,23 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                     mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + PLANES * TILE_BYTES;
-                    const uint64_t a_hi = umma_desc_k_sw128(sa), b_hi = umma_desc_k_sw128(sb);
+                    const uint64_t a_hi = MODE == MODE_WGRAD ? umma_desc_mn_sw128(sa) : umma_desc_k_sw128(sa);
+                    const uint64_t b_hi = MODE == MODE_WGRAD ? umma_desc_mn_sw128(sb) : umma_desc_k_sw128(sb);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {   // 32 bytes of K per instruction (+2 in 16-byte descriptor units)
-                        umma<PREC>(tmem_d, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (k | kk) != 0);
+                    for (int kk = 0; kk < ((p.debug & 1) ? 0 : 4); ++kk) {
+                        umma<PREC>(tmem_d, a_hi + kstep * kk, b_hi + kstep * kk, idesc, (k | kk) != 0);
                         if constexpr (PLANES == 2) {
-                            const uint64_t a_lo = umma_desc_k_sw128(sa + TILE_BYTES), b_lo = umma_desc_k_sw128(sb + TILE_BYTES);
-                            umma<PREC>(tmem_d, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1u);
-                            umma<PREC>(tmem_d, a_hi + 2 * kk, b_lo + 2 * kk, idesc, 1u);
+                            const uint64_t a_lo = a_hi + (TILE_BYTES >> 4), b_lo = b_hi + (TILE_BYTES >> 4);
+                            umma<PREC>(tmem_d, a_lo + kstep * kk, b_hi + kstep * kk, idesc, 1u);
+                            umma<PREC>(tmem_d, a_hi + kstep * kk, b_lo + kstep * kk, idesc, 1u);
                         }
                     }
-                    umma_commit(empty0 + 8 * stage);          // frees the smem stage when these MMAs retire
+                    if (p.debug & 1) mbar_arrive(empty0 + 8 * stage);
+                    else umma_commit(empty0 + 8 * stage);     // frees the smem stage when these MMAs retire
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tfull0 + 8 * acc);                // accumulator complete -> epilogue
+                if (p.debug & 1) mbar_arrive(tfull0 + 8 * acc);
+                else umma_commit(tfull0 + 8 * acc);           // accumulator complete -> epilogue
             }
         }
     } else {
@@ -281,7 +312,12 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
 #pragma unroll 1
             for (int j = 0; j < TN / 32; ++j) {
                 uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN + j * 32, v);
+                if (p.debug & 4) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0u;
+                } else {
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN + j * 32, v);
+                }
                 if (j == TN / 32 - 1) {   // all TMEM reads of this accumulator are done: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
@@ -319,7 +355,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                 }
                 fence_async_smem();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (et == 0) {
+                if (et == 0 && !(p.debug & 8)) {
                     tma_store_3d(&map_y, sOut + (j & 1) * OUT_BYTES, nb, t.o1, t.o2);
                     tma_store_commit();
                 }
@@ -329,7 +365,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 1 && !(p.debug & 16)) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
@@ -452,6 +488,15 @@ int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, 
     return check_launch("gemm_tc");
 }
 
+int tc_debug_mask() {
+    static int mask = -1;
+    if (mask < 0) {
+        const char* e = getenv("DX_TC_DEBUG");
+        mask = e ? atoi(e) : 0;
+    }
+    return mask;
+}
+
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 inline int round8(int x) { return (x + 7) & ~7; }
 
@@ -488,6 +533,7 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     p.num_tiles = p.tiles_m_per_b * a.B * p.tiles_n;
     p.nsplit = 1;
     p.alpha = a.alpha; p.relu = a.relu; p.round_tf32 = a.round_tf32;
+    p.debug = tc_debug_mask();
     CUtensorMap mxh, mxl, mwh, mwl, my;
     int rc;
     if ((rc = make_map_3d(&my, a.y, 4, a.Cout, a.S, a.B, (uint64_t)a.ldy * 4, (uint64_t)a.S * a.ldy * 4, 32, TM, 1))) return rc;
@@ -529,7 +575,7 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
 
 // ---- wgrad -----------------------------------------------------------------------------------------------------------
 bool conv_wgrad_tc_supported(const ConvWgradArgs& a) {
-    if (a.Cin % 4 != 0 || a.Cout % 4 != 0 || a.ldx % 4 != 0) return false;
+    if (a.Cin % 8 != 0 || a.Cout % 8 != 0 || a.ldx % 4 != 0) return false;   // 16-byte pitches of the bf16 row planes
     if (a.Cin < 16 || a.Cout < 16) return false;
     if (((uintptr_t)a.x | (uintptr_t)a.dy) & 15) return false;
     return get_encode() != nullptr;
@@ -551,10 +597,9 @@ static int wgrad_nsplit(const ConvWgradArgs& a) {
 }
 
 size_t conv_wgrad_tc_workspace(const ConvWgradArgs& a) {
-    const int Sp = round8(a.S);
-    const size_t dyT = (size_t)a.Cout * a.B * Sp, xT = (size_t)a.Cin * a.B * Sp;
+    const size_t dye = (size_t)a.B * a.S * a.Cout, xe = (size_t)a.B * a.S * a.Cin;
     const size_t part = (size_t)wgrad_nsplit(a) * a.KW * a.Cout * a.Cin * 4;
-    return 2 * align256(dyT * 2) + 2 * align256(xT * 2) + align256(part) + 256;
+    return 2 * align256(dye * 2) + 2 * align256(xe * 2) + align256(part) + 256;
 }
 
 __global__ void wgrad_reduce_tc_kernel(const float* __restrict__ part, float* __restrict__ dw, int nsplit, int KW, int Cout,
@@ -574,23 +619,22 @@ __global__ void wgrad_reduce_tc_kernel(const float* __restrict__ part, float* __
 int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
     const size_t need = conv_wgrad_tc_workspace(a);
     DX_REQUIRE(a.workspace && a.workspace_bytes >= need, "conv_wgrad_tc: workspace %zu < %zu bytes", a.workspace_bytes, need);
-    const int Sp = round8(a.S);
     const int nsplit = wgrad_nsplit(a);
-    const size_t dyT = (size_t)a.Cout * a.B * Sp, xT = (size_t)a.Cin * a.B * Sp;
+    const size_t dye = (size_t)a.B * a.S * a.Cout, xe = (size_t)a.B * a.S * a.Cin;
     uint8_t* ws = (uint8_t*)(((uintptr_t)a.workspace + 255) & ~(uintptr_t)255);
     __nv_bfloat16* dh = (__nv_bfloat16*)ws;
-    __nv_bfloat16* dl = (__nv_bfloat16*)(ws + align256(dyT * 2));
-    __nv_bfloat16* xh = (__nv_bfloat16*)(ws + 2 * align256(dyT * 2));
-    __nv_bfloat16* xl = (__nv_bfloat16*)(ws + 2 * align256(dyT * 2) + align256(xT * 2));
-    float* part = (float*)(ws + 2 * align256(dyT * 2) + 2 * align256(xT * 2));
+    __nv_bfloat16* dl = (__nv_bfloat16*)(ws + align256(dye * 2));
+    __nv_bfloat16* xh = (__nv_bfloat16*)(ws + 2 * align256(dye * 2));
+    __nv_bfloat16* xl = (__nv_bfloat16*)(ws + 2 * align256(dye * 2) + align256(xe * 2));
+    float* part = (float*)(ws + 2 * align256(dye * 2) + 2 * align256(xe * 2));
     int rc;
     {
         dim3 g1(ceil_div(a.S, 64), ceil_div(a.Cout, 64), a.B);
-        split_planes_kernel<<<g1, 256, 0, st>>>(a.dy, a.Cout, a.S, a.Cout, Sp, nullptr, nullptr, dh, dl, a.B);
-        if ((rc = check_launch("split_planes(dy^T)"))) return rc;
+        split_planes_kernel<<<g1, 256, 0, st>>>(a.dy, a.Cout, a.S, a.Cout, 0, dh, dl, nullptr, nullptr, a.B);
+        if ((rc = check_launch("split_planes(dy)"))) return rc;
         dim3 g2(ceil_div(a.S, 64), ceil_div(a.Cin, 64), a.B);
-        split_planes_kernel<<<g2, 256, 0, st>>>(a.x, a.ldx, a.S, a.Cin, Sp, nullptr, nullptr, xh, xl, a.B);
-        if ((rc = check_launch("split_planes(x^T)"))) return rc;
+        split_planes_kernel<<<g2, 256, 0, st>>>(a.x, a.ldx, a.S, a.Cin, 0, xh, xl, nullptr, nullptr, a.B);
+        if ((rc = check_launch("split_planes(x)"))) return rc;
     }
     TcParams p;
     p.bias = nullptr; p.relu_src = nullptr; p.add_src = nullptr;
@@ -601,12 +645,14 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
     p.num_tiles = p.tiles_m_per_b * p.tiles_n * a.KW * nsplit;
     p.k_chunks = ceil_div(a.S, Cfg<PREC_BF16X3>::TKB);
     p.alpha = 1.f; p.relu = 0; p.round_tf32 = 0;
+    p.debug = tc_debug_mask();
     CUtensorMap mah, mal, mbh, mbl, my;
-    const uint64_t s1 = (uint64_t)Sp * 2, s2 = (uint64_t)a.B * Sp * 2;
-    if ((rc = make_map_3d(&mah, dh, 2, a.S, a.B, a.Cout, s1, s2, 64, 1, TM))) return rc;
-    if ((rc = make_map_3d(&mal, dl, 2, a.S, a.B, a.Cout, s1, s2, 64, 1, TM))) return rc;
-    if ((rc = make_map_3d(&mbh, xh, 2, a.S, a.B, a.Cin, s1, s2, 64, 1, TN))) return rc;
-    if ((rc = make_map_3d(&mbl, xl, 2, a.S, a.B, a.Cin, s1, s2, 64, 1, TN))) return rc;
+    // (c, s, b) maps over the row planes; box = 64 channels (128 B) x 64 rows: one MN chunk of an MN-major operand tile
+    const uint64_t d1 = (uint64_t)a.Cout * 2, d2 = (uint64_t)a.S * a.Cout * 2, x1 = (uint64_t)a.Cin * 2, x2 = (uint64_t)a.S * a.Cin * 2;
+    if ((rc = make_map_3d(&mah, dh, 2, a.Cout, a.S, a.B, d1, d2, 64, 64, 1))) return rc;
+    if ((rc = make_map_3d(&mal, dl, 2, a.Cout, a.S, a.B, d1, d2, 64, 64, 1))) return rc;
+    if ((rc = make_map_3d(&mbh, xh, 2, a.Cin, a.S, a.B, x1, x2, 64, 64, 1))) return rc;
+    if ((rc = make_map_3d(&mbl, xl, 2, a.Cin, a.S, a.B, x1, x2, 64, 64, 1))) return rc;
     if ((rc = make_map_3d(&my, part, 4, a.Cin, a.Cout, (uint64_t)nsplit * a.KW, (uint64_t)a.Cin * 4, (uint64_t)a.Cout * a.Cin * 4, 32, TM, 1)))
         return rc;
     if ((rc = launch<PREC_BF16X3, MODE_WGRAD>(mah, mal, mbh, mbl, my, p, st))) return rc;

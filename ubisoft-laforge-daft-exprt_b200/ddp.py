@@ -10,6 +10,8 @@ issued once per optimiser step, and the optimiser is one fused kernel over the s
 import torch
 import torch.distributed as dist
 
+ALIGN = 64   # elements (256 bytes of fp32)
+
 
 class FlatGradSync:
     """Makes all gradients views of one flat buffer and averages it across ranks with one collective."""
@@ -20,13 +22,16 @@ class FlatGradSync:
             raise ValueError('no trainable parameters')
         dev, dt = self.params[0].device, self.params[0].dtype
         self.numel = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(self.numel, device=dev, dtype=dt)
-        self.group = process_group
-        off = 0
+        # every slot starts on a 256-byte boundary: the kernels use 16-byte vector loads on parameters and gradients
+        self.offsets, off = [], 0
         for p in self.params:
-            n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)   # autograd accumulates in place into existing .grad
-            off += n
+            self.offsets.append(off)
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.padded_numel = off
+        self.flat = torch.zeros(self.padded_numel, device=dev, dtype=dt)
+        self.group = process_group
+        for p, off in zip(self.params, self.offsets):
+            p.grad = self.flat[off:off + p.numel()].view_as(p)   # autograd accumulates in place into existing .grad
 
     def zero_grad(self):
         self.flat.zero_()
@@ -45,11 +50,9 @@ class FlatGradSync:
     def grads_attached(self):
         """True while every p.grad still aliases the flat buffer (an optimiser's zero_grad(set_to_none=True) breaks it)."""
         base = self.flat.data_ptr()
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             if p.grad is None or p.grad.data_ptr() != base + off * self.flat.element_size():
                 return False
-            off += p.numel()
         return True
 
 
@@ -70,14 +73,12 @@ class FlatAdam:
         self.params = sync.params
         assert [id(p) for p in self.params] == [id(p) for p in params if p.requires_grad]
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
-        self.flat_p = torch.empty_like(sync.flat)
-        off = 0
+        self.flat_p = torch.zeros_like(sync.flat)
         with torch.no_grad():
-            for p in self.params:
+            for p, off in zip(self.params, sync.offsets):
                 n = p.numel()
                 self.flat_p[off:off + n].copy_(p.data.reshape(-1))
                 p.data = self.flat_p[off:off + n].view_as(p)
-                off += n
         self.m = torch.zeros_like(self.flat_p)
         self.v = torch.zeros_like(self.flat_p)
         self.step_count = 0
