@@ -39,6 +39,8 @@ uint64_t dx_launch_count(void);
 int dx_device_check(void);
 int dx_set_gemm_backend(int backend);
 int dx_get_gemm_backend(void);
+/* bring-up aid: device buffer of 4*256 int64 receiving clock64() traces of CTA 0 of the tensor-core GEMM (NULL = off) */
+int dx_debug_set_trace(void* buf);
 
 /* ---- Conv1d / Linear as channels-last GEMMs --------------------------------------------------------------------------
  * replaces nn.Conv1d inside ConvNorm1D (model.py:82,86-94) and nn.Linear inside LinearNorm (model.py:63,66-72), incl. the

@@ -61,6 +61,7 @@ int dx_set_gemm_backend(int backend) {
     return DX_OK;
 }
 int dx_get_gemm_backend(void) { return g_backend; }
+int dx_debug_set_trace(void* buf) { set_tc_trace((long long*)buf); return DX_OK; }
 
 int dx_pack_conv_weight(const float* w, float* fwd, float* dgrad, int Cout, int Cin, int KW, int round_tf32, void* stream) {
     return pack_conv_weight(w, fwd, dgrad, Cout, Cin, KW, round_tf32, ST(stream));

@@ -141,6 +141,7 @@ struct TcParams {
     int nsplit;                                         // WGRAD: batch ranges
     float alpha;
     int relu, round_tf32;
+    long long* trace;   // optional [4][256] clock64 trace of block 0 (DX_TC_TRACE), else nullptr
     int debug;   // bring-up bisection mask (DX_TC_DEBUG): 1 no MMA, 2 no TMA loads, 4 no TMEM loads, 8 no TMA store, 16 no TMEM alloc
 };
 
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
 
     if (warp == 0) {
         if (lane == 0) {
-            int stage = 0, phase = 0;
+            int stage = 0, phase = 0, gk = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord t = tile_coord<MODE>(p, tile);
                 for (int k = t.k_begin; k < t.k_end; ++k) {
@@ -253,6 +254,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                                 tma_load_3d(sb + TILE_BYTES + j * 8192, &map_b_lo, bar, b0 + 64 * j, b1, b2);
                             }
                         }
+                        if (p.trace && blockIdx.x == 0 && gk < 256) p.trace[0 * 256 + gk] = clock64();
+                        ++gk;
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
             // descriptor step per K=16 (bf16) / K=8 (tf32) instruction, in 16-byte units:
             //   K-major: 32 bytes along the 128-byte row;  MN-major: 16 rows of 128 bytes
             constexpr uint32_t kstep = MODE == MODE_WGRAD ? (16 * 128) >> 4 : 2;
-            int stage = 0, phase = 0, it = 0;
+            int stage = 0, phase = 0, it = 0, gk = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 const TileCoord t = tile_coord<MODE>(p, tile);
                 const int k_iters = t.k_end - t.k_begin;
@@ -274,6 +277,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                 const uint32_t tmem_d = tmem_base + acc * TN;
                 for (int k = 0; k < k_iters; ++k) {
                     mbar_wait(full0 + 8 * stage, phase);
+                    if (p.trace && blockIdx.x == 0 && gk < 256) p.trace[1 * 256 + gk] = clock64();
+                    ++gk;
                     tc_fence_after();
                     const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + PLANES * TILE_BYTES;
                     const uint64_t a_hi = MODE == MODE_WGRAD ? umma_desc_mn_sw128(sa) : umma_desc_k_sw128(sa);
@@ -305,6 +310,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
             const TileCoord t = tile_coord<MODE>(p, tile);
             const int acc = it & 1, acc_phase = (it >> 1) & 1;
             mbar_wait(tfull0 + 8 * acc, acc_phase);
+            if (p.trace && blockIdx.x == 0 && et == 0 && it < 256) p.trace[2 * 256 + it] = clock64();
             tc_fence_after();
             const int s = t.o1 + row;
             const bool row_ok = MODE == MODE_CONV && s < p.S;
@@ -326,22 +332,64 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                 const int nb = t.o0 + j * 32;
                 float o[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float f = __uint_as_float(v[i]);
-                    if constexpr (MODE == MODE_CONV) {
-                        const int n = nb + i;
-                        f *= p.alpha;
-                        if (n < p.Cout) {
-                            if (p.bias) f += __ldg(p.bias + n);
-                            if (p.relu) f = fmaxf(f, 0.f);
-                            if (row_ok) {
-                                if (p.relu_src) f = __ldg(p.relu_src + grow * p.Cout + n) > 0.f ? f : 0.f;
-                                if (p.add_src) f += __ldg(p.add_src + grow * p.ldy + n);
+                for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]);
+                if constexpr (MODE == MODE_CONV) {
+                    // every condition below is warp-uniform except row_ok; columns >= Cout are clipped by the TMA store
+                    const bool full = nb + 32 <= p.Cout;
+                    if (p.alpha != 1.f) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] *= p.alpha;
+                    }
+                    if (p.bias) {
+                        if (full) {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + c);
+                                o[4 * c] += bv.x; o[4 * c + 1] += bv.y; o[4 * c + 2] += bv.z; o[4 * c + 3] += bv.w;
                             }
-                            if (p.round_tf32) f = round_tf32(f);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (nb + i < p.Cout) o[i] += __ldg(p.bias + nb + i);
                         }
                     }
-                    o[i] = f;
+                    if (p.relu) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = fmaxf(o[i], 0.f);
+                    }
+                    if (p.relu_src && row_ok) {
+                        const float* src = p.relu_src + grow * p.Cout + nb;
+                        if (full) {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const float4 m = __ldg(reinterpret_cast<const float4*>(src) + c);
+                                o[4 * c] = m.x > 0.f ? o[4 * c] : 0.f; o[4 * c + 1] = m.y > 0.f ? o[4 * c + 1] : 0.f;
+                                o[4 * c + 2] = m.z > 0.f ? o[4 * c + 2] : 0.f; o[4 * c + 3] = m.w > 0.f ? o[4 * c + 3] : 0.f;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (nb + i < p.Cout) o[i] = __ldg(src + i) > 0.f ? o[i] : 0.f;
+                        }
+                    }
+                    if (p.add_src && row_ok) {
+                        const float* src = p.add_src + grow * p.ldy + nb;
+                        if (full) {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const float4 a4 = __ldg(reinterpret_cast<const float4*>(src) + c);
+                                o[4 * c] += a4.x; o[4 * c + 1] += a4.y; o[4 * c + 2] += a4.z; o[4 * c + 3] += a4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (nb + i < p.Cout) o[i] += __ldg(src + i);
+                        }
+                    }
+                    if (p.round_tf32) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = round_tf32(o[i]);
+                    }
                 }
                 // staging buffer (j & 1): the TMA store that last read it (2 chunks ago) must have finished reading
                 if (et == 0) tma_store_wait_read<1>();
@@ -360,6 +408,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                     tma_store_commit();
                 }
             }
+            if (p.trace && blockIdx.x == 0 && et == 0 && it < 256) p.trace[3 * 256 + it] = clock64();
         }
         if (et == 0) tma_store_wait_all();
     }
@@ -488,6 +537,8 @@ int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, 
     return check_launch("gemm_tc");
 }
 
+long long* g_trace = nullptr;
+
 int tc_debug_mask() {
     static int mask = -1;
     if (mask < 0) {
@@ -503,6 +554,7 @@ inline int round8(int x) { return (x + 7) & ~7; }
 }  // namespace
 
 void set_tc_precision(int tf32) { g_prec = tf32 ? PREC_TF32 : PREC_BF16X3; }
+void set_tc_trace(long long* buf) { g_trace = buf; }
 
 int split_weight_planes(const float* w, void* planes, size_t n, cudaStream_t st) {
     __nv_bfloat16* hi = (__nv_bfloat16*)planes;
@@ -534,6 +586,7 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     p.nsplit = 1;
     p.alpha = a.alpha; p.relu = a.relu; p.round_tf32 = a.round_tf32;
     p.debug = tc_debug_mask();
+    p.trace = g_trace;
     CUtensorMap mxh, mxl, mwh, mwl, my;
     int rc;
     if ((rc = make_map_3d(&my, a.y, 4, a.Cout, a.S, a.B, (uint64_t)a.ldy * 4, (uint64_t)a.S * a.ldy * 4, 32, TM, 1))) return rc;
@@ -646,6 +699,7 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
     p.k_chunks = ceil_div(a.S, Cfg<PREC_BF16X3>::TKB);
     p.alpha = 1.f; p.relu = 0; p.round_tf32 = 0;
     p.debug = tc_debug_mask();
+    p.trace = nullptr;
     CUtensorMap mah, mal, mbh, mbl, my;
     // (c, s, b) maps over the row planes; box = 64 channels (128 B) x 64 rows: one MN chunk of an MN-major operand tile
     const uint64_t d1 = (uint64_t)a.Cout * 2, d2 = (uint64_t)a.S * a.Cout * 2, x1 = (uint64_t)a.Cin * 2, x2 = (uint64_t)a.S * a.Cin * 2;

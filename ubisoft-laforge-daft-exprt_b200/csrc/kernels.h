@@ -47,6 +47,7 @@ int pack_conv_weight(const float* w, float* fwd, float* dgrad, int Cout, int Cin
 
 // tcgen05 / TMEM / TMA path (gemm_tcgen05.cu)
 void set_tc_precision(int tf32);
+void set_tc_trace(long long* buf);
 int split_weight_planes(const float* w, void* planes, size_t n, cudaStream_t st);
 size_t conv_gemm_tc_workspace(const ConvGemmArgs& a);
 bool conv_gemm_tc_supported(const ConvGemmArgs& a);
