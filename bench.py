@@ -152,16 +152,19 @@ def time_dominant_kernel(dev, iters=20):
     flush = torch.empty(512 * 1024 * 1024 // 4, device=dev)
     for _ in range(3):
         ops.conv_gemm(x, wp, bias, B, S, relu=True)
-    ms = []
+    torch.cuda.synchronize()
+    # enqueue everything first (the 512 MB flush kernels give the host time to run ahead), then read the events:
+    # e0 -> e1 brackets only this library's kernels of one launch (operand split + tcgen05 GEMM)
+    evs = []
     for _ in range(iters):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         ops.conv_gemm(x, wp, bias, B, S, relu=True)
         e1.record()
-        e1.synchronize()
-        ms.append(e0.elapsed_time(e1))
-    ms.sort()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in evs)
     t = sum(ms[: max(1, len(ms) // 2)]) / max(1, len(ms) // 2) * 1e-3
     flops = 2.0 * B * S * Cout * Cin * KW
     return flops, t
