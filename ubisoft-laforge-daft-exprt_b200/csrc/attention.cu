@@ -346,12 +346,18 @@ int attention_fwd(const AttnArgs& a, cudaStream_t st) {
     }
 }
 
-int attention_bwd(const AttnArgs& a, cudaStream_t st) {
+int attention_bwd_prepare(const AttnArgs& a, cudaStream_t st) {
     const int total = a.B * a.S * a.H;
     attn_delta_kernel<<<ceil_div(total, 256), 256, 0, st>>>(a);
     int rc = check_launch("attn_delta");
     if (rc) return rc;
     DX_CUDA(cudaMemsetAsync(a.dqkv, 0, (size_t)a.B * a.S * 3 * a.H * a.dh * sizeof(float), st));
+    return DX_OK;
+}
+
+int attention_bwd(const AttnArgs& a, cudaStream_t st) {
+    int rc = attention_bwd_prepare(a, st);
+    if (rc) return rc;
     switch (a.dh) {
         case 16: return launch_bwd<16>(a, st);
         case 32: return launch_bwd<32>(a, st);

@@ -1,0 +1,488 @@
+// Tensor-core flash attention (forward) with fp32-grade accuracy: every operand of Q·K^T and P·V is split into bf16
+// hi + lo and each product is formed as hi*hi + lo*hi + hi*lo with fp32 accumulation (the same "bf16x3" scheme as the
+// tcgen05 GEMMs), so the result matches the reference's fp32 nn.MultiheadAttention math path (model.py:182-186) to ~1e-5
+// while running on the tensor pipe.  Scores, softmax state and the output accumulator never leave registers.
+//
+// CTA = 128 threads = 4 warps; one CTA per (64-query tile, head, utterance); each warp owns 16 query rows and walks the
+// valid keys in tiles of 64.  `mma.sync.m16n8k16` (register-resident flash-attention-2 dataflow): the score accumulator's
+// C-fragment layout is re-used directly as the A-fragment of the P·V product, so P never touches shared memory.
+// K is staged in smem as [key][d] (B-operand of Q·K^T), V transposed as [d][key] (B-operand of P·V), both as bf16 hi|lo.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dx {
+
+namespace {
+
+constexpr int QT = 64, KT = 64;
+
+__device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// (x, y) -> packed bf16 pairs: hi = bf16(x), lo = bf16(x - hi)
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat16 xh = __float2bfloat16_rn(x), yh = __float2bfloat16_rn(y);
+    const __nv_bfloat16 xl = __float2bfloat16_rn(x - __bfloat162float(xh)), yl = __float2bfloat16_rn(y - __bfloat162float(yh));
+    hi = (uint32_t)__bfloat16_as_ushort(xh) | ((uint32_t)__bfloat16_as_ushort(yh) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(xl) | ((uint32_t)__bfloat16_as_ushort(yl) << 16);
+}
+
+template <int DH>
+__global__ void __launch_bounds__(128) attn_fwd_mma_kernel(AttnArgs p) {
+    constexpr int KS = DH / 16;       // k-steps of Q·K^T
+    constexpr int ND = DH / 8;        // n-tiles of the output
+    constexpr int KP = DH + 8;        // padded row of the K tile   ([key][d])
+    constexpr int VP = KT + 8;        // padded row of the V^T tile ([d][key])
+    __shared__ __align__(16) __nv_bfloat16 Ks[2][KT][KP];
+    __shared__ __align__(16) __nv_bfloat16 Vt[2][DH][VP];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int q0 = blockIdx.x * QT, h = blockIdx.y, b = blockIdx.z;
+    const int D = p.H * DH, ld = 3 * D;
+    const int len = min((int)p.lens[b], p.S);
+    const float* base = p.qkv + (size_t)b * p.S * ld + h * DH;
+    float* ctx = p.ctx + (size_t)b * p.S * D + h * DH;
+    float* lse = p.lse + ((size_t)b * p.H + h) * p.S;
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;   // this lane's two query rows
+
+    if (q0 >= len) {   // whole tile is padding: zeros (their only consumer masks them, model.py:259)
+        for (int idx = tid; idx < QT * DH; idx += 128) {
+            const int r = idx / DH, c = idx % DH;
+            if (q0 + r < p.S) ctx[(size_t)(q0 + r) * D + c] = 0.f;
+        }
+        if (tid < QT && q0 + tid < p.S) lse[q0 + tid] = 0.f;
+        return;
+    }
+
+    // Q fragments (scaled by 1/sqrt(dh), an exact power of two for dh = 16, 64), bf16 hi/lo, kept in registers
+    const float scale = rsqrtf((float)DH);
+    uint32_t qh[KS][4], ql[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {      // columns 2t (+8*half)
+            const int c = ks * 16 + 2 * t + 8 * half;
+            float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
+            if (r0 < len) v0 = *reinterpret_cast<const float2*>(base + (size_t)r0 * ld + c);
+            if (r1 < len) v1 = *reinterpret_cast<const float2*>(base + (size_t)r1 * ld + c);
+            split_pair(v0.x * scale, v0.y * scale, qh[ks][2 * half], ql[ks][2 * half]);
+            split_pair(v1.x * scale, v1.y * scale, qh[ks][2 * half + 1], ql[ks][2 * half + 1]);
+        }
+    }
+
+    float o[ND][4];
+#pragma unroll
+    for (int n = 0; n < ND; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    const float inv_keep = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
+    const unsigned long long bh = ((unsigned long long)b * p.H + h) * (unsigned long long)p.S;
+
+    for (int k0 = 0; k0 < len; k0 += KT) {
+        __syncthreads();   // previous tile fully consumed
+        // K tile: [key][d], coalesced float4 reads
+        for (int idx = tid; idx < KT * (DH / 4); idx += 128) {
+            const int r = idx / (DH / 4), c = (idx % (DH / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k0 + r < len) v = *reinterpret_cast<const float4*>(base + D + (size_t)(k0 + r) * ld + c);
+            uint32_t h0, l0w, h1, l1w;
+            split_pair(v.x, v.y, h0, l0w);
+            split_pair(v.z, v.w, h1, l1w);
+            *reinterpret_cast<uint2*>(&Ks[0][r][c]) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(&Ks[1][r][c]) = make_uint2(l0w, l1w);
+        }
+        // V tile transposed: [d][key]; lanes run along keys so the 2-byte smem stores are conflict-free
+        for (int idx = tid; idx < KT * (DH / 4); idx += 128) {
+            const int r = idx % KT, c = (idx / KT) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k0 + r < len) v = *reinterpret_cast<const float4*>(base + 2 * D + (size_t)(k0 + r) * ld + c);
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat16 hi = __float2bfloat16_rn(vv[e]);
+                Vt[0][c + e][r] = hi;
+                Vt[1][c + e][r] = __float2bfloat16_rn(vv[e] - __bfloat162float(hi));
+            }
+        }
+        __syncthreads();
+
+        // S = Q K^T  (16 x 64 per warp)
+        float s[8][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                const int key = n * 8 + g, c = ks * 16 + 2 * t;
+                const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&Ks[0][key][c]);
+                const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&Ks[0][key][c + 8]);
+                const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&Ks[1][key][c]);
+                const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&Ks[1][key][c + 8]);
+                mma_bf16(s[n], qh[ks], bh0, bh1);
+                mma_bf16(s[n], ql[ks], bh0, bh1);
+                mma_bf16(s[n], qh[ks], bl0, bl1);
+            }
+        }
+        // key padding -> -inf, online softmax (rows g and g+8; a row's 64 scores live in the 4 lanes of a quad)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const int key = k0 + n * 8 + 2 * t;
+            if (key >= len) { s[n][0] = -INFINITY; s[n][2] = -INFINITY; }
+            if (key + 1 >= len) { s[n][1] = -INFINITY; s[n][3] = -INFINITY; }
+            mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite: every processed tile has >= 1 valid key
+        const float c0 = expf(m0 - mn0), c1 = expf(m1 - mn1);
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            s[n][0] = expf(s[n][0] - mn0); s[n][1] = expf(s[n][1] - mn0);
+            s[n][2] = expf(s[n][2] - mn1); s[n][3] = expf(s[n][3] - mn1);
+            rs0 += s[n][0] + s[n][1];
+            rs1 += s[n][2] + s[n][3];
+            if (p.dropout_p > 0.f) {   // dropout on the attention weights: applied to what multiplies V, not to the row sum
+                const unsigned long long kk = (unsigned long long)(k0 + n * 8 + 2 * t);
+                const unsigned long long i0 = (bh + r0) * (unsigned long long)p.S + kk, i1 = (bh + r1) * (unsigned long long)p.S + kk;
+                s[n][0] *= dropout_scale(p.seed, i0, p.dropout_p, inv_keep);
+                s[n][1] *= dropout_scale(p.seed, i0 + 1, p.dropout_p, inv_keep);
+                s[n][2] *= dropout_scale(p.seed, i1, p.dropout_p, inv_keep);
+                s[n][3] *= dropout_scale(p.seed, i1 + 1, p.dropout_p, inv_keep);
+            }
+        }
+        rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+        rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+        l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1;
+        m0 = mn0; m1 = mn1;
+#pragma unroll
+        for (int n = 0; n < ND; ++n) { o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1; }
+
+        // O += P V : the C-fragments of two adjacent score n-tiles form one A-fragment (16 keys)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t ph[4], pl[4];
+            split_pair(s[2 * j][0], s[2 * j][1], ph[0], pl[0]);
+            split_pair(s[2 * j][2], s[2 * j][3], ph[1], pl[1]);
+            split_pair(s[2 * j + 1][0], s[2 * j + 1][1], ph[2], pl[2]);
+            split_pair(s[2 * j + 1][2], s[2 * j + 1][3], ph[3], pl[3]);
+#pragma unroll
+            for (int n = 0; n < ND; ++n) {
+                const int d = n * 8 + g, c = j * 16 + 2 * t;
+                const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&Vt[0][d][c]);
+                const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&Vt[0][d][c + 8]);
+                const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&Vt[1][d][c]);
+                const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&Vt[1][d][c + 8]);
+                mma_bf16(o[n], ph, bh0, bh1);
+                mma_bf16(o[n], pl, bh0, bh1);
+                mma_bf16(o[n], ph, bl0, bl1);
+            }
+        }
+    }
+
+    const bool v0 = r0 < len, v1 = r1 < len;
+    const float i0 = v0 ? 1.f / l0 : 0.f, i1 = v1 ? 1.f / l1 : 0.f;
+#pragma unroll
+    for (int n = 0; n < ND; ++n) {
+        const int c = n * 8 + 2 * t;
+        if (r0 < p.S) *reinterpret_cast<float2*>(ctx + (size_t)r0 * D + c) = make_float2(v0 ? o[n][0] * i0 : 0.f, v0 ? o[n][1] * i0 : 0.f);
+        if (r1 < p.S) *reinterpret_cast<float2*>(ctx + (size_t)r1 * D + c) = make_float2(v1 ? o[n][2] * i1 : 0.f, v1 ? o[n][3] * i1 : 0.f);
+    }
+    if (t == 0) {
+        if (r0 < p.S) lse[r0] = v0 ? m0 + logf(l0) : 0.f;
+        if (r1 < p.S) lse[r1] = v1 ? m1 + logf(l1) : 0.f;
+    }
+}
+
+template <int DH>
+int launch_fwd_mma(const AttnArgs& a, cudaStream_t st) {
+    dim3 grid(ceil_div(a.S, QT), a.H, a.B);
+    attn_fwd_mma_kernel<DH><<<grid, 128, 0, st>>>(a);
+    return check_launch("attn_fwd_mma");
+}
+
+}  // namespace
+
+bool attention_mma_supported(const AttnArgs& a) { return a.dh == 16 || a.dh == 32 || a.dh == 64; }
+
+int attention_fwd_mma(const AttnArgs& a, cudaStream_t st) {
+    switch (a.dh) {
+        case 16: return launch_fwd_mma<16>(a, st);
+        case 32: return launch_fwd_mma<32>(a, st);
+        case 64: return launch_fwd_mma<64>(a, st);
+        default: set_last_error("attention_mma: unsupported head_dim %d", a.dh); return DX_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace dx
+
+// =====================================================================================================================
+// Backward.  CTA = 128 threads = 4 warps, one CTA per (64-key tile, head, utterance); warp w owns keys 16w..16w+15 and
+// accumulates dK, dV for them in registers while the CTA walks the valid query tiles:
+//   S^T = K Q^T, dP^T = V dO^T            (A = K / V rows of this warp, B = Q / dO tiles in smem)
+//   P^T = exp(S^T - lse), dS^T = P^T (dP^T * drop - delta)
+//   dV += P^T_drop dO, dK += dS^T Q       (score C-fragments re-used as A-fragments; B = dO^T / Q^T tiles in smem)
+//   dQ += scale * dS K                    (dS staged in smem q-major; warp w takes query rows 16w..; fp32 atomics to HBM)
+// All five products use the bf16 hi/lo split (3 tensor-core passes, fp32 accumulation).
+// =====================================================================================================================
+namespace dx {
+namespace {
+
+template <int DH>
+struct BwdSmem {
+    static constexpr int RP = DH + 8;   // row pitch of [row][d] tiles
+    static constexpr int TP = 64 + 8;   // row pitch of [d][row] and [q][key] tiles
+    __nv_bfloat16 K[2][64][RP], V[2][64][RP], Kt[2][DH][TP];
+    __nv_bfloat16 Q[2][64][RP], G[2][64][RP], Qt[2][DH][TP], Gt[2][DH][TP];
+    __nv_bfloat16 dS[2][64][TP];
+    float lse[64], delta[64];
+};
+
+// fp32 [64 rows][DH] tile (row stride ld) -> bf16 hi/lo, row-major copy and/or transposed copy
+template <int DH, int RP, int TP>
+__device__ __forceinline__ void stage_tile(const float* __restrict__ src, int ld, int r0, int limit, float scale,
+                                           __nv_bfloat16 (*rm)[64][RP], __nv_bfloat16 (*tr)[DH][TP]) {
+    const int tid = threadIdx.x;
+    if (rm) {
+        for (int idx = tid; idx < 64 * (DH / 4); idx += 128) {
+            const int r = idx / (DH / 4), c = (idx % (DH / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r0 + r < limit) v = *reinterpret_cast<const float4*>(src + (size_t)(r0 + r) * ld + c);
+            uint32_t h0, l0, h1, l1;
+            split_pair(v.x * scale, v.y * scale, h0, l0);
+            split_pair(v.z * scale, v.w * scale, h1, l1);
+            *reinterpret_cast<uint2*>(&rm[0][r][c]) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(&rm[1][r][c]) = make_uint2(l0, l1);
+        }
+    }
+    if (tr) {
+        for (int idx = tid; idx < 64 * (DH / 4); idx += 128) {
+            const int r = idx % 64, c = (idx / 64) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r0 + r < limit) v = *reinterpret_cast<const float4*>(src + (size_t)(r0 + r) * ld + c);
+            const float vv[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat16 hi = __float2bfloat16_rn(vv[e]);
+                tr[0][c + e][r] = hi;
+                tr[1][c + e][r] = __float2bfloat16_rn(vv[e] - __bfloat162float(hi));
+            }
+        }
+    }
+}
+
+// acc[n] (16 x 8 each, n < NT) += A(16 x 16*KSTEPS, rows a_row0.., from smem [row][k]) * B^T (B from smem [n][k])
+template <int KSTEPS, int NT, int AP, int BP>
+__device__ __forceinline__ void mma_smem_ab(float (*acc)[4], const __nv_bfloat16 (*A)[64][AP], int a_row0,
+                                            const __nv_bfloat16 (*Bm)[64][BP], int g, int t) {
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+        uint32_t ah[4], al[4];
+        const int c = ks * 16 + 2 * t;
+        ah[0] = *reinterpret_cast<const uint32_t*>(&A[0][a_row0 + g][c]);
+        ah[1] = *reinterpret_cast<const uint32_t*>(&A[0][a_row0 + g + 8][c]);
+        ah[2] = *reinterpret_cast<const uint32_t*>(&A[0][a_row0 + g][c + 8]);
+        ah[3] = *reinterpret_cast<const uint32_t*>(&A[0][a_row0 + g + 8][c + 8]);
+        al[0] = *reinterpret_cast<const uint32_t*>(&A[1][a_row0 + g][c]);
+        al[1] = *reinterpret_cast<const uint32_t*>(&A[1][a_row0 + g + 8][c]);
+        al[2] = *reinterpret_cast<const uint32_t*>(&A[1][a_row0 + g][c + 8]);
+        al[3] = *reinterpret_cast<const uint32_t*>(&A[1][a_row0 + g + 8][c + 8]);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&Bm[0][n * 8 + g][c]);
+            const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&Bm[0][n * 8 + g][c + 8]);
+            const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&Bm[1][n * 8 + g][c]);
+            const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&Bm[1][n * 8 + g][c + 8]);
+            mma_bf16(acc[n], ah, bh0, bh1);
+            mma_bf16(acc[n], al, bh0, bh1);
+            mma_bf16(acc[n], ah, bl0, bl1);
+        }
+    }
+}
+
+// acc[n] (n < NT) += A (from score C-fragments sc[8][4], 64 columns = 4 k-steps) * B^T (B from smem [n][k], pitch BP)
+template <int NT, int BP, int BR>
+__device__ __forceinline__ void mma_frag_b(float (*acc)[4], const float (*sc)[4], const __nv_bfloat16 (*Bm)[BR][BP], int g, int t) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t ah[4], al[4];
+        split_pair(sc[2 * j][0], sc[2 * j][1], ah[0], al[0]);
+        split_pair(sc[2 * j][2], sc[2 * j][3], ah[1], al[1]);
+        split_pair(sc[2 * j + 1][0], sc[2 * j + 1][1], ah[2], al[2]);
+        split_pair(sc[2 * j + 1][2], sc[2 * j + 1][3], ah[3], al[3]);
+        const int c = j * 16 + 2 * t;
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&Bm[0][n * 8 + g][c]);
+            const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&Bm[0][n * 8 + g][c + 8]);
+            const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&Bm[1][n * 8 + g][c]);
+            const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&Bm[1][n * 8 + g][c + 8]);
+            mma_bf16(acc[n], ah, bh0, bh1);
+            mma_bf16(acc[n], al, bh0, bh1);
+            mma_bf16(acc[n], ah, bl0, bl1);
+        }
+    }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(128) attn_bwd_mma_kernel(AttnArgs p) {
+    using SM = BwdSmem<DH>;
+    constexpr int KS = DH / 16, ND = DH / 8;
+    extern __shared__ __align__(16) uint8_t bwd_smem_raw[];
+    SM& sm = *reinterpret_cast<SM*>(bwd_smem_raw);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int k0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+    const int D = p.H * DH, ld = 3 * D;
+    const int len = min((int)p.lens[b], p.S);
+    if (k0 >= len) return;   // dK = dV = 0 for padded keys (dqkv is zero-initialised)
+    const float* base = p.qkv + (size_t)b * p.S * ld + h * DH;
+    const float* dctx = p.dctx + (size_t)b * p.S * D + h * DH;
+    float* dbase = p.dqkv + (size_t)b * p.S * ld + h * DH;
+    const float* lse = p.lse + ((size_t)b * p.H + h) * p.S;
+    const float* delta = p.delta + ((size_t)b * p.H + h) * p.S;
+    const float scale = rsqrtf((float)DH);
+    const float inv_keep = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
+    const unsigned long long bh = ((unsigned long long)b * p.H + h) * (unsigned long long)p.S;
+
+    stage_tile<DH, SM::RP, SM::TP>(base + D, ld, k0, len, 1.f, sm.K, sm.Kt);
+    stage_tile<DH, SM::RP, SM::TP>(base + 2 * D, ld, k0, len, 1.f, sm.V, (__nv_bfloat16 (*)[DH][SM::TP]) nullptr);
+
+    float dk[ND][4], dv[ND][4];
+#pragma unroll
+    for (int n = 0; n < ND; ++n) { dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f; dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f; }
+    const int key0 = k0 + warp * 16 + g, key1 = key0 + 8;   // this lane's two key rows
+
+    for (int q0 = 0; q0 < len; q0 += 64) {
+        __syncthreads();
+        stage_tile<DH, SM::RP, SM::TP>(base, ld, q0, len, scale, sm.Q, sm.Qt);
+        stage_tile<DH, SM::RP, SM::TP>(dctx, D, q0, len, 1.f, sm.G, sm.Gt);
+        if (tid < 64) {
+            sm.lse[tid] = (q0 + tid < len) ? lse[q0 + tid] : 0.f;
+            sm.delta[tid] = (q0 + tid < len) ? delta[q0 + tid] : 0.f;
+        }
+        __syncthreads();
+
+        float st[8][4], dp[8][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) { st[n][0] = st[n][1] = st[n][2] = st[n][3] = 0.f; dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f; }
+        mma_smem_ab<KS, 8, SM::RP, SM::RP>(st, sm.K, warp * 16, sm.Q, g, t);   // S^T  [16 keys][64 q]
+        mma_smem_ab<KS, 8, SM::RP, SM::RP>(dp, sm.V, warp * 16, sm.G, g, t);   // dP^T [16 keys][64 q]
+
+        // P^T (dropped) in st, dS^T in dp
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int ql = n * 8 + 2 * t + (e & 1), q = q0 + ql;
+                const int key = (e < 2) ? key0 : key1;
+                float pd = 0.f, ds = 0.f;
+                if (q < len && key < len) {
+                    const float pv = expf(st[n][e] - sm.lse[ql]);
+                    float dm = 1.f;
+                    if (p.dropout_p > 0.f) dm = dropout_scale(p.seed, (bh + q) * (unsigned long long)p.S + key, p.dropout_p, inv_keep);
+                    pd = pv * dm;
+                    ds = pv * (dp[n][e] * dm - sm.delta[ql]);
+                }
+                st[n][e] = pd;
+                dp[n][e] = ds;
+            }
+        }
+        mma_frag_b<ND, SM::TP, DH>(dv, st, sm.Gt, g, t);   // dV += P^T dO
+        mma_frag_b<ND, SM::TP, DH>(dk, dp, sm.Qt, g, t);   // dK += dS^T Q   (Q carries 1/sqrt(dh))
+        // dS, q-major, for the dQ product
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int ql = n * 8 + 2 * t + (e & 1);
+                const int kl = warp * 16 + g + ((e < 2) ? 0 : 8);
+                const __nv_bfloat16 hi = __float2bfloat16_rn(dp[n][e]);
+                sm.dS[0][ql][kl] = hi;
+                sm.dS[1][ql][kl] = __float2bfloat16_rn(dp[n][e] - __bfloat162float(hi));
+            }
+        }
+        __syncthreads();
+        // dQ[16 q rows of this warp][DH] = dS[q][64 keys] K[64 keys][DH]  (B = K^T tile [d][key])
+        float dq[ND][4];
+#pragma unroll
+        for (int n = 0; n < ND; ++n) { dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t ah[4], al[4];
+            const int c = ks * 16 + 2 * t, r = warp * 16 + g;
+            ah[0] = *reinterpret_cast<const uint32_t*>(&sm.dS[0][r][c]);
+            ah[1] = *reinterpret_cast<const uint32_t*>(&sm.dS[0][r + 8][c]);
+            ah[2] = *reinterpret_cast<const uint32_t*>(&sm.dS[0][r][c + 8]);
+            ah[3] = *reinterpret_cast<const uint32_t*>(&sm.dS[0][r + 8][c + 8]);
+            al[0] = *reinterpret_cast<const uint32_t*>(&sm.dS[1][r][c]);
+            al[1] = *reinterpret_cast<const uint32_t*>(&sm.dS[1][r + 8][c]);
+            al[2] = *reinterpret_cast<const uint32_t*>(&sm.dS[1][r][c + 8]);
+            al[3] = *reinterpret_cast<const uint32_t*>(&sm.dS[1][r + 8][c + 8]);
+#pragma unroll
+            for (int n = 0; n < ND; ++n) {
+                const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&sm.Kt[0][n * 8 + g][c]);
+                const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&sm.Kt[0][n * 8 + g][c + 8]);
+                const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&sm.Kt[1][n * 8 + g][c]);
+                const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&sm.Kt[1][n * 8 + g][c + 8]);
+                mma_bf16(dq[n], ah, bh0, bh1);
+                mma_bf16(dq[n], al, bh0, bh1);
+                mma_bf16(dq[n], ah, bl0, bl1);
+            }
+        }
+        const int qa = q0 + warp * 16 + g, qb = qa + 8;
+#pragma unroll
+        for (int n = 0; n < ND; ++n) {
+            const int c = n * 8 + 2 * t;
+            if (qa < len) { atomicAdd(dbase + (size_t)qa * ld + c, scale * dq[n][0]); atomicAdd(dbase + (size_t)qa * ld + c + 1, scale * dq[n][1]); }
+            if (qb < len) { atomicAdd(dbase + (size_t)qb * ld + c, scale * dq[n][2]); atomicAdd(dbase + (size_t)qb * ld + c + 1, scale * dq[n][3]); }
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < ND; ++n) {
+        const int c = n * 8 + 2 * t;
+        if (key0 < len) {
+            *reinterpret_cast<float2*>(dbase + (size_t)key0 * ld + D + c) = make_float2(dk[n][0], dk[n][1]);
+            *reinterpret_cast<float2*>(dbase + (size_t)key0 * ld + 2 * D + c) = make_float2(dv[n][0], dv[n][1]);
+        }
+        if (key1 < len) {
+            *reinterpret_cast<float2*>(dbase + (size_t)key1 * ld + D + c) = make_float2(dk[n][2], dk[n][3]);
+            *reinterpret_cast<float2*>(dbase + (size_t)key1 * ld + 2 * D + c) = make_float2(dv[n][2], dv[n][3]);
+        }
+    }
+}
+
+template <int DH>
+int launch_bwd_mma(const AttnArgs& a, cudaStream_t st) {
+    const size_t smem = sizeof(BwdSmem<DH>);
+    static bool configured = false;
+    if (!configured) {
+        DX_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid(ceil_div(a.S, 64), a.H, a.B);
+    attn_bwd_mma_kernel<DH><<<grid, 128, smem, st>>>(a);
+    return check_launch("attn_bwd_mma");
+}
+
+}  // namespace
+
+// dqkv must be zero-initialised and a.delta filled (attention_bwd_prepare) before this call
+int attention_bwd_mma(const AttnArgs& a, cudaStream_t st) {
+    switch (a.dh) {
+        case 16: return launch_bwd_mma<16>(a, st);
+        case 32: return launch_bwd_mma<32>(a, st);
+        case 64: return launch_bwd_mma<64>(a, st);
+        default: set_last_error("attention_mma: unsupported head_dim %d", a.dh); return DX_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace dx

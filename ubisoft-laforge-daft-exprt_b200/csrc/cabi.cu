@@ -138,6 +138,7 @@ int dx_attention_fwd(const float* qkv, const int64_t* lens, float* ctx, float* l
     memset(&a, 0, sizeof(a));
     a.qkv = qkv; a.lens = (cll)lens; a.ctx = ctx; a.lse = lse; a.B = B; a.S = S; a.H = H; a.dh = dh;
     a.dropout_p = dropout_p; a.seed = seed;
+    if (g_backend != DX_GEMM_FP32_CUDA_CORES && attention_mma_supported(a)) return attention_fwd_mma(a, ST(stream));
     return attention_fwd(a, ST(stream));
 }
 
@@ -147,6 +148,11 @@ int dx_attention_bwd(const float* qkv, const int64_t* lens, const float* ctx, co
     memset(&a, 0, sizeof(a));
     a.qkv = qkv; a.lens = (cll)lens; a.ctx = (float*)ctx; a.lse = (float*)lse; a.dctx = dctx; a.dqkv = dqkv; a.delta = delta;
     a.B = B; a.S = S; a.H = H; a.dh = dh; a.dropout_p = dropout_p; a.seed = seed;
+    if (g_backend != DX_GEMM_FP32_CUDA_CORES && attention_mma_supported(a)) {
+        int rc = attention_bwd_prepare(a, ST(stream));
+        if (rc) return rc;
+        return attention_bwd_mma(a, ST(stream));
+    }
     return attention_bwd(a, ST(stream));
 }
 

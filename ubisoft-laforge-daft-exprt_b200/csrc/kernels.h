@@ -70,6 +70,11 @@ struct AttnArgs {
     unsigned long long seed;
 };
 int attention_fwd(const AttnArgs& a, cudaStream_t st);
+// tensor-core (mma.sync bf16x3) variants, attention_mma.cu
+bool attention_mma_supported(const AttnArgs& a);
+int attention_fwd_mma(const AttnArgs& a, cudaStream_t st);
+int attention_bwd_mma(const AttnArgs& a, cudaStream_t st);
+int attention_bwd_prepare(const AttnArgs& a, cudaStream_t st);   // delta + zero dqkv
 int attention_bwd(const AttnArgs& a, cudaStream_t st);
 
 // LayerNorm family (norm.cu):  v = dropout_in(a) + res;  y = mask(film_g * dropout_out(LN(v) * w + b) + film_b)
