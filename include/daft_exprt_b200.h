@@ -52,15 +52,19 @@ int dx_pack_conv_weight(const float* w, float* fwd, float* dgrad, int Cout, int 
  * (same layout as y; residual / gradient accumulation) when != NULL, then optional tf32 rounding of the stored value.  backend < 0 selects the global default. */
 /* w_planes (nullable): cached bf16 hi|lo planes of w_packed made by dx_split_weight_planes (2 * KW*Cout*Cin bf16);
  * workspace: dx_conv_gemm_workspace(...) bytes (operand planes of the bf16x3 tensor-core path; 0 for the fp32 backend). */
-int dx_conv_gemm(const float* x, const float* w_packed, const void* w_planes, const float* bias, const float* relu_src,
-                 const float* add_src, float* y, void* workspace, size_t workspace_bytes, int B, int S, int Cin, int Cout, int KW,
-                 int ldx, int ldy, float alpha, int relu, int round_tf32, int backend, void* stream);
-size_t dx_conv_gemm_workspace(int B, int S, int Cin, int Cout, int KW, int have_w_planes, int backend);
+/* x_planes / dy_planes (nullable): bf16 hi|lo planes of an activation made once by dx_split_planes (2 * rows*C bf16) and shared by
+ * every GEMM that consumes it (forward + wgrad, or dgrad + wgrad); when NULL the call splits into its workspace. */
+int dx_conv_gemm(const float* x, const void* x_planes, const float* w_packed, const void* w_planes, const float* bias,
+                 const float* relu_src, const float* add_src, float* y, void* workspace, size_t workspace_bytes, int B, int S,
+                 int Cin, int Cout, int KW, int ldx, int ldy, float alpha, int relu, int round_tf32, int backend, void* stream);
+size_t dx_conv_gemm_workspace(int B, int S, int Cin, int Cout, int KW, int have_x_planes, int have_w_planes, int backend);
+int dx_split_planes(const float* x, int ld, void* planes, int rows, int C, void* stream);
 int dx_split_weight_planes(const float* w_packed, void* planes, size_t n, void* stream);
-size_t dx_conv_wgrad_workspace(int B, int S, int Cin, int Cout, int KW, int backend);
+size_t dx_conv_wgrad_workspace(int B, int S, int Cin, int Cout, int KW, int have_x_planes, int have_dy_planes, int backend);
 /* dw[co][ci][tap] = alpha * sum_{b,s} dy[b,s,co] * x[b, s+tap-pad, ci]  (parameter layout);  dbias[co] = alpha * sum dy */
-int dx_conv_wgrad(const float* x, const float* dy, float* dw, float* dbias, void* workspace, size_t workspace_bytes, int B,
-                  int S, int Cin, int Cout, int KW, int ldx, float alpha, int backend, void* stream);
+int dx_conv_wgrad(const float* x, const void* x_planes, const float* dy, const void* dy_planes, float* dw, float* dbias,
+                  void* workspace, size_t workspace_bytes, int B, int S, int Cin, int Cout, int KW, int ldx, float alpha, int backend,
+                  void* stream);
 int dx_colsum(const float* dy, float* db, int rows, int C, float alpha, void* stream);
 int dx_relu_bwd(const float* dy, const float* y, float* dx, size_t n, void* stream);
 int dx_scale_copy(const float* x, float* y, float alpha, size_t n, void* stream);

@@ -67,14 +67,14 @@ int dx_pack_conv_weight(const float* w, float* fwd, float* dgrad, int Cout, int 
     return pack_conv_weight(w, fwd, dgrad, Cout, Cin, KW, round_tf32, ST(stream));
 }
 
-static ConvGemmArgs gemm_args(const float* x, const float* w_packed, const void* w_planes, const float* bias,
+static ConvGemmArgs gemm_args(const float* x, const void* x_planes, const float* w_packed, const void* w_planes, const float* bias,
                               const float* relu_src, const float* add_src, float* y, void* ws, size_t wsb, int B, int S, int Cin,
                               int Cout, int KW, int ldx, int ldy, float alpha, int relu, int round_tf32) {
     ConvGemmArgs a;
     a.x = x; a.w = w_packed; a.bias = bias; a.relu_src = relu_src; a.add_src = add_src; a.y = y;
     a.B = B; a.S = S; a.Cin = Cin; a.Cout = Cout; a.KW = KW; a.ldx = ldx; a.ldy = ldy;
     a.alpha = alpha; a.relu = relu; a.round_tf32 = round_tf32;
-    a.w_planes = w_planes; a.workspace = ws; a.workspace_bytes = wsb;
+    a.w_planes = w_planes; a.x_planes = x_planes; a.workspace = ws; a.workspace_bytes = wsb;
     return a;
 }
 
@@ -82,35 +82,41 @@ int dx_split_weight_planes(const float* w_packed, void* planes, size_t n, void* 
     return split_weight_planes(w_packed, planes, n, ST(stream));
 }
 
-size_t dx_conv_gemm_workspace(int B, int S, int Cin, int Cout, int KW, int have_w_planes, int backend) {
+int dx_split_planes(const float* x, int ld, void* planes, int rows, int C, void* stream) {
+    return split_activation_planes(x, ld, planes, rows, C, ST(stream));
+}
+
+size_t dx_conv_gemm_workspace(int B, int S, int Cin, int Cout, int KW, int have_x_planes, int have_w_planes, int backend) {
     const int be = backend < 0 ? g_backend : backend;
     if (be == DX_GEMM_FP32_CUDA_CORES) return 0;
-    ConvGemmArgs a = gemm_args(nullptr, nullptr, have_w_planes ? (const void*)16 : nullptr, nullptr, nullptr, nullptr, nullptr,
-                               nullptr, 0, B, S, Cin, Cout, KW, Cin, Cout, 1.f, 0, 0);
+    ConvGemmArgs a = gemm_args(nullptr, have_x_planes ? (const void*)16 : nullptr, nullptr, have_w_planes ? (const void*)16 : nullptr,
+                               nullptr, nullptr, nullptr, nullptr, nullptr, 0, B, S, Cin, Cout, KW, Cin, Cout, 1.f, 0, 0);
     return conv_gemm_tc_workspace(a);
 }
 
-int dx_conv_gemm(const float* x, const float* w_packed, const void* w_planes, const float* bias, const float* relu_src,
-                 const float* add_src, float* y, void* workspace, size_t workspace_bytes, int B, int S, int Cin, int Cout, int KW,
-                 int ldx, int ldy, float alpha, int relu, int round_tf32, int backend, void* stream) {
-    ConvGemmArgs a = gemm_args(x, w_packed, w_planes, bias, relu_src, add_src, y, workspace, workspace_bytes, B, S, Cin, Cout, KW,
-                               ldx, ldy, alpha, relu, round_tf32);
+int dx_conv_gemm(const float* x, const void* x_planes, const float* w_packed, const void* w_planes, const float* bias,
+                 const float* relu_src, const float* add_src, float* y, void* workspace, size_t workspace_bytes, int B, int S,
+                 int Cin, int Cout, int KW, int ldx, int ldy, float alpha, int relu, int round_tf32, int backend, void* stream) {
+    ConvGemmArgs a = gemm_args(x, x_planes, w_packed, w_planes, bias, relu_src, add_src, y, workspace, workspace_bytes, B, S, Cin,
+                               Cout, KW, ldx, ldy, alpha, relu, round_tf32);
     DX_REQUIRE(B > 0 && S > 0 && Cin > 0 && Cout > 0 && (KW == 1 || KW == 3), "dx_conv_gemm: bad shape B=%d S=%d Cin=%d Cout=%d KW=%d", B, S, Cin, Cout, KW);
     const int be = backend < 0 ? g_backend : backend;
     if (be != DX_GEMM_FP32_CUDA_CORES && conv_gemm_tc_supported(a)) return conv_gemm_tc(a, ST(stream));
     return conv_gemm_simt(a, ST(stream));
 }
 
-static ConvWgradArgs wgrad_args(const float* x, const float* dy, float* dw, float* dbias, void* ws, size_t wsb, int B, int S,
-                                int Cin, int Cout, int KW, int ldx, float alpha) {
+static ConvWgradArgs wgrad_args(const float* x, const void* x_planes, const float* dy, const void* dy_planes, float* dw,
+                                float* dbias, void* ws, size_t wsb, int B, int S, int Cin, int Cout, int KW, int ldx, float alpha) {
     ConvWgradArgs a;
     a.x = x; a.dy = dy; a.dw = dw; a.dbias = dbias; a.workspace = ws; a.workspace_bytes = wsb;
     a.B = B; a.S = S; a.Cin = Cin; a.Cout = Cout; a.KW = KW; a.ldx = ldx; a.alpha = alpha;
+    a.x_planes = x_planes; a.dy_planes = dy_planes;
     return a;
 }
 
-size_t dx_conv_wgrad_workspace(int B, int S, int Cin, int Cout, int KW, int backend) {
-    ConvWgradArgs a = wgrad_args(nullptr, nullptr, nullptr, nullptr, nullptr, 0, B, S, Cin, Cout, KW, Cin, 1.f);
+size_t dx_conv_wgrad_workspace(int B, int S, int Cin, int Cout, int KW, int have_x_planes, int have_dy_planes, int backend) {
+    ConvWgradArgs a = wgrad_args(nullptr, have_x_planes ? (const void*)16 : nullptr, nullptr, have_dy_planes ? (const void*)16 : nullptr,
+                                 nullptr, nullptr, nullptr, 0, B, S, Cin, Cout, KW, Cin, 1.f);
     size_t need = conv_wgrad_simt_workspace(a, nullptr);
     const int be = backend < 0 ? g_backend : backend;
     if (be != DX_GEMM_FP32_CUDA_CORES && conv_wgrad_tc_supported(a)) {
@@ -120,9 +126,10 @@ size_t dx_conv_wgrad_workspace(int B, int S, int Cin, int Cout, int KW, int back
     return need;
 }
 
-int dx_conv_wgrad(const float* x, const float* dy, float* dw, float* dbias, void* workspace, size_t workspace_bytes, int B,
-                  int S, int Cin, int Cout, int KW, int ldx, float alpha, int backend, void* stream) {
-    ConvWgradArgs a = wgrad_args(x, dy, dw, dbias, workspace, workspace_bytes, B, S, Cin, Cout, KW, ldx, alpha);
+int dx_conv_wgrad(const float* x, const void* x_planes, const float* dy, const void* dy_planes, float* dw, float* dbias,
+                  void* workspace, size_t workspace_bytes, int B, int S, int Cin, int Cout, int KW, int ldx, float alpha, int backend,
+                  void* stream) {
+    ConvWgradArgs a = wgrad_args(x, x_planes, dy, dy_planes, dw, dbias, workspace, workspace_bytes, B, S, Cin, Cout, KW, ldx, alpha);
     const int be = backend < 0 ? g_backend : backend;
     if (be != DX_GEMM_FP32_CUDA_CORES && conv_wgrad_tc_supported(a)) return conv_wgrad_tc(a, ST(stream));
     return conv_wgrad_simt(a, ST(stream));

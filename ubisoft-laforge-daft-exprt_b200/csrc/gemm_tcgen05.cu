@@ -556,6 +556,14 @@ inline int round8(int x) { return (x + 7) & ~7; }
 void set_tc_precision(int tf32) { g_prec = tf32 ? PREC_TF32 : PREC_BF16X3; }
 void set_tc_trace(long long* buf) { g_trace = buf; }
 
+int split_activation_planes(const float* x, int ld, void* planes, int rows, int C, cudaStream_t st) {
+    DX_REQUIRE(C % 8 == 0 && ld % 4 == 0, "split_activation_planes: C=%d ld=%d", C, ld);
+    __nv_bfloat16* hi = (__nv_bfloat16*)planes;
+    dim3 grid(ceil_div(rows, 64), ceil_div(C, 64), 1);
+    split_planes_kernel<<<grid, 256, 0, st>>>(x, ld, rows, C, 0, hi, hi + (size_t)rows * C, nullptr, nullptr, 1);
+    return check_launch("split_planes");
+}
+
 int split_weight_planes(const float* w, void* planes, size_t n, cudaStream_t st) {
     __nv_bfloat16* hi = (__nv_bfloat16*)planes;
     split_flat_kernel<<<grid_1d(n), 256, 0, st>>>(w, hi, hi + n, n);
@@ -573,7 +581,7 @@ bool conv_gemm_tc_supported(const ConvGemmArgs& a) {
 size_t conv_gemm_tc_workspace(const ConvGemmArgs& a) {
     if (g_prec == PREC_TF32) return 0;
     const size_t xe = (size_t)a.B * a.S * a.Cin, we = (size_t)a.KW * a.Cout * a.Cin;
-    return 2 * align256(xe * 2) + (a.w_planes ? 0 : 2 * align256(we * 2)) + 256;
+    return (a.x_planes ? 0 : 2 * align256(xe * 2)) + (a.w_planes ? 0 : 2 * align256(we * 2)) + 256;
 }
 
 int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
@@ -597,17 +605,23 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
         return launch<PREC_TF32, MODE_CONV>(mxh, mxh, mwh, mwh, my, p, st);
     }
     const size_t need = conv_gemm_tc_workspace(a);
-    DX_REQUIRE(a.workspace && a.workspace_bytes >= need, "conv_gemm_tc: workspace %zu < %zu bytes", a.workspace_bytes, need);
+    DX_REQUIRE(need <= 256 || (a.workspace && a.workspace_bytes >= need), "conv_gemm_tc: workspace %zu < %zu bytes", a.workspace_bytes, need);
     const size_t xe = (size_t)a.B * a.S * a.Cin, we = (size_t)a.KW * a.Cout * a.Cin;
     uint8_t* ws = (uint8_t*)(((uintptr_t)a.workspace + 255) & ~(uintptr_t)255);
-    __nv_bfloat16* xh = (__nv_bfloat16*)ws;
-    __nv_bfloat16* xl = (__nv_bfloat16*)(ws + align256(xe * 2));
-    const __nv_bfloat16* wh = (const __nv_bfloat16*)(ws + 2 * align256(xe * 2));
-    const __nv_bfloat16* wl = (const __nv_bfloat16*)(ws + 2 * align256(xe * 2) + align256(we * 2));
+    const size_t xbytes = a.x_planes ? 0 : 2 * align256(xe * 2);
+    const __nv_bfloat16* xh = (const __nv_bfloat16*)ws;
+    const __nv_bfloat16* xl = (const __nv_bfloat16*)(ws + align256(xe * 2));
+    const __nv_bfloat16* wh = (const __nv_bfloat16*)(ws + xbytes);
+    const __nv_bfloat16* wl = (const __nv_bfloat16*)(ws + xbytes + align256(we * 2));
     {
-        dim3 grid(ceil_div(a.S, 64), ceil_div(a.Cin, 64), a.B);
-        split_planes_kernel<<<grid, 256, 0, st>>>(a.x, a.ldx, a.S, a.Cin, 0, xh, xl, nullptr, nullptr, a.B);
-        if ((rc = check_launch("split_planes"))) return rc;
+        if (a.x_planes) {
+            xh = (const __nv_bfloat16*)a.x_planes;
+            xl = xh + xe;
+        } else {
+            dim3 grid(ceil_div(a.S, 64), ceil_div(a.Cin, 64), a.B);
+            split_planes_kernel<<<grid, 256, 0, st>>>(a.x, a.ldx, a.S, a.Cin, 0, (__nv_bfloat16*)xh, (__nv_bfloat16*)xl, nullptr, nullptr, a.B);
+            if ((rc = check_launch("split_planes"))) return rc;
+        }
         if (a.w_planes) {   // cached by the caller: hi plane followed by lo plane
             wh = (const __nv_bfloat16*)a.w_planes;
             wl = wh + we;
@@ -615,6 +629,10 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
             split_flat_kernel<<<grid_1d(we), 256, 0, st>>>(a.w, (__nv_bfloat16*)wh, (__nv_bfloat16*)wl, we);
             if ((rc = check_launch("split_flat"))) return rc;
         }
+    }
+    if (((uintptr_t)xh | (uintptr_t)xl | (uintptr_t)wh | (uintptr_t)wl) & 15) {
+        set_last_error("conv_gemm_tc: operand planes must be 16-byte aligned");
+        return DX_ERR_ARG;
     }
     p.k_chunks = ceil_div(a.Cin, Cfg<PREC_BF16X3>::TKB);
     const uint64_t xs1 = (uint64_t)a.Cin * 2, xs2 = (uint64_t)a.S * a.Cin * 2;
@@ -652,7 +670,7 @@ static int wgrad_nsplit(const ConvWgradArgs& a) {
 size_t conv_wgrad_tc_workspace(const ConvWgradArgs& a) {
     const size_t dye = (size_t)a.B * a.S * a.Cout, xe = (size_t)a.B * a.S * a.Cin;
     const size_t part = (size_t)wgrad_nsplit(a) * a.KW * a.Cout * a.Cin * 4;
-    return 2 * align256(dye * 2) + 2 * align256(xe * 2) + align256(part) + 256;
+    return (a.dy_planes ? 0 : 2 * align256(dye * 2)) + (a.x_planes ? 0 : 2 * align256(xe * 2)) + align256(part) + 256;
 }
 
 __global__ void wgrad_reduce_tc_kernel(const float* __restrict__ part, float* __restrict__ dw, int nsplit, int KW, int Cout,
@@ -675,19 +693,32 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
     const int nsplit = wgrad_nsplit(a);
     const size_t dye = (size_t)a.B * a.S * a.Cout, xe = (size_t)a.B * a.S * a.Cin;
     uint8_t* ws = (uint8_t*)(((uintptr_t)a.workspace + 255) & ~(uintptr_t)255);
-    __nv_bfloat16* dh = (__nv_bfloat16*)ws;
-    __nv_bfloat16* dl = (__nv_bfloat16*)(ws + align256(dye * 2));
-    __nv_bfloat16* xh = (__nv_bfloat16*)(ws + 2 * align256(dye * 2));
-    __nv_bfloat16* xl = (__nv_bfloat16*)(ws + 2 * align256(dye * 2) + align256(xe * 2));
-    float* part = (float*)(ws + 2 * align256(dye * 2) + 2 * align256(xe * 2));
+    const size_t dyb = a.dy_planes ? 0 : 2 * align256(dye * 2), xb = a.x_planes ? 0 : 2 * align256(xe * 2);
+    const __nv_bfloat16* dh = (const __nv_bfloat16*)ws;
+    const __nv_bfloat16* dl = (const __nv_bfloat16*)(ws + align256(dye * 2));
+    const __nv_bfloat16* xh = (const __nv_bfloat16*)(ws + dyb);
+    const __nv_bfloat16* xl = (const __nv_bfloat16*)(ws + dyb + align256(xe * 2));
+    float* part = (float*)(ws + dyb + xb);
     int rc;
-    {
+    if (a.dy_planes) {
+        dh = (const __nv_bfloat16*)a.dy_planes;
+        dl = dh + dye;
+    } else {
         dim3 g1(ceil_div(a.S, 64), ceil_div(a.Cout, 64), a.B);
-        split_planes_kernel<<<g1, 256, 0, st>>>(a.dy, a.Cout, a.S, a.Cout, 0, dh, dl, nullptr, nullptr, a.B);
+        split_planes_kernel<<<g1, 256, 0, st>>>(a.dy, a.Cout, a.S, a.Cout, 0, (__nv_bfloat16*)dh, (__nv_bfloat16*)dl, nullptr, nullptr, a.B);
         if ((rc = check_launch("split_planes(dy)"))) return rc;
+    }
+    if (a.x_planes) {
+        xh = (const __nv_bfloat16*)a.x_planes;
+        xl = xh + xe;
+    } else {
         dim3 g2(ceil_div(a.S, 64), ceil_div(a.Cin, 64), a.B);
-        split_planes_kernel<<<g2, 256, 0, st>>>(a.x, a.ldx, a.S, a.Cin, 0, xh, xl, nullptr, nullptr, a.B);
+        split_planes_kernel<<<g2, 256, 0, st>>>(a.x, a.ldx, a.S, a.Cin, 0, (__nv_bfloat16*)xh, (__nv_bfloat16*)xl, nullptr, nullptr, a.B);
         if ((rc = check_launch("split_planes(x)"))) return rc;
+    }
+    if (((uintptr_t)dh | (uintptr_t)dl | (uintptr_t)xh | (uintptr_t)xl) & 15) {
+        set_last_error("conv_wgrad_tc: operand planes must be 16-byte aligned");
+        return DX_ERR_ARG;
     }
     TcParams p;
     p.bias = nullptr; p.relu_src = nullptr; p.add_src = nullptr;

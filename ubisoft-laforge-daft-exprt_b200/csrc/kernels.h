@@ -22,6 +22,7 @@ struct ConvGemmArgs {
     int relu;
     int round_tf32;
     const void* w_planes;   // optional cached bf16 hi|lo planes of w (tensor-core bf16x3 path), else nullptr
+    const void* x_planes;   // optional bf16 hi|lo planes of x ([B*S][Cin] each, made by split_activation_planes), else nullptr
     void* workspace;        // tensor-core bf16x3 path: operand planes (see conv_gemm_tc_workspace)
     size_t workspace_bytes;
 };
@@ -37,6 +38,8 @@ struct ConvWgradArgs {
     int B, S, Cin, Cout, KW;
     int ldx;
     float alpha;
+    const void* x_planes;    // optional bf16 hi|lo planes of x  ([B*S][Cin] each)
+    const void* dy_planes;   // optional bf16 hi|lo planes of dy ([B*S][Cout] each)
 };
 
 int conv_gemm_simt(const ConvGemmArgs& a, cudaStream_t st);
@@ -49,6 +52,7 @@ int pack_conv_weight(const float* w, float* fwd, float* dgrad, int Cout, int Cin
 void set_tc_precision(int tf32);
 void set_tc_trace(long long* buf);
 int split_weight_planes(const float* w, void* planes, size_t n, cudaStream_t st);
+int split_activation_planes(const float* x, int ld, void* planes, int rows, int C, cudaStream_t st);
 size_t conv_gemm_tc_workspace(const ConvGemmArgs& a);
 bool conv_gemm_tc_supported(const ConvGemmArgs& a);
 int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st);

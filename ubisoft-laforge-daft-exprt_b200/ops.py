@@ -128,15 +128,25 @@ def packed(weight):
     return fwd, dgrad
 
 
-def conv_gemm(x, wp, bias, B, S, relu=False, relu_src=None, add_src=None, alpha=1.0, round_out=False, ldx=None):
+def make_planes(x, rows, C, ld=None):
+    """bf16 hi|lo operand planes of an fp32 activation [rows, C] (made ONCE, shared by every tensor-core GEMM that consumes
+    the activation: forward + wgrad, or dgrad + wgrad).  None when the active backend does not use planes."""
+    if _backend[0] == cabi.DX_GEMM_FP32_CUDA_CORES or C % 8 != 0 or C < 16:
+        return None
+    planes = torch.empty(2, rows, C, device=x.device, dtype=torch.bfloat16)
+    _call('dx_split_planes', _p(x), C if ld is None else ld, _p(planes), rows, C, _st())
+    return planes
+
+
+def conv_gemm(x, wp, bias, B, S, relu=False, relu_src=None, add_src=None, alpha=1.0, round_out=False, ldx=None, x_planes=None):
     """x [B,S,Cin] (row stride ldx) · packed weight [KW,Cout,Cin] -> [B,S,Cout]"""
     kw, cout, cin = wp.shape
     dev = wp.w.device
     y = torch.empty(B, S, cout, device=dev, dtype=torch.float32)
     rnd = 1 if (round_out and _backend[0] == cabi.DX_GEMM_TCGEN05_TF32) else 0
-    nbytes = lib().dx_conv_gemm_workspace(B, S, cin, cout, kw, int(wp.planes is not None), -1)
+    nbytes = lib().dx_conv_gemm_workspace(B, S, cin, cout, kw, int(x_planes is not None), int(wp.planes is not None), -1)
     ws = torch.empty(nbytes + 256, device=dev, dtype=torch.uint8) if nbytes else None
-    _call('dx_conv_gemm', _p(x), _p(wp.w), _p(wp.planes), _p(bias), _p(relu_src), _p(add_src), _p(y), _p(ws),
+    _call('dx_conv_gemm', _p(x), _p(x_planes), _p(wp.w), _p(wp.planes), _p(bias), _p(relu_src), _p(add_src), _p(y), _p(ws),
           ws.numel() if ws is not None else 0, B, S, cin, cout, kw, cin if ldx is None else ldx, cout, float(alpha),
           int(relu), rnd, -1, _st())
     return y
@@ -148,13 +158,13 @@ def linear_rows(x2d, wp, bias, **kw):
     return conv_gemm(x2d, wp, bias, 1, R, **kw).view(R, -1)
 
 
-def conv_wgrad(x, dy, B, S, cin, cout, kw, shape, want_bias=True, ldx=None, alpha=1.0):
+def conv_wgrad(x, dy, B, S, cin, cout, kw, shape, want_bias=True, ldx=None, alpha=1.0, x_planes=None, dy_planes=None):
     """-> (dw in the parameter's own layout `shape`, dbias [Cout] or None)"""
     dw = torch.empty(tuple(shape), device=dy.device, dtype=torch.float32)
     db = torch.empty(cout, device=dy.device, dtype=torch.float32) if want_bias else None
-    nbytes = lib().dx_conv_wgrad_workspace(B, S, cin, cout, kw, -1)
+    nbytes = lib().dx_conv_wgrad_workspace(B, S, cin, cout, kw, int(x_planes is not None), int(dy_planes is not None), -1)
     ws = torch.empty(max(nbytes, 16) // 4 + 4, device=dy.device, dtype=torch.float32)
-    _call('dx_conv_wgrad', _p(x), _p(dy), _p(dw), _p(db), _p(ws), ws.numel() * 4, B, S, cin, cout, kw,
+    _call('dx_conv_wgrad', _p(x), _p(x_planes), _p(dy), _p(dy_planes), _p(dw), _p(db), _p(ws), ws.numel() * 4, B, S, cin, cout, kw,
           cin if ldx is None else ldx, float(alpha), -1, _st())
     return dw, db
 
@@ -191,33 +201,37 @@ class AttentionSubLayer(torch.autograd.Function):
         dh = D // nb_heads
         in_wp, in_wd = packed(in_w)
         out_wp, out_wd = packed(out_w)
-        qkv = conv_gemm(x, in_wp, in_b, 1, B * S).view(B, S, 3 * D)
+        xP = make_planes(x, B * S, D)
+        qkv = conv_gemm(x, in_wp, in_b, 1, B * S, x_planes=xP).view(B, S, 3 * D)
         att = torch.empty(B, S, D, device=x.device, dtype=torch.float32)
         lse = torch.empty(B, nb_heads, S, device=x.device, dtype=torch.float32)
         seed_attn, seed_out = (next_seed(), next_seed()) if p_drop > 0 else (0, 0)
         _call('dx_attention_fwd', _p(qkv), _p(lens), _p(att), _p(lse), B, S, nb_heads, dh, float(p_drop), seed_attn, _st())
-        proj = conv_gemm(att, out_wp, out_b, 1, B * S)
+        attP = make_planes(att, B * S, D)
+        proj = conv_gemm(att, out_wp, out_b, 1, B * S, x_planes=attP)
         y, xhat, rstd = ln_fwd(proj, x, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p_drop, seed_in=seed_out)
-        ctx.save_for_backward(x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b)
+        ctx.save_for_backward(x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b, xP, attP)
         ctx.packed = (in_wd, out_wd)
         ctx.cfg = (B, S, D, nb_heads, dh, float(p_drop), seed_attn, seed_out, in_w.shape, out_w.shape)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b = ctx.saved_tensors
+        x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b, xP, attP = ctx.saved_tensors
         in_wd, out_wd = ctx.packed
         B, S, D, H, dh, p, seed_attn, seed_out, in_shape, out_shape = ctx.cfg
         dy = _check_input(dy)
         dv, dproj, dln_w, dln_b, _ = ln_bwd(dy, xhat, rstd, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p, seed_in=seed_out)
-        datt = conv_gemm(dproj, out_wd, None, 1, B * S)
-        d_out_w, d_out_b = conv_wgrad(att, dproj, B, S, D, D, 1, out_shape)
+        dprojP = make_planes(dproj, B * S, D)
+        datt = conv_gemm(dproj, out_wd, None, 1, B * S, x_planes=dprojP)
+        d_out_w, d_out_b = conv_wgrad(att, dproj, B, S, D, D, 1, out_shape, x_planes=attP, dy_planes=dprojP)
         dqkv = torch.empty(B, S, 3 * D, device=dy.device, dtype=torch.float32)
         delta = torch.empty(B, H, S, device=dy.device, dtype=torch.float32)
         _call('dx_attention_bwd', _p(qkv), _p(lens), _p(att), _p(lse), _p(datt), _p(dqkv), _p(delta), B, S, H, dh, p,
               seed_attn, _st())
-        dx = conv_gemm(dqkv, in_wd, None, 1, B * S, add_src=dv).view(B, S, D)
-        d_in_w, d_in_b = conv_wgrad(x, dqkv, B, S, D, 3 * D, 1, in_shape)
+        dqkvP = make_planes(dqkv, B * S, 3 * D)
+        dx = conv_gemm(dqkv, in_wd, None, 1, B * S, add_src=dv, x_planes=dqkvP).view(B, S, D)
+        d_in_w, d_in_b = conv_wgrad(x, dqkv, B, S, D, 3 * D, 1, in_shape, x_planes=xP, dy_planes=dqkvP)
         return dx, None, d_in_w, d_in_b, d_out_w, d_out_b, dln_w, dln_b, None, None
 
 
@@ -231,30 +245,34 @@ class ConvFFSubLayer(torch.autograd.Function):
         w1p, w1d = packed(w1)
         w2p, w2d = packed(w2)
         C = w1.shape[0]
-        h = conv_gemm(x, w1p, b1, B, S, relu=True, round_out=True)
-        o = conv_gemm(h, w2p, b2, B, S)
+        xP = make_planes(x, B * S, D)
+        h = conv_gemm(x, w1p, b1, B, S, relu=True, round_out=True, x_planes=xP)
+        hP = make_planes(h, B * S, C)
+        o = conv_gemm(h, w2p, b2, B, S, x_planes=hP)
         seed = next_seed() if p_drop > 0 else 0
         if film is not None:
             film = _check_input(film)
             assert film.shape[1] == 2 * D   # reference model.py:232
         y, xhat, rstd = ln_fwd(o, x, ln_w, ln_b, film, 2 * D, lens, B, S, D, p_in=p_drop, seed_in=seed)
-        ctx.save_for_backward(x, lens, h, xhat, rstd, ln_w, ln_b, film)
+        ctx.save_for_backward(x, lens, h, xhat, rstd, ln_w, ln_b, film, xP, hP)
         ctx.packed = (w1d, w2d)
         ctx.cfg = (B, S, D, C, float(p_drop), seed, w1.shape, w2.shape)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, lens, h, xhat, rstd, ln_w, ln_b, film = ctx.saved_tensors
+        x, lens, h, xhat, rstd, ln_w, ln_b, film, xP, hP = ctx.saved_tensors
         w1d, w2d = ctx.packed
         B, S, D, C, p, seed, w1_shape, w2_shape = ctx.cfg
         dy = _check_input(dy)
         dv, do, dln_w, dln_b, dfilm = ln_bwd(dy, xhat, rstd, ln_w, ln_b, film, 2 * D, lens, B, S, D, p_in=p, seed_in=seed,
                                              want_film=film is not None)
-        dh = conv_gemm(do, w2d, None, B, S, relu_src=h, round_out=True)
-        dw2, db2 = conv_wgrad(h, do, B, S, C, D, w2_shape[2], w2_shape)
-        dx = conv_gemm(dh, w1d, None, B, S, add_src=dv)
-        dw1, db1 = conv_wgrad(x, dh, B, S, D, C, w1_shape[2], w1_shape)
+        doP = make_planes(do, B * S, D)
+        dh = conv_gemm(do, w2d, None, B, S, relu_src=h, round_out=True, x_planes=doP)
+        dw2, db2 = conv_wgrad(h, do, B, S, C, D, w2_shape[2], w2_shape, x_planes=hP, dy_planes=doP)
+        dhP = make_planes(dh, B * S, C)
+        dx = conv_gemm(dh, w1d, None, B, S, add_src=dv, x_planes=dhP)
+        dw1, db1 = conv_wgrad(x, dh, B, S, D, C, w1_shape[2], w1_shape, x_planes=xP, dy_planes=dhP)
         return dx, None, dw1, db1, dw2, db2, dln_w, dln_b, dfilm, None
 
 
@@ -269,10 +287,12 @@ class PreNet(torch.autograd.Function):
         x = torch.empty(B, T, M, device=mel.device, dtype=torch.float32)
         _call('dx_mask_transpose_bwd', _p(mel), _p(full), _p(x), B, T, M, _st())   # plain [B,M,T] -> [B,T,M]
         saved, cur = [x], x
-        seeds, wds = [], []
+        seeds, wds, in_planes = [], [], []
         for w, b, g, e in ((w0, b0, g0, e0), (w1, b1, g1, e1), (w2, b2, g2, e2)):
             wp, wd = packed(w)
-            a = conv_gemm(cur, wp, b, B, T, relu=True)
+            curP = make_planes(cur, B * T, w.shape[1])
+            in_planes.append(curP)
+            a = conv_gemm(cur, wp, b, B, T, relu=True, x_planes=curP)
             seed = next_seed() if p_drop > 0 else 0
             y, xhat, rstd = ln_fwd(a, None, g, e, None, 0, None, B, T, w.shape[0], p_out=p_drop, seed_out=seed)
             saved += [a, xhat, rstd, g, e]
@@ -281,6 +301,7 @@ class PreNet(torch.autograd.Function):
             cur = y
             saved.append(y)
         ctx.save_for_backward(*saved)
+        ctx.in_planes = in_planes   # bf16 planes of each layer's input (not autograd tensors of interest: plain buffers)
         ctx.packed = wds
         ctx.cfg = (B, T, M, float(p_drop), seeds, (w0.shape, w1.shape, w2.shape))
         return cur
@@ -299,10 +320,11 @@ class PreNet(torch.autograd.Function):
             cout, cin, kw = shapes[i]
             inp = x if i == 0 else layers[i - 1][5]
             dpre, _, dg, de, _ = ln_bwd(d, xhat, rstd, g, e, None, 0, None, B, T, cout, relu_src=a, p_out=p, seed_out=seeds[i])
-            dw, db = conv_wgrad(inp, dpre, B, T, cin, cout, kw, shapes[i])
+            dpreP = make_planes(dpre, B * T, cout)
+            dw, db = conv_wgrad(inp, dpre, B, T, cin, cout, kw, shapes[i], x_planes=ctx.in_planes[i], dy_planes=dpreP)
             grads[4 * i: 4 * i + 4] = [dw, db, dg, de]
             if i > 0:
-                d = conv_gemm(dpre, wd, None, B, T)
+                d = conv_gemm(dpre, wd, None, B, T, x_planes=dpreP)
         return (None, *grads, None)
 
 
