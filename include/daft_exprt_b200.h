@@ -58,7 +58,8 @@ int dx_conv_gemm(const float* x, const void* x_planes, const float* w_packed, co
                  const float* relu_src, const float* add_src, float* y, void* workspace, size_t workspace_bytes, int B, int S,
                  int Cin, int Cout, int KW, int ldx, int ldy, float alpha, int relu, int round_tf32, int backend, void* stream);
 size_t dx_conv_gemm_workspace(int B, int S, int Cin, int Cout, int KW, int have_x_planes, int have_w_planes, int backend);
-int dx_split_planes(const float* x, int ld, void* planes, int rows, int C, void* stream);
+/* colsum_out (nullable, [C]): column sums of x accumulated in the same pass (= the bias gradient when x is a dy) */
+int dx_split_planes(const float* x, int ld, void* planes, float* colsum_out, int rows, int C, void* stream);
 int dx_split_weight_planes(const float* w_packed, void* planes, size_t n, void* stream);
 size_t dx_conv_wgrad_workspace(int B, int S, int Cin, int Cout, int KW, int have_x_planes, int have_dy_planes, int backend);
 /* dw[co][ci][tap] = alpha * sum_{b,s} dy[b,s,co] * x[b, s+tap-pad, ci]  (parameter layout);  dbias[co] = alpha * sum dy */

@@ -388,3 +388,46 @@ def test_full_size_properties(dev):
     mel_t = model(din)[3][0]
     assert not torch.equal(mel_t, mel) and torch.isfinite(mel_t).all()
     assert float(mel_t.abs().masked_select(~tmask[:, None, :].expand_as(mel_t)).max()) == 0.0
+
+
+def test_dropout_statistics_and_mask_consistency(dev):
+    """Train-mode dropout: kept fraction ~ 1-p, kept values scaled by 1/(1-p), and the backward regenerates the same mask."""
+    from daft_exprt_b200 import ops
+    B, S, D, p = 4, 300, 128, 0.1
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(B, S, D, generator=g).to(dev)
+    w, b = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+    y0, _, _ = ops.ln_fwd(a, None, w, b, None, 0, None, B, S, D)
+    y1, xhat, rstd = ops.ln_fwd(a, None, w, b, None, 0, None, B, S, D, p_out=p, seed_out=12345)
+    ratio = (y1 / y0).flatten()
+    kept = ratio.abs() > 1e-6
+    frac = kept.float().mean().item()
+    n = ratio.numel()
+    assert abs(frac - (1 - p)) < 5 * np.sqrt(p * (1 - p) / n)
+    assert torch.allclose(ratio[kept], torch.full_like(ratio[kept], 1 / (1 - p)), rtol=1e-5)
+    y2, _, _ = ops.ln_fwd(a, None, w, b, None, 0, None, B, S, D, p_out=p, seed_out=12345)
+    assert torch.equal(y1, y2)                                   # same seed -> same mask
+    y3, _, _ = ops.ln_fwd(a, None, w, b, None, 0, None, B, S, D, p_out=p, seed_out=54321)
+    assert not torch.equal(y1, y3)
+    # backward with an all-ones upstream gradient: d(ln_bias)[c] = sum of the mask scale over rows == column sums of ratio
+    dy = torch.ones(B, S, D, device=dev)
+    _, _, dw_, db_, _ = ops.ln_bwd(dy, xhat, rstd, w, b, None, 0, None, B, S, D, p_out=p, seed_out=12345)
+    assert torch.allclose(db_, ratio.view(B * S, D).sum(0), rtol=1e-4)
+    # attention-weight dropout: forward (tensor-core kernel) and backward agree on the mask -> finite-difference check on V
+    set_backend('bf16x3')
+    Bq, Sq, H, dh = 2, 96, 2, 64
+    qkv = torch.randn(Bq, Sq, 3 * H * dh, generator=g).to(dev)
+    lens = torch.tensor([Sq, 70], device=dev)
+    ctx = torch.empty(Bq, Sq, H * dh, device=dev); lse = torch.empty(Bq, H, Sq, device=dev)
+    ops._call('dx_attention_fwd', qkv.data_ptr(), lens.data_ptr(), ctx.data_ptr(), lse.data_ptr(), Bq, Sq, H, dh, 0.25, 777, ops._st())
+    dctx = torch.randn(Bq, Sq, H * dh, generator=g).to(dev) * oracle.valid_mask(lens.cpu(), Sq).to(dev)[:, :, None]
+    dqkv = torch.empty_like(qkv); delta = torch.empty(Bq, H, Sq, device=dev)
+    ops._call('dx_attention_bwd', qkv.data_ptr(), lens.data_ptr(), ctx.data_ptr(), lse.data_ptr(), dctx.data_ptr(), dqkv.data_ptr(),
+              delta.data_ptr(), Bq, Sq, H, dh, 0.25, 777, ops._st())
+    # ctx is linear in V: <dctx, ctx(V + e dV)> - <dctx, ctx(V)> = e <dV_grad, dV>
+    dV = torch.zeros_like(qkv); dV[:, :, 2 * H * dh:] = torch.randn(Bq, Sq, H * dh, generator=g).to(dev)
+    ctx2 = torch.empty_like(ctx)
+    ops._call('dx_attention_fwd', (qkv + dV).data_ptr(), lens.data_ptr(), ctx2.data_ptr(), lse.data_ptr(), Bq, Sq, H, dh, 0.25, 777, ops._st())
+    lhs = ((ctx2 - ctx) * dctx).sum().item()
+    rhs = (dqkv * dV).sum().item()
+    assert abs(lhs - rhs) < 2e-3 * max(abs(lhs), abs(rhs), 1.0)

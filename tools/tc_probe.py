@@ -1,6 +1,6 @@
 """Bring-up probe for the tcgen05 GEMM: one small conv-GEMM through the C-ABI, compared with torch (run per DX_TC_DEBUG mask)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from daft_exprt_b200 import ops
 backend = sys.argv[1] if len(sys.argv) > 1 else 'bf16x3'

@@ -1,6 +1,6 @@
 """Time one conv-GEMM shape through the C-ABI (back-to-back launches, CUDA events around the loop)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from daft_exprt_b200 import ops
 backend = sys.argv[1] if len(sys.argv) > 1 else 'bf16x3'

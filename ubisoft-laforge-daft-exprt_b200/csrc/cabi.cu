@@ -82,8 +82,8 @@ int dx_split_weight_planes(const float* w_packed, void* planes, size_t n, void* 
     return split_weight_planes(w_packed, planes, n, ST(stream));
 }
 
-int dx_split_planes(const float* x, int ld, void* planes, int rows, int C, void* stream) {
-    return split_activation_planes(x, ld, planes, rows, C, ST(stream));
+int dx_split_planes(const float* x, int ld, void* planes, float* colsum_out, int rows, int C, void* stream) {
+    return split_activation_planes(x, ld, planes, colsum_out, rows, C, ST(stream));
 }
 
 size_t dx_conv_gemm_workspace(int B, int S, int Cin, int Cout, int KW, int have_x_planes, int have_w_planes, int backend) {

@@ -61,14 +61,19 @@ __device__ __forceinline__ float round_tf32(float x) {
     return __uint_as_float(r);
 }
 
-// Stateless counter-based uniform in [0,1): the same (seed, index) gives the same value in forward and backward,
-// so dropout masks are never stored.
+// Stateless counter-based dropout: the same (seed, index) gives the same decision in forward and backward, so masks are
+// never stored.  32-bit murmur3-style finaliser over (index, seed): ~10 integer instructions per element (the attention
+// kernels evaluate it once per score).  keep <=> hash >= p * 2^32.
+__device__ __forceinline__ uint32_t hash_u32(unsigned long long seed, unsigned long long idx) {
+    uint32_t x = (uint32_t)idx * 0x9E3779B1u + (uint32_t)seed;
+    x ^= (uint32_t)(idx >> 32) * 0x85EBCA77u + (uint32_t)(seed >> 32);
+    x ^= x >> 16; x *= 0x85EBCA6Bu;
+    x ^= x >> 13; x *= 0xC2B2AE35u;
+    x ^= x >> 16;
+    return x;
+}
 __device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned long long idx) {
-    unsigned long long x = seed + idx * 0x9E3779B97F4A7C15ull;
-    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
-    x ^= x >> 27; x *= 0x94D049BB133111EBull;
-    x ^= x >> 31;
-    return (float)(x >> 40) * (1.0f / 16777216.0f);
+    return (float)(hash_u32(seed, idx) >> 8) * (1.0f / 16777216.0f);
 }
 __device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned long long idx, float p, float inv_keep) {
     return hash_uniform(seed, idx) >= p ? inv_keep : 0.f;

@@ -429,16 +429,20 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 // grid (ceil(S/64), ceil(C/64), B), 256 threads; one 64(s) x 64(c) tile per block
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ src, int ld, int S, int C, int Sp,
                                                            __nv_bfloat16* __restrict__ row_hi, __nv_bfloat16* __restrict__ row_lo,
-                                                           __nv_bfloat16* __restrict__ t_hi, __nv_bfloat16* __restrict__ t_lo, int B) {
+                                                           __nv_bfloat16* __restrict__ t_hi, __nv_bfloat16* __restrict__ t_lo, int B,
+                                                           float* __restrict__ colsum = nullptr) {
     __shared__ __nv_bfloat16 th[64][72], tl[64][72];   // [c][s], padded rows (144 B: 16-byte aligned chunks)
+    __shared__ float csum[16][68];
     const int b = blockIdx.z, s0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
     const int t = threadIdx.x;
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int idx = t + 256 * i, r = idx >> 4, cq = (idx & 15) * 4;
         const int s = s0 + r, c = c0 + cq;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (s < S && c < C) v = *reinterpret_cast<const float4*>(src + ((size_t)b * S + s) * ld + c);   // C % 4 == 0
+        cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
         __nv_bfloat16 h[4], l[4];
         split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
         if (row_hi && s < S && c < C) {
@@ -449,6 +453,16 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
         if (t_hi) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) { th[cq + e][r] = h[e]; tl[cq + e][r] = l[e]; }
+        }
+    }
+    if (colsum) {   // thread (t >> 4) covers rows (t >> 4) + 16 i of column quad (t & 15): reduce the 16 row groups in smem
+        *reinterpret_cast<float4*>(&csum[t >> 4][(t & 15) * 4]) = cs;
+        __syncthreads();
+        if (t < 64 && c0 + t < C) {
+            float tot = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) tot += csum[k][t];
+            atomicAdd(colsum + c0 + t, tot);
         }
     }
     if (!t_hi) return;
@@ -556,11 +570,12 @@ inline int round8(int x) { return (x + 7) & ~7; }
 void set_tc_precision(int tf32) { g_prec = tf32 ? PREC_TF32 : PREC_BF16X3; }
 void set_tc_trace(long long* buf) { g_trace = buf; }
 
-int split_activation_planes(const float* x, int ld, void* planes, int rows, int C, cudaStream_t st) {
+int split_activation_planes(const float* x, int ld, void* planes, float* colsum_out, int rows, int C, cudaStream_t st) {
     DX_REQUIRE(C % 8 == 0 && ld % 4 == 0, "split_activation_planes: C=%d ld=%d", C, ld);
     __nv_bfloat16* hi = (__nv_bfloat16*)planes;
+    if (colsum_out) DX_CUDA(cudaMemsetAsync(colsum_out, 0, (size_t)C * sizeof(float), st));
     dim3 grid(ceil_div(rows, 64), ceil_div(C, 64), 1);
-    split_planes_kernel<<<grid, 256, 0, st>>>(x, ld, rows, C, 0, hi, hi + (size_t)rows * C, nullptr, nullptr, 1);
+    split_planes_kernel<<<grid, 256, 0, st>>>(x, ld, rows, C, 0, hi, hi + (size_t)rows * C, nullptr, nullptr, 1, colsum_out);
     return check_launch("split_planes");
 }
 

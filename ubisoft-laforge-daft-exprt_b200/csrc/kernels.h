@@ -52,7 +52,7 @@ int pack_conv_weight(const float* w, float* fwd, float* dgrad, int Cout, int Cin
 void set_tc_precision(int tf32);
 void set_tc_trace(long long* buf);
 int split_weight_planes(const float* w, void* planes, size_t n, cudaStream_t st);
-int split_activation_planes(const float* x, int ld, void* planes, int rows, int C, cudaStream_t st);
+int split_activation_planes(const float* x, int ld, void* planes, float* colsum_out, int rows, int C, cudaStream_t st);
 size_t conv_gemm_tc_workspace(const ConvGemmArgs& a);
 bool conv_gemm_tc_supported(const ConvGemmArgs& a);
 int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st);

@@ -128,14 +128,16 @@ def packed(weight):
     return fwd, dgrad
 
 
-def make_planes(x, rows, C, ld=None):
+def make_planes(x, rows, C, ld=None, want_colsum=False):
     """bf16 hi|lo operand planes of an fp32 activation [rows, C] (made ONCE, shared by every tensor-core GEMM that consumes
-    the activation: forward + wgrad, or dgrad + wgrad).  None when the active backend does not use planes."""
+    the activation: forward + wgrad, or dgrad + wgrad).  None when the active backend does not use planes.
+    want_colsum: also return the column sums of x (the bias gradient when x is an output gradient), fused into the same pass."""
     if _backend[0] == cabi.DX_GEMM_FP32_CUDA_CORES or C % 8 != 0 or C < 16:
-        return None
+        return (None, None) if want_colsum else None
     planes = torch.empty(2, rows, C, device=x.device, dtype=torch.bfloat16)
-    _call('dx_split_planes', _p(x), C if ld is None else ld, _p(planes), rows, C, _st())
-    return planes
+    cs = torch.empty(C, device=x.device, dtype=torch.float32) if want_colsum else None
+    _call('dx_split_planes', _p(x), C if ld is None else ld, _p(planes), _p(cs), rows, C, _st())
+    return (planes, cs) if want_colsum else planes
 
 
 def conv_gemm(x, wp, bias, B, S, relu=False, relu_src=None, add_src=None, alpha=1.0, round_out=False, ldx=None, x_planes=None):
@@ -158,15 +160,17 @@ def linear_rows(x2d, wp, bias, **kw):
     return conv_gemm(x2d, wp, bias, 1, R, **kw).view(R, -1)
 
 
-def conv_wgrad(x, dy, B, S, cin, cout, kw, shape, want_bias=True, ldx=None, alpha=1.0, x_planes=None, dy_planes=None):
-    """-> (dw in the parameter's own layout `shape`, dbias [Cout] or None)"""
+def conv_wgrad(x, dy, B, S, cin, cout, kw, shape, want_bias=True, ldx=None, alpha=1.0, x_planes=None, dy_planes=None, dbias=None):
+    """-> (dw in the parameter's own layout `shape`, dbias [Cout] or None).  `dbias`: already computed (fused into make_planes)."""
     dw = torch.empty(tuple(shape), device=dy.device, dtype=torch.float32)
+    if dbias is not None:
+        want_bias = False
     db = torch.empty(cout, device=dy.device, dtype=torch.float32) if want_bias else None
     nbytes = lib().dx_conv_wgrad_workspace(B, S, cin, cout, kw, int(x_planes is not None), int(dy_planes is not None), -1)
     ws = torch.empty(max(nbytes, 16) // 4 + 4, device=dy.device, dtype=torch.float32)
     _call('dx_conv_wgrad', _p(x), _p(x_planes), _p(dy), _p(dy_planes), _p(dw), _p(db), _p(ws), ws.numel() * 4, B, S, cin, cout, kw,
           cin if ldx is None else ldx, float(alpha), -1, _st())
-    return dw, db
+    return dw, (dbias if dbias is not None else db)
 
 
 def ln_fwd(a, res, ln_w, ln_b, film, film_stride, lens, B, S, D, p_in=0.0, seed_in=0, p_out=0.0, seed_out=0):
@@ -222,16 +226,16 @@ class AttentionSubLayer(torch.autograd.Function):
         B, S, D, H, dh, p, seed_attn, seed_out, in_shape, out_shape = ctx.cfg
         dy = _check_input(dy)
         dv, dproj, dln_w, dln_b, _ = ln_bwd(dy, xhat, rstd, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p, seed_in=seed_out)
-        dprojP = make_planes(dproj, B * S, D)
+        dprojP, dpb = make_planes(dproj, B * S, D, want_colsum=True)
         datt = conv_gemm(dproj, out_wd, None, 1, B * S, x_planes=dprojP)
-        d_out_w, d_out_b = conv_wgrad(att, dproj, B, S, D, D, 1, out_shape, x_planes=attP, dy_planes=dprojP)
+        d_out_w, d_out_b = conv_wgrad(att, dproj, B, S, D, D, 1, out_shape, x_planes=attP, dy_planes=dprojP, dbias=dpb)
         dqkv = torch.empty(B, S, 3 * D, device=dy.device, dtype=torch.float32)
         delta = torch.empty(B, H, S, device=dy.device, dtype=torch.float32)
         _call('dx_attention_bwd', _p(qkv), _p(lens), _p(att), _p(lse), _p(datt), _p(dqkv), _p(delta), B, S, H, dh, p,
               seed_attn, _st())
-        dqkvP = make_planes(dqkv, B * S, 3 * D)
+        dqkvP, dqb = make_planes(dqkv, B * S, 3 * D, want_colsum=True)
         dx = conv_gemm(dqkv, in_wd, None, 1, B * S, add_src=dv, x_planes=dqkvP).view(B, S, D)
-        d_in_w, d_in_b = conv_wgrad(x, dqkv, B, S, D, 3 * D, 1, in_shape, x_planes=xP, dy_planes=dqkvP)
+        d_in_w, d_in_b = conv_wgrad(x, dqkv, B, S, D, 3 * D, 1, in_shape, x_planes=xP, dy_planes=dqkvP, dbias=dqb)
         return dx, None, d_in_w, d_in_b, d_out_w, d_out_b, dln_w, dln_b, None, None
 
 
@@ -267,12 +271,12 @@ class ConvFFSubLayer(torch.autograd.Function):
         dy = _check_input(dy)
         dv, do, dln_w, dln_b, dfilm = ln_bwd(dy, xhat, rstd, ln_w, ln_b, film, 2 * D, lens, B, S, D, p_in=p, seed_in=seed,
                                              want_film=film is not None)
-        doP = make_planes(do, B * S, D)
+        doP, dob = make_planes(do, B * S, D, want_colsum=True)
         dh = conv_gemm(do, w2d, None, B, S, relu_src=h, round_out=True, x_planes=doP)
-        dw2, db2 = conv_wgrad(h, do, B, S, C, D, w2_shape[2], w2_shape, x_planes=hP, dy_planes=doP)
-        dhP = make_planes(dh, B * S, C)
+        dw2, db2 = conv_wgrad(h, do, B, S, C, D, w2_shape[2], w2_shape, x_planes=hP, dy_planes=doP, dbias=dob)
+        dhP, dhb = make_planes(dh, B * S, C, want_colsum=True)
         dx = conv_gemm(dh, w1d, None, B, S, add_src=dv, x_planes=dhP)
-        dw1, db1 = conv_wgrad(x, dh, B, S, D, C, w1_shape[2], w1_shape, x_planes=xP, dy_planes=dhP)
+        dw1, db1 = conv_wgrad(x, dh, B, S, D, C, w1_shape[2], w1_shape, x_planes=xP, dy_planes=dhP, dbias=dhb)
         return dx, None, dw1, db1, dw2, db2, dln_w, dln_b, dfilm, None
 
 
@@ -320,8 +324,8 @@ class PreNet(torch.autograd.Function):
             cout, cin, kw = shapes[i]
             inp = x if i == 0 else layers[i - 1][5]
             dpre, _, dg, de, _ = ln_bwd(d, xhat, rstd, g, e, None, 0, None, B, T, cout, relu_src=a, p_out=p, seed_out=seeds[i])
-            dpreP = make_planes(dpre, B * T, cout)
-            dw, db = conv_wgrad(inp, dpre, B, T, cin, cout, kw, shapes[i], x_planes=ctx.in_planes[i], dy_planes=dpreP)
+            dpreP, dpreb = make_planes(dpre, B * T, cout, want_colsum=True)
+            dw, db = conv_wgrad(inp, dpre, B, T, cin, cout, kw, shapes[i], x_planes=ctx.in_planes[i], dy_planes=dpreP, dbias=dpreb)
             grads[4 * i: 4 * i + 4] = [dw, db, dg, de]
             if i > 0:
                 d = conv_gemm(dpre, wd, None, B, T, x_planes=dpreP)
