@@ -73,11 +73,16 @@ int dx_scale_copy(const float* x, float* y, float alpha, size_t n, void* stream)
 /* ---- multi-head self-attention core (flash style, S x S never materialised) ------------------------------------------
  * replaces nn.MultiheadAttention's scaled-dot-product part as called at model.py:182-186 (key_padding_mask from lengths).
  * qkv [B,S,3*H*dh] = in-projection output (q|k|v); ctx [B,S,H*dh]; lse [B,H,S]; padded query rows are written as 0. */
-int dx_attention_fwd(const float* qkv, const int64_t* lens, float* ctx, float* lse, int B, int S, int H, int dh,
+/* planes: workspace of dx_attention_planes_bytes() written by the forward (per-head bf16 hi|lo operand planes of q|k|v used by
+ * the tensor-core kernels) and handed back to the backward; may be NULL with the fp32 backend. */
+size_t dx_attention_planes_bytes(int B, int S, int H, int dh);
+size_t dx_attention_bwd_scratch_bytes(int B, int S, int H, int dh);
+int dx_attention_fwd(const float* qkv, const int64_t* lens, float* ctx, float* lse, void* planes, int B, int S, int H, int dh,
                      float dropout_p, uint64_t seed, void* stream);
-/* delta: scratch [B,H,S]; dqkv [B,S,3*H*dh] is fully written */
-int dx_attention_bwd(const float* qkv, const int64_t* lens, const float* ctx, const float* lse, const float* dctx, float* dqkv,
-                     float* delta, int B, int S, int H, int dh, float dropout_p, uint64_t seed, void* stream);
+/* scratch: dx_attention_bwd_scratch_bytes() bytes; dqkv [B,S,3*H*dh] is fully written */
+int dx_attention_bwd(const float* qkv, const void* planes, const int64_t* lens, const float* ctx, const float* lse,
+                     const float* dctx, float* dqkv, void* scratch, int B, int S, int H, int dh, float dropout_p, uint64_t seed,
+                     void* stream);
 
 /* ---- residual + LayerNorm + FiLM + padding mask ----------------------------------------------------------------------
  * v = dropout_in(a) + res;  y = mask(film_gamma * dropout_out(LN(v)*w + b) + film_beta)

@@ -131,12 +131,13 @@ def test_attention_forward_backward(dev, cfg, backend):
     qd, ld = qkv.to(dev), lens.to(dev)
     ctx = torch.empty(B, S, D, device=dev)
     lse = torch.empty(B, H, S, device=dev)
-    ops._call('dx_attention_fwd', qd.data_ptr(), ld.data_ptr(), ctx.data_ptr(), lse.data_ptr(), B, S, H, dh, 0.0, 0, ops._st())
+    planes = ops.attention_planes(B, S, H, dh, dev)
+    ops._call('dx_attention_fwd', qd.data_ptr(), ld.data_ptr(), ctx.data_ptr(), lse.data_ptr(), ops._p(planes), B, S, H, dh, 0.0, 0, ops._st())
     assert scale_rel_err(ctx, ctx_ref.detach()) < (2e-5 if backend == 'fp32' else 5e-5)
     dqkv = torch.empty(B, S, 3 * D, device=dev)
-    delta = torch.empty(B, H, S, device=dev)
-    ops._call('dx_attention_bwd', qd.data_ptr(), ld.data_ptr(), ctx.data_ptr(), lse.data_ptr(), dctx.to(dev).data_ptr(),
-              dqkv.data_ptr(), delta.data_ptr(), B, S, H, dh, 0.0, 0, ops._st())
+    scratch = torch.empty(ops.lib().dx_attention_bwd_scratch_bytes(B, S, H, dh), device=dev, dtype=torch.uint8)
+    ops._call('dx_attention_bwd', qd.data_ptr(), ops._p(planes), ld.data_ptr(), ctx.data_ptr(), lse.data_ptr(), dctx.to(dev).data_ptr(),
+              dqkv.data_ptr(), scratch.data_ptr(), B, S, H, dh, 0.0, 0, ops._st())
     ref_g = q64.grad * 1.0
     # gradients wrt padded rows of q/k/v are exactly zero in both
     assert scale_rel_err(dqkv, ref_g) < (5e-5 if backend == 'fp32' else 2e-4)
@@ -419,15 +420,18 @@ def test_dropout_statistics_and_mask_consistency(dev):
     qkv = torch.randn(Bq, Sq, 3 * H * dh, generator=g).to(dev)
     lens = torch.tensor([Sq, 70], device=dev)
     ctx = torch.empty(Bq, Sq, H * dh, device=dev); lse = torch.empty(Bq, H, Sq, device=dev)
-    ops._call('dx_attention_fwd', qkv.data_ptr(), lens.data_ptr(), ctx.data_ptr(), lse.data_ptr(), Bq, Sq, H, dh, 0.25, 777, ops._st())
+    planes = ops.attention_planes(Bq, Sq, H, dh, dev)
+    ops._call('dx_attention_fwd', qkv.data_ptr(), lens.data_ptr(), ctx.data_ptr(), lse.data_ptr(), ops._p(planes), Bq, Sq, H, dh, 0.25, 777, ops._st())
     dctx = torch.randn(Bq, Sq, H * dh, generator=g).to(dev) * oracle.valid_mask(lens.cpu(), Sq).to(dev)[:, :, None]
-    dqkv = torch.empty_like(qkv); delta = torch.empty(Bq, H, Sq, device=dev)
-    ops._call('dx_attention_bwd', qkv.data_ptr(), lens.data_ptr(), ctx.data_ptr(), lse.data_ptr(), dctx.data_ptr(), dqkv.data_ptr(),
-              delta.data_ptr(), Bq, Sq, H, dh, 0.25, 777, ops._st())
+    dqkv = torch.empty_like(qkv)
+    scratch = torch.empty(ops.lib().dx_attention_bwd_scratch_bytes(Bq, Sq, H, dh), device=dev, dtype=torch.uint8)
+    ops._call('dx_attention_bwd', qkv.data_ptr(), ops._p(planes), lens.data_ptr(), ctx.data_ptr(), lse.data_ptr(), dctx.data_ptr(),
+              dqkv.data_ptr(), scratch.data_ptr(), Bq, Sq, H, dh, 0.25, 777, ops._st())
     # ctx is linear in V: <dctx, ctx(V + e dV)> - <dctx, ctx(V)> = e <dV_grad, dV>
     dV = torch.zeros_like(qkv); dV[:, :, 2 * H * dh:] = torch.randn(Bq, Sq, H * dh, generator=g).to(dev)
     ctx2 = torch.empty_like(ctx)
-    ops._call('dx_attention_fwd', (qkv + dV).data_ptr(), lens.data_ptr(), ctx2.data_ptr(), lse.data_ptr(), Bq, Sq, H, dh, 0.25, 777, ops._st())
+    planes2 = ops.attention_planes(Bq, Sq, H, dh, dev)
+    ops._call('dx_attention_fwd', (qkv + dV).data_ptr(), lens.data_ptr(), ctx2.data_ptr(), lse.data_ptr(), ops._p(planes2), Bq, Sq, H, dh, 0.25, 777, ops._st())
     lhs = ((ctx2 - ctx) * dctx).sum().item()
     rhs = (dqkv * dV).sum().item()
     assert abs(lhs - rhs) < 2e-3 * max(abs(lhs), abs(rhs), 1.0)

@@ -139,27 +139,30 @@ int dx_colsum(const float* dy, float* db, int rows, int C, float alpha, void* st
 int dx_relu_bwd(const float* dy, const float* y, float* dx_, size_t n, void* stream) { return relu_bwd(dy, y, dx_, n, ST(stream)); }
 int dx_scale_copy(const float* x, float* y, float alpha, size_t n, void* stream) { return scale_copy(x, y, alpha, n, ST(stream)); }
 
-int dx_attention_fwd(const float* qkv, const int64_t* lens, float* ctx, float* lse, int B, int S, int H, int dh,
+size_t dx_attention_planes_bytes(int B, int S, int H, int dh) { return attention_planes_bytes(B, S, H, dh); }
+size_t dx_attention_bwd_scratch_bytes(int B, int S, int H, int dh) { return attention_bwd_scratch_bytes(B, S, H, dh); }
+
+int dx_attention_fwd(const float* qkv, const int64_t* lens, float* ctx, float* lse, void* planes, int B, int S, int H, int dh,
                      float dropout_p, uint64_t seed, void* stream) {
     AttnArgs a;
     memset(&a, 0, sizeof(a));
     a.qkv = qkv; a.lens = (cll)lens; a.ctx = ctx; a.lse = lse; a.B = B; a.S = S; a.H = H; a.dh = dh;
     a.dropout_p = dropout_p; a.seed = seed;
-    if (g_backend != DX_GEMM_FP32_CUDA_CORES && attention_mma_supported(a)) return attention_fwd_mma(a, ST(stream));
+    if (g_backend != DX_GEMM_FP32_CUDA_CORES && attention_mma_supported(a)) return attention_fwd_mma(a, planes, ST(stream));
     return attention_fwd(a, ST(stream));
 }
 
-int dx_attention_bwd(const float* qkv, const int64_t* lens, const float* ctx, const float* lse, const float* dctx, float* dqkv,
-                     float* delta, int B, int S, int H, int dh, float dropout_p, uint64_t seed, void* stream) {
+int dx_attention_bwd(const float* qkv, const void* planes, const int64_t* lens, const float* ctx, const float* lse,
+                     const float* dctx, float* dqkv, void* scratch, int B, int S, int H, int dh, float dropout_p, uint64_t seed,
+                     void* stream) {
     AttnArgs a;
     memset(&a, 0, sizeof(a));
-    a.qkv = qkv; a.lens = (cll)lens; a.ctx = (float*)ctx; a.lse = (float*)lse; a.dctx = dctx; a.dqkv = dqkv; a.delta = delta;
+    a.qkv = qkv; a.lens = (cll)lens; a.ctx = (float*)ctx; a.lse = (float*)lse; a.dctx = dctx; a.dqkv = dqkv;
     a.B = B; a.S = S; a.H = H; a.dh = dh; a.dropout_p = dropout_p; a.seed = seed;
-    if (g_backend != DX_GEMM_FP32_CUDA_CORES && attention_mma_supported(a)) {
-        int rc = attention_bwd_prepare(a, ST(stream));
-        if (rc) return rc;
-        return attention_bwd_mma(a, ST(stream));
-    }
+    DX_REQUIRE(scratch != nullptr, "dx_attention_bwd: scratch (dx_attention_bwd_scratch_bytes) required");
+    if (g_backend != DX_GEMM_FP32_CUDA_CORES && attention_mma_supported(a))
+        return attention_bwd_mma(a, (void*)planes, scratch, ST(stream));
+    a.delta = (float*)scratch;
     return attention_bwd(a, ST(stream));
 }
 

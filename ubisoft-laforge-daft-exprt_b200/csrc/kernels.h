@@ -1,5 +1,6 @@
 // Internal C++ launcher API shared by the .cu files; the public C-ABI over these is in cabi.cu / include/daft_exprt_b200.h.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -72,12 +73,18 @@ struct AttnArgs {
     int B, S, H, dh;
     float dropout_p;
     unsigned long long seed;
+    // tensor-core path: per-head bf16 hi|lo operand planes (attention_mma.cu), S padded to Sp (multiple of 64)
+    const __nv_bfloat16 *R, *Tr;     // of qkv:  [2][B][3H][Sp][dh] row-major / [2][B][3H][dh][Sp] transposed
+    const __nv_bfloat16 *GR, *GTr;   // of dctx: [2][B][H][Sp][dh] / [2][B][H][dh][Sp]
+    int Sp;
 };
 int attention_fwd(const AttnArgs& a, cudaStream_t st);
 // tensor-core (mma.sync bf16x3) variants, attention_mma.cu
 bool attention_mma_supported(const AttnArgs& a);
-int attention_fwd_mma(const AttnArgs& a, cudaStream_t st);
-int attention_bwd_mma(const AttnArgs& a, cudaStream_t st);
+int attention_fwd_mma(const AttnArgs& a, void* planes, cudaStream_t st);
+int attention_bwd_mma(const AttnArgs& a, void* planes, void* scratch, cudaStream_t st);
+size_t attention_planes_bytes(int B, int S, int H, int dh);
+size_t attention_bwd_scratch_bytes(int B, int S, int H, int dh);
 int attention_bwd_prepare(const AttnArgs& a, cudaStream_t st);   // delta + zero dqkv
 int attention_bwd(const AttnArgs& a, cudaStream_t st);
 

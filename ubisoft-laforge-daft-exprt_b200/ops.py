@@ -173,6 +173,13 @@ def conv_wgrad(x, dy, B, S, cin, cout, kw, shape, want_bias=True, ldx=None, alph
     return dw, (dbias if dbias is not None else db)
 
 
+def attention_planes(B, S, H, dh, device):
+    """Workspace for the tensor-core attention's operand planes (None with the exact-fp32 backend)."""
+    if _backend[0] == cabi.DX_GEMM_FP32_CUDA_CORES:
+        return None
+    return torch.empty(lib().dx_attention_planes_bytes(B, S, H, dh), device=device, dtype=torch.uint8)
+
+
 def ln_fwd(a, res, ln_w, ln_b, film, film_stride, lens, B, S, D, p_in=0.0, seed_in=0, p_out=0.0, seed_out=0):
     y = torch.empty(B, S, D, device=a.device, dtype=torch.float32)
     xhat = torch.empty(B, S, D, device=a.device, dtype=torch.float32)
@@ -210,18 +217,19 @@ class AttentionSubLayer(torch.autograd.Function):
         att = torch.empty(B, S, D, device=x.device, dtype=torch.float32)
         lse = torch.empty(B, nb_heads, S, device=x.device, dtype=torch.float32)
         seed_attn, seed_out = (next_seed(), next_seed()) if p_drop > 0 else (0, 0)
-        _call('dx_attention_fwd', _p(qkv), _p(lens), _p(att), _p(lse), B, S, nb_heads, dh, float(p_drop), seed_attn, _st())
+        planes = attention_planes(B, S, nb_heads, dh, x.device)
+        _call('dx_attention_fwd', _p(qkv), _p(lens), _p(att), _p(lse), _p(planes), B, S, nb_heads, dh, float(p_drop), seed_attn, _st())
         attP = make_planes(att, B * S, D)
         proj = conv_gemm(att, out_wp, out_b, 1, B * S, x_planes=attP)
         y, xhat, rstd = ln_fwd(proj, x, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p_drop, seed_in=seed_out)
-        ctx.save_for_backward(x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b, xP, attP)
+        ctx.save_for_backward(x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b, xP, attP, planes)
         ctx.packed = (in_wd, out_wd)
         ctx.cfg = (B, S, D, nb_heads, dh, float(p_drop), seed_attn, seed_out, in_w.shape, out_w.shape)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b, xP, attP = ctx.saved_tensors
+        x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b, xP, attP, planes = ctx.saved_tensors
         in_wd, out_wd = ctx.packed
         B, S, D, H, dh, p, seed_attn, seed_out, in_shape, out_shape = ctx.cfg
         dy = _check_input(dy)
@@ -230,8 +238,8 @@ class AttentionSubLayer(torch.autograd.Function):
         datt = conv_gemm(dproj, out_wd, None, 1, B * S, x_planes=dprojP)
         d_out_w, d_out_b = conv_wgrad(att, dproj, B, S, D, D, 1, out_shape, x_planes=attP, dy_planes=dprojP, dbias=dpb)
         dqkv = torch.empty(B, S, 3 * D, device=dy.device, dtype=torch.float32)
-        delta = torch.empty(B, H, S, device=dy.device, dtype=torch.float32)
-        _call('dx_attention_bwd', _p(qkv), _p(lens), _p(att), _p(lse), _p(datt), _p(dqkv), _p(delta), B, S, H, dh, p,
+        scratch = torch.empty(lib().dx_attention_bwd_scratch_bytes(B, S, H, dh), device=dy.device, dtype=torch.uint8)
+        _call('dx_attention_bwd', _p(qkv), _p(planes), _p(lens), _p(att), _p(lse), _p(datt), _p(dqkv), _p(scratch), B, S, H, dh, p,
               seed_attn, _st())
         dqkvP, dqb = make_planes(dqkv, B * S, 3 * D, want_colsum=True)
         dx = conv_gemm(dqkv, in_wd, None, 1, B * S, add_src=dv, x_planes=dqkvP).view(B, S, D)
