@@ -45,8 +45,11 @@ int dx_debug_set_trace(void* buf);
 /* ---- Conv1d / Linear as channels-last GEMMs --------------------------------------------------------------------------
  * replaces nn.Conv1d inside ConvNorm1D (model.py:82,86-94) and nn.Linear inside LinearNorm (model.py:63,66-72), incl. the
  * in/out projections of nn.MultiheadAttention (model.py:165).  Weights are consumed in a packed, cached layout. */
-/* w [Cout][Cin][KW] (the parameter) -> fwd [KW][Cout][Cin] and dgrad [KW][Cin][Cout] with taps flipped (either may be NULL) */
-int dx_pack_conv_weight(const float* w, float* fwd, float* dgrad, int Cout, int Cin, int KW, int round_tf32, void* stream);
+/* w [Cout][Cin][KW] (the parameter) -> fwd [KW][Cout][Cin] and dgrad [KW][Cin][Cout] with taps flipped (either may be NULL);
+ * fwd_planes / dgrad_planes (nullable): bf16 hi|lo planes of the same packed layouts (2 * KW*Cout*Cin bf16 each), fused in the
+ * same pass (what dx_split_weight_planes would produce). */
+int dx_pack_conv_weight(const float* w, float* fwd, float* dgrad, void* fwd_planes, void* dgrad_planes, int Cout, int Cin, int KW,
+                        int round_tf32, void* stream);
 /* y[b,s,n] = epi(alpha * sum_{tap,c} x[b, s+tap-(KW-1)/2, c] * w[tap][n][c] + bias[n]); zero padding at s<0, s>=S only.
  * epi: relu, then multiply by (relu_src > 0) when relu_src != NULL (ReLU backward fused into a dgrad), then + add_src
  * (same layout as y; residual / gradient accumulation) when != NULL, then optional tf32 rounding of the stored value.  backend < 0 selects the global default. */

@@ -63,8 +63,9 @@ int dx_set_gemm_backend(int backend) {
 int dx_get_gemm_backend(void) { return g_backend; }
 int dx_debug_set_trace(void* buf) { set_tc_trace((long long*)buf); return DX_OK; }
 
-int dx_pack_conv_weight(const float* w, float* fwd, float* dgrad, int Cout, int Cin, int KW, int round_tf32, void* stream) {
-    return pack_conv_weight(w, fwd, dgrad, Cout, Cin, KW, round_tf32, ST(stream));
+int dx_pack_conv_weight(const float* w, float* fwd, float* dgrad, void* fwd_planes, void* dgrad_planes, int Cout, int Cin, int KW,
+                        int round_tf32, void* stream) {
+    return pack_conv_weight(w, fwd, dgrad, fwd_planes, dgrad_planes, Cout, Cin, KW, round_tf32, ST(stream));
 }
 
 static ConvGemmArgs gemm_args(const float* x, const void* x_planes, const float* w_packed, const void* w_planes, const float* bias,

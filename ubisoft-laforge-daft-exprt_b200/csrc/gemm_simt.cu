@@ -6,6 +6,8 @@
 //
 // Conv1d over the padded [B, S, C] layout, reference model.py:86-94 (ConvNorm1D) — stride 1, zero 'same' padding at
 // s = -1 and s = S only (no masking between convs: the halo leak of SURVEY.md §0.6 is reproduced by construction).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -263,7 +265,9 @@ int conv_wgrad_simt(const ConvWgradArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------------------------
 // weight repacks: parameter layout [Cout][Cin][KW]  ->  fwd [KW][Cout][Cin]  and  dgrad [KW][Cin][Cout] (taps flipped)
 // ---------------------------------------------------------------------------------------------------------------------
+// optional fwd_planes / dgrad_planes: bf16 hi plane followed by lo plane (n elements each) in the same packed layouts
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, float* __restrict__ fwd, float* __restrict__ dgrad,
+                                        __nv_bfloat16* __restrict__ fwd_planes, __nv_bfloat16* __restrict__ dgrad_planes,
                                         int Cout, int Cin, int KW, int round) {
     const size_t n = (size_t)Cout * Cin * KW;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -272,15 +276,23 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, float* __re
         const int ci = (int)(q % Cin), co = (int)(q / Cin);
         float v = w[i];
         if (round) v = round_tf32(v);
-        if (fwd) fwd[((size_t)tap * Cout + co) * Cin + ci] = v;
-        if (dgrad) dgrad[((size_t)(KW - 1 - tap) * Cin + ci) * Cout + co] = v;
+        const size_t of = ((size_t)tap * Cout + co) * Cin + ci, od = ((size_t)(KW - 1 - tap) * Cin + ci) * Cout + co;
+        if (fwd) fwd[of] = v;
+        if (dgrad) dgrad[od] = v;
+        if (fwd_planes || dgrad_planes) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v), lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+            if (fwd_planes) { fwd_planes[of] = hi; fwd_planes[n + of] = lo; }
+            if (dgrad_planes) { dgrad_planes[od] = hi; dgrad_planes[n + od] = lo; }
+        }
     }
 }
 
-int pack_conv_weight(const float* w, float* fwd, float* dgrad, int Cout, int Cin, int KW, int round, cudaStream_t st) {
+int pack_conv_weight(const float* w, float* fwd, float* dgrad, void* fwd_planes, void* dgrad_planes, int Cout, int Cin, int KW,
+                     int round, cudaStream_t st) {
     const size_t n = (size_t)Cout * Cin * KW;
     const int blocks = grid_1d(n);
-    pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(w, fwd, dgrad, Cout, Cin, KW, round);
+    pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(w, fwd, dgrad, (__nv_bfloat16*)fwd_planes, (__nv_bfloat16*)dgrad_planes, Cout, Cin,
+                                                     KW, round);
     return check_launch("pack_conv_weight");
 }
 

@@ -391,26 +391,28 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                         for (int i = 0; i < 32; ++i) o[i] = round_tf32(o[i]);
                     }
                 }
-                // staging buffer (j & 1): the TMA store that last read it (2 chunks ago) must have finished reading
-                if (et == 0) tma_store_wait_read<1>();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const uint32_t obuf = sOut + (j & 1) * OUT_BYTES + row * 128;
+                // each epilogue warp stages and stores its own 32 rows x 32 columns (4 KB, two buffers per warp): no
+                // cross-warp barrier.  Buffer (j & 1): the TMA store that last read it (2 chunks ago) must be done reading.
+                if (lane == 0) tma_store_wait_read<1>();
+                __syncwarp();
+                const uint32_t wbuf = sOut + (quad * 2 + (j & 1)) * (32 * 128);
+                const uint32_t obuf = wbuf + lane * 128;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {   // 16-byte chunk c of this row lands at chunk (c ^ (row & 7)): SWIZZLE_128B
-                    const uint32_t dst = obuf + ((c ^ (row & 7)) << 4);
+                    const uint32_t dst = obuf + ((c ^ (lane & 7)) << 4);
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o[4 * c]), "f"(o[4 * c + 1]),
                                  "f"(o[4 * c + 2]), "f"(o[4 * c + 3]) : "memory");
                 }
                 fence_async_smem();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (et == 0 && !(p.debug & 8)) {
-                    tma_store_3d(&map_y, sOut + (j & 1) * OUT_BYTES, nb, t.o1, t.o2);
+                __syncwarp();
+                if (lane == 0 && !(p.debug & 8)) {
+                    tma_store_3d(&map_y, wbuf, nb, t.o1 + quad * 32, t.o2);
                     tma_store_commit();
                 }
             }
             if (p.trace && blockIdx.x == 0 && et == 0 && it < 256) p.trace[3 * 256 + it] = clock64();
         }
-        if (et == 0) tma_store_wait_all();
+        if (lane == 0) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -612,7 +614,7 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     p.trace = g_trace;
     CUtensorMap mxh, mxl, mwh, mwl, my;
     int rc;
-    if ((rc = make_map_3d(&my, a.y, 4, a.Cout, a.S, a.B, (uint64_t)a.ldy * 4, (uint64_t)a.S * a.ldy * 4, 32, TM, 1))) return rc;
+    if ((rc = make_map_3d(&my, a.y, 4, a.Cout, a.S, a.B, (uint64_t)a.ldy * 4, (uint64_t)a.S * a.ldy * 4, 32, 32, 1))) return rc;
     if (g_prec == PREC_TF32) {
         p.k_chunks = ceil_div(a.Cin, Cfg<PREC_TF32>::TKB);
         if ((rc = make_map_3d(&mxh, a.x, 4, a.Cin, a.S, a.B, (uint64_t)a.ldx * 4, (uint64_t)a.S * a.ldx * 4, 32, TM, 1))) return rc;
@@ -753,7 +755,7 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
     if ((rc = make_map_3d(&mal, dl, 2, a.Cout, a.S, a.B, d1, d2, 64, 64, 1))) return rc;
     if ((rc = make_map_3d(&mbh, xh, 2, a.Cin, a.S, a.B, x1, x2, 64, 64, 1))) return rc;
     if ((rc = make_map_3d(&mbl, xl, 2, a.Cin, a.S, a.B, x1, x2, 64, 64, 1))) return rc;
-    if ((rc = make_map_3d(&my, part, 4, a.Cin, a.Cout, (uint64_t)nsplit * a.KW, (uint64_t)a.Cin * 4, (uint64_t)a.Cout * a.Cin * 4, 32, TM, 1)))
+    if ((rc = make_map_3d(&my, part, 4, a.Cin, a.Cout, (uint64_t)nsplit * a.KW, (uint64_t)a.Cin * 4, (uint64_t)a.Cout * a.Cin * 4, 32, 32, 1)))
         return rc;
     if ((rc = launch<PREC_BF16X3, MODE_WGRAD>(mah, mal, mbh, mbl, my, p, st))) return rc;
     const size_t per = (size_t)a.KW * a.Cout * a.Cin;

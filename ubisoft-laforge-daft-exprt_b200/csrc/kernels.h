@@ -47,7 +47,8 @@ int conv_gemm_simt(const ConvGemmArgs& a, cudaStream_t st);
 int conv_wgrad_simt(const ConvWgradArgs& a, cudaStream_t st);
 size_t conv_wgrad_simt_workspace(const ConvWgradArgs& a, int* nsplit_out);
 int colsum(const float* dy, float* db, int R, int C, float alpha, cudaStream_t st);
-int pack_conv_weight(const float* w, float* fwd, float* dgrad, int Cout, int Cin, int KW, int round, cudaStream_t st);
+int pack_conv_weight(const float* w, float* fwd, float* dgrad, void* fwd_planes, void* dgrad_planes, int Cout, int Cin, int KW,
+                     int round, cudaStream_t st);
 
 // tcgen05 / TMEM / TMA path (gemm_tcgen05.cu)
 void set_tc_precision(int tf32);

@@ -100,16 +100,9 @@ class PackedWeight:
         self.w, self.planes, self.shape = w, planes, tuple(w.shape)
 
 
-def _make_packed(t):
-    planes = None
-    if _backend[0] == cabi.DX_GEMM_TCGEN05_BF16X3:
-        planes = torch.empty(2 * t.numel(), device=t.device, dtype=torch.bfloat16)
-        _call('dx_split_weight_planes', _p(t), _p(planes), t.numel(), _st())
-    return PackedWeight(t, planes)
-
-
 def packed(weight):
-    """weight [Cout, Cin, KW] or [Cout, Cin] -> (fwd [KW, Cout, Cin], dgrad [KW, Cin, Cout] taps flipped) PackedWeights."""
+    """weight [Cout, Cin, KW] or [Cout, Cin] -> (fwd [KW, Cout, Cin], dgrad [KW, Cin, Cout] taps flipped) PackedWeights;
+    one fused launch makes both fp32 packs and (bf16x3 backend) their bf16 hi|lo planes."""
     w = weight.detach()
     key = id(weight)
     ver = (w.data_ptr(), w._version, _weights_epoch, _backend[0])
@@ -122,8 +115,12 @@ def packed(weight):
     fwd = torch.empty(kw, cout, cin, device=w.device, dtype=torch.float32)
     dgrad = torch.empty(kw, cin, cout, device=w.device, dtype=torch.float32)
     rnd = 1 if _backend[0] == cabi.DX_GEMM_TCGEN05_TF32 else 0
-    _call('dx_pack_conv_weight', _p(w), _p(fwd), _p(dgrad), cout, cin, kw, rnd, _st())
-    fwd, dgrad = _make_packed(fwd), _make_packed(dgrad)
+    fp = dp = None
+    if _backend[0] == cabi.DX_GEMM_TCGEN05_BF16X3:
+        fp = torch.empty(2 * fwd.numel(), device=w.device, dtype=torch.bfloat16)
+        dp = torch.empty(2 * fwd.numel(), device=w.device, dtype=torch.bfloat16)
+    _call('dx_pack_conv_weight', _p(w), _p(fwd), _p(dgrad), _p(fp), _p(dp), cout, cin, kw, rnd, _st())
+    fwd, dgrad = PackedWeight(fwd, fp), PackedWeight(dgrad, dp)
     _pack_cache[key] = (ver, fwd, dgrad, weakref.ref(weight))
     return fwd, dgrad
 
