@@ -215,7 +215,7 @@ def main():
     broadcast_parameters(model)
     crit = DaftExprtLoss(local_rank, hp)
     params = list(model.parameters())
-    sync = FlatGradSync(params)
+    sync = FlatGradSync(params, mode='gather')
     opt = FlatAdam(params, sync, lr=hp.initial_learning_rate, betas=hp.betas, eps=hp.epsilon, weight_decay=hp.weight_decay)
 
     host_batch = make_host_batch(rank)

@@ -33,6 +33,14 @@ def _worker(rank, world, port, ret):
     model(x).pow(2).mean().backward()
     assert sync.grads_attached()                        # autograd accumulated into the flat buffer in place
     sync.all_reduce_mean()
+    # the 'gather' mode must give the same bucket without aliasing
+    model2 = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    model2.load_state_dict(model.state_dict())
+    sync2 = FlatGradSync(model2.parameters(), mode='gather')
+    sync2.zero_grad()
+    model2(x).pow(2).mean().backward()
+    sync2.all_reduce_mean()
+    assert torch.allclose(torch.cat([v.reshape(-1) for v in sync2.views]), torch.cat([p.grad.reshape(-1) for p in model.parameters()]))
     ret[rank] = (torch.cat([p.grad.reshape(-1) for p in model.parameters()]), torch.cat([p.data.reshape(-1) for p in model.parameters()]))
     dist.destroy_process_group()
 

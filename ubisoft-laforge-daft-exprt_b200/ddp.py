@@ -14,12 +14,21 @@ ALIGN = 64   # elements (256 bytes of fp32)
 
 
 class FlatGradSync:
-    """Makes all gradients views of one flat buffer and averages it across ranks with one collective."""
+    """One flat fp32 gradient bucket for all parameters, averaged across ranks with one collective.
 
-    def __init__(self, params, process_group=None):
+    mode='alias'  : every `p.grad` is a view of the flat buffer; autograd accumulates into it in place (one small add kernel
+                    per parameter per backward) — the layout stock optimisers can also consume.
+    mode='gather' : gradients are left to autograd (`p.grad = None` before backward, so AccumulateGrad just keeps the tensors
+                    the backward kernels produced: no add kernels, no zeroing pass) and are packed into the flat buffer by ONE
+                    multi-tensor copy before the all-reduce.  Used by bench.py.
+    """
+
+    def __init__(self, params, process_group=None, mode='alias'):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError('no trainable parameters')
+        assert mode in ('alias', 'gather')
+        self.mode = mode
         dev, dt = self.params[0].device, self.params[0].dtype
         self.numel = sum(p.numel() for p in self.params)
         # every slot starts on a 256-byte boundary: the kernels use 16-byte vector loads on parameters and gradients
@@ -30,17 +39,37 @@ class FlatGradSync:
         self.padded_numel = off
         self.flat = torch.zeros(self.padded_numel, device=dev, dtype=dt)
         self.group = process_group
-        for p, off in zip(self.params, self.offsets):
-            p.grad = self.flat[off:off + p.numel()].view_as(p)   # autograd accumulates in place into existing .grad
+        self.views = [self.flat[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
+        if mode == 'alias':
+            for p, v in zip(self.params, self.views):
+                p.grad = v   # autograd accumulates in place into existing .grad
 
     def zero_grad(self):
-        self.flat.zero_()
+        if self.mode == 'alias':
+            self.flat.zero_()
+        else:
+            for p in self.params:
+                p.grad = None
+
+    def gather(self):
+        """mode='gather': pack the per-parameter gradients into the flat bucket (one multi-tensor copy)."""
+        if self.mode != 'gather':
+            return
+        views, grads = [], []
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            else:
+                views.append(v)
+                grads.append(p.grad)
+        torch._foreach_copy_(views, grads)
 
     def world_size(self):
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
     def all_reduce_mean(self, async_op=False):
         """Average gradients over ranks (DDP semantics).  No-op for a single process."""
+        self.gather()
         ws = self.world_size()
         if ws == 1:
             return None
@@ -48,7 +77,7 @@ class FlatGradSync:
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
 
     def grads_attached(self):
-        """True while every p.grad still aliases the flat buffer (an optimiser's zero_grad(set_to_none=True) breaks it)."""
+        """mode='alias': True while every p.grad still aliases the flat buffer (zero_grad(set_to_none=True) breaks it)."""
         base = self.flat.data_ptr()
         for p, off in zip(self.params, self.offsets):
             if p.grad is None or p.grad.data_ptr() != base + off * self.flat.element_size():
