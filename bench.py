@@ -293,8 +293,12 @@ def main():
         hbm, tf_burst, tf_sust, src = peaks()
         flops, t = time_dominant_kernel(dev)
         passes = 3 if args.backend == 'bf16x3' else 1
+        traffic = None
+        prof = os.path.join(ROOT, 'profiles', 'r1_dominant_kernel.json')
+        if args.backend == 'bf16x3' and os.path.exists(prof):   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+            traffic = json.load(open(prof)).get('traffic_bytes_per_launch')
         line['roofline'] = {'bound': 'tensor', 'achieved': flops / t / 1e12, 'peak': tf_burst, 'unit': 'TFLOP/s',
-                            'frac': flops / t / 1e12 / tf_burst, 'traffic': None,
+                            'frac': flops / t / 1e12 / tf_burst, 'traffic': traffic,
                             'kernel': 'gemm_tc_kernel (conv-GEMM, FFT-block conv1: 32x1000 rows, 128->1024, k=3)',
                             'note': f'algorithmic flops 2*rows*Cout*Cin*KW per launch; peak = {src} bf16 dense burst; this backend issues '
                                     f'{passes} tensor-core pass(es) per algorithmic flop'}
