@@ -57,18 +57,23 @@ int dx_pack_conv_weight(const float* w, float* fwd, float* dgrad, void* fwd_plan
  * workspace: dx_conv_gemm_workspace(...) bytes (operand planes of the bf16x3 tensor-core path; 0 for the fp32 backend). */
 /* x_planes / dy_planes (nullable): bf16 hi|lo planes of an activation made once by dx_split_planes (2 * rows*C bf16) and shared by
  * every GEMM that consumes it (forward + wgrad, or dgrad + wgrad); when NULL the call splits into its workspace. */
+/* lens (nullable, [B] int64) + halo: padding skip.  The caller asserts that output rows s >= len[b] + halo cannot reach any valid
+ * result (they are masked downstream / beyond the receptive field of what follows); the tensor-core path then writes whole
+ * 128-row tiles made of such rows as ZEROS without computing them (the fp32 backend computes everything). */
 int dx_conv_gemm(const float* x, const void* x_planes, const float* w_packed, const void* w_planes, const float* bias,
-                 const float* relu_src, const float* add_src, float* y, void* workspace, size_t workspace_bytes, int B, int S,
-                 int Cin, int Cout, int KW, int ldx, int ldy, float alpha, int relu, int round_tf32, int backend, void* stream);
+                 const float* relu_src, const float* add_src, float* y, void* workspace, size_t workspace_bytes,
+                 const int64_t* lens, int halo, int B, int S, int Cin, int Cout, int KW, int ldx, int ldy, float alpha, int relu,
+                 int round_tf32, int backend, void* stream);
 size_t dx_conv_gemm_workspace(int B, int S, int Cin, int Cout, int KW, int have_x_planes, int have_w_planes, int backend);
 /* colsum_out (nullable, [C]): column sums of x accumulated in the same pass (= the bias gradient when x is a dy) */
 int dx_split_planes(const float* x, int ld, void* planes, float* colsum_out, int rows, int C, void* stream);
 int dx_split_weight_planes(const float* w_packed, void* planes, size_t n, void* stream);
 size_t dx_conv_wgrad_workspace(int B, int S, int Cin, int Cout, int KW, int have_x_planes, int have_dy_planes, int backend);
 /* dw[co][ci][tap] = alpha * sum_{b,s} dy[b,s,co] * x[b, s+tap-pad, ci]  (parameter layout);  dbias[co] = alpha * sum dy */
+/* lens + halo (nullable): the caller asserts dy[b, s, :] == 0 for s >= len[b] + halo; such 64-row K-chunks are skipped. */
 int dx_conv_wgrad(const float* x, const void* x_planes, const float* dy, const void* dy_planes, float* dw, float* dbias,
-                  void* workspace, size_t workspace_bytes, int B, int S, int Cin, int Cout, int KW, int ldx, float alpha, int backend,
-                  void* stream);
+                  void* workspace, size_t workspace_bytes, const int64_t* lens, int halo, int B, int S, int Cin, int Cout, int KW,
+                  int ldx, float alpha, int backend, void* stream);
 int dx_colsum(const float* dy, float* db, int rows, int C, float alpha, void* stream);
 int dx_relu_bwd(const float* dy, const float* y, float* dx, size_t n, void* stream);
 int dx_scale_copy(const float* x, float* y, float alpha, size_t n, void* stream);

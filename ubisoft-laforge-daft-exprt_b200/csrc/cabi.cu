@@ -70,8 +70,10 @@ int dx_pack_conv_weight(const float* w, float* fwd, float* dgrad, void* fwd_plan
 
 static ConvGemmArgs gemm_args(const float* x, const void* x_planes, const float* w_packed, const void* w_planes, const float* bias,
                               const float* relu_src, const float* add_src, float* y, void* ws, size_t wsb, int B, int S, int Cin,
-                              int Cout, int KW, int ldx, int ldy, float alpha, int relu, int round_tf32) {
+                              int Cout, int KW, int ldx, int ldy, float alpha, int relu, int round_tf32,
+                              const int64_t* lens = nullptr, int halo = 0) {
     ConvGemmArgs a;
+    a.lens = (cll)lens; a.halo = halo;
     a.x = x; a.w = w_packed; a.bias = bias; a.relu_src = relu_src; a.add_src = add_src; a.y = y;
     a.B = B; a.S = S; a.Cin = Cin; a.Cout = Cout; a.KW = KW; a.ldx = ldx; a.ldy = ldy;
     a.alpha = alpha; a.relu = relu; a.round_tf32 = round_tf32;
@@ -96,10 +98,11 @@ size_t dx_conv_gemm_workspace(int B, int S, int Cin, int Cout, int KW, int have_
 }
 
 int dx_conv_gemm(const float* x, const void* x_planes, const float* w_packed, const void* w_planes, const float* bias,
-                 const float* relu_src, const float* add_src, float* y, void* workspace, size_t workspace_bytes, int B, int S,
-                 int Cin, int Cout, int KW, int ldx, int ldy, float alpha, int relu, int round_tf32, int backend, void* stream) {
+                 const float* relu_src, const float* add_src, float* y, void* workspace, size_t workspace_bytes,
+                 const int64_t* lens, int halo, int B, int S, int Cin, int Cout, int KW, int ldx, int ldy, float alpha, int relu,
+                 int round_tf32, int backend, void* stream) {
     ConvGemmArgs a = gemm_args(x, x_planes, w_packed, w_planes, bias, relu_src, add_src, y, workspace, workspace_bytes, B, S, Cin,
-                               Cout, KW, ldx, ldy, alpha, relu, round_tf32);
+                               Cout, KW, ldx, ldy, alpha, relu, round_tf32, lens, halo);
     DX_REQUIRE(B > 0 && S > 0 && Cin > 0 && Cout > 0 && (KW == 1 || KW == 3), "dx_conv_gemm: bad shape B=%d S=%d Cin=%d Cout=%d KW=%d", B, S, Cin, Cout, KW);
     const int be = backend < 0 ? g_backend : backend;
     if (be != DX_GEMM_FP32_CUDA_CORES && conv_gemm_tc_supported(a)) return conv_gemm_tc(a, ST(stream));
@@ -107,8 +110,10 @@ int dx_conv_gemm(const float* x, const void* x_planes, const float* w_packed, co
 }
 
 static ConvWgradArgs wgrad_args(const float* x, const void* x_planes, const float* dy, const void* dy_planes, float* dw,
-                                float* dbias, void* ws, size_t wsb, int B, int S, int Cin, int Cout, int KW, int ldx, float alpha) {
+                                float* dbias, void* ws, size_t wsb, int B, int S, int Cin, int Cout, int KW, int ldx, float alpha,
+                                const int64_t* lens = nullptr, int halo = 0) {
     ConvWgradArgs a;
+    a.lens = (cll)lens; a.halo = halo;
     a.x = x; a.dy = dy; a.dw = dw; a.dbias = dbias; a.workspace = ws; a.workspace_bytes = wsb;
     a.B = B; a.S = S; a.Cin = Cin; a.Cout = Cout; a.KW = KW; a.ldx = ldx; a.alpha = alpha;
     a.x_planes = x_planes; a.dy_planes = dy_planes;
@@ -128,9 +133,10 @@ size_t dx_conv_wgrad_workspace(int B, int S, int Cin, int Cout, int KW, int have
 }
 
 int dx_conv_wgrad(const float* x, const void* x_planes, const float* dy, const void* dy_planes, float* dw, float* dbias,
-                  void* workspace, size_t workspace_bytes, int B, int S, int Cin, int Cout, int KW, int ldx, float alpha, int backend,
-                  void* stream) {
-    ConvWgradArgs a = wgrad_args(x, x_planes, dy, dy_planes, dw, dbias, workspace, workspace_bytes, B, S, Cin, Cout, KW, ldx, alpha);
+                  void* workspace, size_t workspace_bytes, const int64_t* lens, int halo, int B, int S, int Cin, int Cout, int KW,
+                  int ldx, float alpha, int backend, void* stream) {
+    ConvWgradArgs a = wgrad_args(x, x_planes, dy, dy_planes, dw, dbias, workspace, workspace_bytes, B, S, Cin, Cout, KW, ldx, alpha,
+                                 lens, halo);
     const int be = backend < 0 ? g_backend : backend;
     if (be != DX_GEMM_FP32_CUDA_CORES && conv_wgrad_tc_supported(a)) return conv_wgrad_tc(a, ST(stream));
     return conv_wgrad_simt(a, ST(stream));

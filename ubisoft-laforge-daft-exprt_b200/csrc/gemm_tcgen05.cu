@@ -139,6 +139,8 @@ struct TcParams {
     int B, S, Cin, Cout, KW, ldy;
     int tiles_m_per_b, tiles_n, num_tiles, k_chunks;   // CONV: tiles over (b, s) x n;  WGRAD: tiles_m = co tiles, tiles_n = ci tiles
     int nsplit;                                         // WGRAD: batch ranges
+    const long long* lens;   // optional [B]: rows >= len[b] + halo cannot reach a valid output -> tiles / K-chunks skipped
+    int halo;
     float alpha;
     int relu, round_tf32;
     long long* trace;   // optional [4][256] clock64 trace of block 0 (DX_TC_TRACE), else nullptr
@@ -178,6 +180,29 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int tile) {
         t.k_end = (int)(((split + 1) * total_k) / p.nsplit);
     }
     return t;
+}
+
+// ---- padding skip: rows at or beyond len[b] + halo of an utterance never influence a valid output (the caller chooses halo
+// from the receptive field of what follows), so CONV output tiles made only of such rows are written as zeros without any
+// loads or MMAs, and WGRAD K-chunks made only of such rows (where dy is exactly zero) are not accumulated.
+__device__ __forceinline__ int live_rows(const TcParams& p, int b) { return min((int)p.lens[b], p.S) + p.halo; }
+
+template <int MODE>
+__device__ __forceinline__ bool k_dead(const TcParams& p, int k) {   // WGRAD only
+    if (MODE == MODE_CONV || p.lens == nullptr) return false;
+    const int b = k / p.k_chunks, kc = k - b * p.k_chunks;
+    return kc * 64 >= live_rows(p, b);
+}
+
+template <int MODE>
+__device__ __forceinline__ bool tile_dead(const TcParams& p, const TileCoord& t) {
+    if (p.lens == nullptr) return false;
+    if (MODE == MODE_CONV) return t.a1 >= live_rows(p, t.a2);
+    for (int b = t.k_begin / p.k_chunks; b <= (t.k_end - 1) / p.k_chunks; ++b) {
+        const int kc_lo = max(t.k_begin - b * p.k_chunks, 0);
+        if (kc_lo * 64 < live_rows(p, b)) return false;
+    }
+    return true;
 }
 
 template <int PREC, int MODE>
@@ -222,7 +247,9 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
             int stage = 0, phase = 0, gk = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord t = tile_coord<MODE>(p, tile);
+                if (tile_dead<MODE>(p, t)) continue;
                 for (int k = t.k_begin; k < t.k_end; ++k) {
+                    if (k_dead<MODE>(p, k)) continue;
                     {
                         const int o = k / p.k_chunks, kc = k - o * p.k_chunks;
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
@@ -268,14 +295,17 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
             //   K-major: 32 bytes along the 128-byte row;  MN-major: 16 rows of 128 bytes
             constexpr uint32_t kstep = MODE == MODE_WGRAD ? (16 * 128) >> 4 : 2;
             int stage = 0, phase = 0, it = 0, gk = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord t = tile_coord<MODE>(p, tile);
-                const int k_iters = t.k_end - t.k_begin;
+                if (tile_dead<MODE>(p, t)) continue;             // (the accumulator sequence `it` only counts live tiles)
                 const int acc = it & 1, acc_phase = (it >> 1) & 1;
+                ++it;
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);     // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * TN;
-                for (int k = 0; k < k_iters; ++k) {
+                uint32_t started = 0;
+                for (int k = t.k_begin; k < t.k_end; ++k) {
+                    if (k_dead<MODE>(p, k)) continue;
                     mbar_wait(full0 + 8 * stage, phase);
                     if (p.trace && blockIdx.x == 0 && gk < 256) p.trace[1 * 256 + gk] = clock64();
                     ++gk;
@@ -285,13 +315,14 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                     const uint64_t b_hi = MODE == MODE_WGRAD ? umma_desc_mn_sw128(sb) : umma_desc_k_sw128(sb);
 #pragma unroll
                     for (int kk = 0; kk < ((p.debug & 1) ? 0 : 4); ++kk) {
-                        umma<PREC>(tmem_d, a_hi + kstep * kk, b_hi + kstep * kk, idesc, (k | kk) != 0);
+                        umma<PREC>(tmem_d, a_hi + kstep * kk, b_hi + kstep * kk, idesc, started | (uint32_t)kk);
                         if constexpr (PLANES == 2) {
                             const uint64_t a_lo = a_hi + (TILE_BYTES >> 4), b_lo = b_hi + (TILE_BYTES >> 4);
                             umma<PREC>(tmem_d, a_lo + kstep * kk, b_hi + kstep * kk, idesc, 1u);
                             umma<PREC>(tmem_d, a_hi + kstep * kk, b_lo + kstep * kk, idesc, 1u);
                         }
                     }
+                    started = 1;
                     if (p.debug & 1) mbar_arrive(empty0 + 8 * stage);
                     else umma_commit(empty0 + 8 * stage);     // frees the smem stage when these MMAs retire
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -306,25 +337,28 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         const int row = quad * 32 + lane;
         const int et = threadIdx.x - 64;          // 0..127
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const TileCoord t = tile_coord<MODE>(p, tile);
+            const bool dead = tile_dead<MODE>(p, t);             // dead tiles are stored as zeros, no accumulator involved
             const int acc = it & 1, acc_phase = (it >> 1) & 1;
-            mbar_wait(tfull0 + 8 * acc, acc_phase);
-            if (p.trace && blockIdx.x == 0 && et == 0 && it < 256) p.trace[2 * 256 + it] = clock64();
-            tc_fence_after();
+            if (!dead) {
+                mbar_wait(tfull0 + 8 * acc, acc_phase);
+                if (p.trace && blockIdx.x == 0 && et == 0 && it < 256) p.trace[2 * 256 + it] = clock64();
+                tc_fence_after();
+            }
             const int s = t.o1 + row;
             const bool row_ok = MODE == MODE_CONV && s < p.S;
             const size_t grow = (size_t)t.o2 * p.S + s;
 #pragma unroll 1
             for (int j = 0; j < TN / 32; ++j) {
                 uint32_t v[32];
-                if (p.debug & 4) {
+                if (dead || (p.debug & 4)) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = 0u;
                 } else {
                     tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN + j * 32, v);
                 }
-                if (j == TN / 32 - 1) {   // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+                if (!dead && j == TN / 32 - 1) {   // all TMEM reads of this accumulator are done: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
@@ -333,7 +367,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                 float o[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]);
-                if constexpr (MODE == MODE_CONV) {
+                if (MODE == MODE_CONV && !dead) {
                     // every condition below is warp-uniform except row_ok; columns >= Cout are clipped by the TMA store
                     const bool full = nb + 32 <= p.Cout;
                     if (p.alpha != 1.f) {
@@ -411,6 +445,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                 }
             }
             if (p.trace && blockIdx.x == 0 && et == 0 && it < 256) p.trace[3 * 256 + it] = clock64();
+            if (!dead) ++it;
         }
         if (lane == 0) tma_store_wait_all();
     }
@@ -609,6 +644,7 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     p.tiles_n = ceil_div(a.Cout, TN);
     p.num_tiles = p.tiles_m_per_b * a.B * p.tiles_n;
     p.nsplit = 1;
+    p.lens = a.lens; p.halo = a.halo;
     p.alpha = a.alpha; p.relu = a.relu; p.round_tf32 = a.round_tf32;
     p.debug = tc_debug_mask();
     p.trace = g_trace;
@@ -743,6 +779,7 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
     p.tiles_m_per_b = ceil_div(a.Cout, TM);
     p.tiles_n = ceil_div(a.Cin, TN);
     p.nsplit = nsplit;
+    p.lens = a.lens; p.halo = a.halo;
     p.num_tiles = p.tiles_m_per_b * p.tiles_n * a.KW * nsplit;
     p.k_chunks = ceil_div(a.S, Cfg<PREC_BF16X3>::TKB);
     p.alpha = 1.f; p.relu = 0; p.round_tf32 = 0;

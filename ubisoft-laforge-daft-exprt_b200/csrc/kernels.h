@@ -22,6 +22,8 @@ struct ConvGemmArgs {
     float alpha;
     int relu;
     int round_tf32;
+    const long long* lens;  // optional [B] valid lengths: output rows >= len[b] + halo are written as zeros by the tensor-core path
+    int halo;
     const void* w_planes;   // optional cached bf16 hi|lo planes of w (tensor-core bf16x3 path), else nullptr
     const void* x_planes;   // optional bf16 hi|lo planes of x ([B*S][Cin] each, made by split_activation_planes), else nullptr
     void* workspace;        // tensor-core bf16x3 path: operand planes (see conv_gemm_tc_workspace)
@@ -39,6 +41,8 @@ struct ConvWgradArgs {
     int B, S, Cin, Cout, KW;
     int ldx;
     float alpha;
+    const long long* lens;   // optional [B]: rows >= len[b] + halo carry dy == 0 and are skipped by the tensor-core path
+    int halo;
     const void* x_planes;    // optional bf16 hi|lo planes of x  ([B*S][Cin] each)
     const void* dy_planes;   // optional bf16 hi|lo planes of dy ([B*S][Cout] each)
 };

@@ -137,7 +137,7 @@ class ProsodyEncoder(nn.Module):  # model.py:295-464
         T = mel_specs.shape[2]
         p = self.p if self.training else 0.0
         c = self.convs
-        x = ops.PreNet.apply(mel_specs, c[0].conv.weight, c[0].conv.bias, c[2].weight, c[2].bias,
+        x = ops.PreNet.apply(mel_specs, output_lengths, c[0].conv.weight, c[0].conv.bias, c[2].weight, c[2].bias,
                              c[4].conv.weight, c[4].conv.bias, c[6].weight, c[6].bias,
                              c[8].conv.weight, c[8].conv.bias, c[10].weight, c[10].bias, p)
         pe = positional_table(T, self.dim, mel_specs.device)

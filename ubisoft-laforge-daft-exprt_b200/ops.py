@@ -137,8 +137,10 @@ def make_planes(x, rows, C, ld=None, want_colsum=False):
     return (planes, cs) if want_colsum else planes
 
 
-def conv_gemm(x, wp, bias, B, S, relu=False, relu_src=None, add_src=None, alpha=1.0, round_out=False, ldx=None, x_planes=None):
-    """x [B,S,Cin] (row stride ldx) · packed weight [KW,Cout,Cin] -> [B,S,Cout]"""
+def conv_gemm(x, wp, bias, B, S, relu=False, relu_src=None, add_src=None, alpha=1.0, round_out=False, ldx=None, x_planes=None,
+              lens=None, halo=0):
+    """x [B,S,Cin] (row stride ldx) · packed weight [KW,Cout,Cin] -> [B,S,Cout].
+    lens/halo: padding skip — output rows s >= lens[b] + halo are declared irrelevant by the caller (written as zeros)."""
     kw, cout, cin = wp.shape
     dev = wp.w.device
     y = torch.empty(B, S, cout, device=dev, dtype=torch.float32)
@@ -146,8 +148,8 @@ def conv_gemm(x, wp, bias, B, S, relu=False, relu_src=None, add_src=None, alpha=
     nbytes = lib().dx_conv_gemm_workspace(B, S, cin, cout, kw, int(x_planes is not None), int(wp.planes is not None), -1)
     ws = torch.empty(nbytes + 256, device=dev, dtype=torch.uint8) if nbytes else None
     _call('dx_conv_gemm', _p(x), _p(x_planes), _p(wp.w), _p(wp.planes), _p(bias), _p(relu_src), _p(add_src), _p(y), _p(ws),
-          ws.numel() if ws is not None else 0, B, S, cin, cout, kw, cin if ldx is None else ldx, cout, float(alpha),
-          int(relu), rnd, -1, _st())
+          ws.numel() if ws is not None else 0, _p(lens), int(halo), B, S, cin, cout, kw, cin if ldx is None else ldx, cout,
+          float(alpha), int(relu), rnd, -1, _st())
     return y
 
 
@@ -157,7 +159,8 @@ def linear_rows(x2d, wp, bias, **kw):
     return conv_gemm(x2d, wp, bias, 1, R, **kw).view(R, -1)
 
 
-def conv_wgrad(x, dy, B, S, cin, cout, kw, shape, want_bias=True, ldx=None, alpha=1.0, x_planes=None, dy_planes=None, dbias=None):
+def conv_wgrad(x, dy, B, S, cin, cout, kw, shape, want_bias=True, ldx=None, alpha=1.0, x_planes=None, dy_planes=None, dbias=None,
+               lens=None, halo=0):
     """-> (dw in the parameter's own layout `shape`, dbias [Cout] or None).  `dbias`: already computed (fused into make_planes)."""
     dw = torch.empty(tuple(shape), device=dy.device, dtype=torch.float32)
     if dbias is not None:
@@ -165,8 +168,8 @@ def conv_wgrad(x, dy, B, S, cin, cout, kw, shape, want_bias=True, ldx=None, alph
     db = torch.empty(cout, device=dy.device, dtype=torch.float32) if want_bias else None
     nbytes = lib().dx_conv_wgrad_workspace(B, S, cin, cout, kw, int(x_planes is not None), int(dy_planes is not None), -1)
     ws = torch.empty(max(nbytes, 16) // 4 + 4, device=dy.device, dtype=torch.float32)
-    _call('dx_conv_wgrad', _p(x), _p(x_planes), _p(dy), _p(dy_planes), _p(dw), _p(db), _p(ws), ws.numel() * 4, B, S, cin, cout, kw,
-          cin if ldx is None else ldx, float(alpha), -1, _st())
+    _call('dx_conv_wgrad', _p(x), _p(x_planes), _p(dy), _p(dy_planes), _p(dw), _p(db), _p(ws), ws.numel() * 4, _p(lens), int(halo),
+          B, S, cin, cout, kw, cin if ldx is None else ldx, float(alpha), -1, _st())
     return dw, (dbias if dbias is not None else db)
 
 
@@ -210,14 +213,14 @@ class AttentionSubLayer(torch.autograd.Function):
         in_wp, in_wd = packed(in_w)
         out_wp, out_wd = packed(out_w)
         xP = make_planes(x, B * S, D)
-        qkv = conv_gemm(x, in_wp, in_b, 1, B * S, x_planes=xP).view(B, S, 3 * D)
+        qkv = conv_gemm(x, in_wp, in_b, B, S, x_planes=xP, lens=lens)   # rows >= len: keys masked, queries skipped
         att = torch.empty(B, S, D, device=x.device, dtype=torch.float32)
         lse = torch.empty(B, nb_heads, S, device=x.device, dtype=torch.float32)
         seed_attn, seed_out = (next_seed(), next_seed()) if p_drop > 0 else (0, 0)
         planes = attention_planes(B, S, nb_heads, dh, x.device)
         _call('dx_attention_fwd', _p(qkv), _p(lens), _p(att), _p(lse), _p(planes), B, S, nb_heads, dh, float(p_drop), seed_attn, _st())
         attP = make_planes(att, B * S, D)
-        proj = conv_gemm(att, out_wp, out_b, 1, B * S, x_planes=attP)
+        proj = conv_gemm(att, out_wp, out_b, B, S, x_planes=attP, lens=lens)   # rows >= len are masked by the LayerNorm kernel
         y, xhat, rstd = ln_fwd(proj, x, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p_drop, seed_in=seed_out)
         ctx.save_for_backward(x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b, xP, attP, planes)
         ctx.packed = (in_wd, out_wd)
@@ -232,15 +235,15 @@ class AttentionSubLayer(torch.autograd.Function):
         dy = _check_input(dy)
         dv, dproj, dln_w, dln_b, _ = ln_bwd(dy, xhat, rstd, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p, seed_in=seed_out)
         dprojP, dpb = make_planes(dproj, B * S, D, want_colsum=True)
-        datt = conv_gemm(dproj, out_wd, None, 1, B * S, x_planes=dprojP)
-        d_out_w, d_out_b = conv_wgrad(att, dproj, B, S, D, D, 1, out_shape, x_planes=attP, dy_planes=dprojP, dbias=dpb)
+        datt = conv_gemm(dproj, out_wd, None, B, S, x_planes=dprojP, lens=lens)   # dproj == 0 beyond len: exact
+        d_out_w, d_out_b = conv_wgrad(att, dproj, B, S, D, D, 1, out_shape, x_planes=attP, dy_planes=dprojP, dbias=dpb, lens=lens)
         dqkv = torch.empty(B, S, 3 * D, device=dy.device, dtype=torch.float32)
         scratch = torch.empty(lib().dx_attention_bwd_scratch_bytes(B, S, H, dh), device=dy.device, dtype=torch.uint8)
         _call('dx_attention_bwd', _p(qkv), _p(planes), _p(lens), _p(att), _p(lse), _p(datt), _p(dqkv), _p(scratch), B, S, H, dh, p,
               seed_attn, _st())
         dqkvP, dqb = make_planes(dqkv, B * S, 3 * D, want_colsum=True)
-        dx = conv_gemm(dqkv, in_wd, None, 1, B * S, add_src=dv, x_planes=dqkvP).view(B, S, D)
-        d_in_w, d_in_b = conv_wgrad(x, dqkv, B, S, D, 3 * D, 1, in_shape, x_planes=xP, dy_planes=dqkvP, dbias=dqb)
+        dx = conv_gemm(dqkv, in_wd, None, B, S, add_src=dv, x_planes=dqkvP, lens=lens)   # dqkv == dv == 0 beyond len: exact
+        d_in_w, d_in_b = conv_wgrad(x, dqkv, B, S, D, 3 * D, 1, in_shape, x_planes=xP, dy_planes=dqkvP, dbias=dqb, lens=lens)
         return dx, None, d_in_w, d_in_b, d_out_w, d_out_b, dln_w, dln_b, None, None
 
 
@@ -255,9 +258,9 @@ class ConvFFSubLayer(torch.autograd.Function):
         w2p, w2d = packed(w2)
         C = w1.shape[0]
         xP = make_planes(x, B * S, D)
-        h = conv_gemm(x, w1p, b1, B, S, relu=True, round_out=True, x_planes=xP)
+        h = conv_gemm(x, w1p, b1, B, S, relu=True, round_out=True, x_planes=xP, lens=lens, halo=(w2.shape[2] - 1) // 2)
         hP = make_planes(h, B * S, C)
-        o = conv_gemm(h, w2p, b2, B, S, x_planes=hP)
+        o = conv_gemm(h, w2p, b2, B, S, x_planes=hP, lens=lens)   # rows >= len are masked by the LayerNorm kernel
         seed = next_seed() if p_drop > 0 else 0
         if film is not None:
             film = _check_input(film)
@@ -277,11 +280,12 @@ class ConvFFSubLayer(torch.autograd.Function):
         dv, do, dln_w, dln_b, dfilm = ln_bwd(dy, xhat, rstd, ln_w, ln_b, film, 2 * D, lens, B, S, D, p_in=p, seed_in=seed,
                                              want_film=film is not None)
         doP, dob = make_planes(do, B * S, D, want_colsum=True)
-        dh = conv_gemm(do, w2d, None, B, S, relu_src=h, round_out=True, x_planes=doP)
-        dw2, db2 = conv_wgrad(h, do, B, S, C, D, w2_shape[2], w2_shape, x_planes=hP, dy_planes=doP, dbias=dob)
+        k2 = (w2_shape[2] - 1) // 2
+        dh = conv_gemm(do, w2d, None, B, S, relu_src=h, round_out=True, x_planes=doP, lens=lens, halo=k2)   # do == 0 beyond len: exact
+        dw2, db2 = conv_wgrad(h, do, B, S, C, D, w2_shape[2], w2_shape, x_planes=hP, dy_planes=doP, dbias=dob, lens=lens)
         dhP, dhb = make_planes(dh, B * S, C, want_colsum=True)
-        dx = conv_gemm(dh, w1d, None, B, S, add_src=dv, x_planes=dhP)
-        dw1, db1 = conv_wgrad(x, dh, B, S, D, C, w1_shape[2], w1_shape, x_planes=xP, dy_planes=dhP, dbias=dhb)
+        dx = conv_gemm(dh, w1d, None, B, S, add_src=dv, x_planes=dhP, lens=lens)   # rows >= len are masked by the producer's LN bwd
+        dw1, db1 = conv_wgrad(x, dh, B, S, D, C, w1_shape[2], w1_shape, x_planes=xP, dy_planes=dhP, dbias=dhb, lens=lens, halo=k2)
         return dx, None, dw1, db1, dw2, db2, dln_w, dln_b, dfilm, None
 
 
@@ -289,7 +293,7 @@ class PreNet(torch.autograd.Function):
     """3 x (Conv1d k3 -> ReLU -> LayerNorm -> Dropout) on the reference mel-spec [B, M, T] -> [B, T, D]"""
 
     @staticmethod
-    def forward(ctx, mel, w0, b0, g0, e0, w1, b1, g1, e1, w2, b2, g2, e2, p_drop):
+    def forward(ctx, mel, lens, w0, b0, g0, e0, w1, b1, g1, e1, w2, b2, g2, e2, p_drop):
         mel = _check_input(mel)
         B, M, T = mel.shape
         full = torch.full((B,), T, device=mel.device, dtype=torch.int64)
@@ -297,11 +301,15 @@ class PreNet(torch.autograd.Function):
         _call('dx_mask_transpose_bwd', _p(mel), _p(full), _p(x), B, T, M, _st())   # plain [B,M,T] -> [B,T,M]
         saved, cur = [x], x
         seeds, wds, in_planes = [], [], []
-        for w, b, g, e in ((w0, b0, g0, e0), (w1, b1, g1, e1), (w2, b2, g2, e2)):
+        layers = ((w0, b0, g0, e0), (w1, b1, g1, e1), (w2, b2, g2, e2))
+        pads = [(w.shape[2] - 1) // 2 for w, _, _, _ in layers]
+        # padding skip: rows >= len + (receptive field of the convs still to come) cannot reach a valid pre-net output row
+        halos = [sum(pads[i + 1:]) for i in range(3)]
+        for i, (w, b, g, e) in enumerate(layers):
             wp, wd = packed(w)
             curP = make_planes(cur, B * T, w.shape[1])
             in_planes.append(curP)
-            a = conv_gemm(cur, wp, b, B, T, relu=True, x_planes=curP)
+            a = conv_gemm(cur, wp, b, B, T, relu=True, x_planes=curP, lens=lens, halo=halos[i])
             seed = next_seed() if p_drop > 0 else 0
             y, xhat, rstd = ln_fwd(a, None, g, e, None, 0, None, B, T, w.shape[0], p_out=p_drop, seed_out=seed)
             saved += [a, xhat, rstd, g, e]
@@ -309,6 +317,8 @@ class PreNet(torch.autograd.Function):
             wds.append(wd)
             cur = y
             saved.append(y)
+        saved.append(lens)
+        ctx.halos = halos
         ctx.save_for_backward(*saved)
         ctx.in_planes = in_planes   # bf16 planes of each layer's input (not autograd tensors of interest: plain buffers)
         ctx.packed = wds
@@ -319,7 +329,8 @@ class PreNet(torch.autograd.Function):
     def backward(ctx, dy):
         saved = ctx.saved_tensors
         B, T, M, p, seeds, shapes = ctx.cfg
-        x = saved[0]
+        x, lens = saved[0], saved[-1]
+        halos = ctx.halos
         layers = [saved[1 + 6 * i: 7 + 6 * i] for i in range(3)]   # a, xhat, rstd, g, e, y
         grads = [None] * 12
         d = _check_input(dy)
@@ -330,11 +341,13 @@ class PreNet(torch.autograd.Function):
             inp = x if i == 0 else layers[i - 1][5]
             dpre, _, dg, de, _ = ln_bwd(d, xhat, rstd, g, e, None, 0, None, B, T, cout, relu_src=a, p_out=p, seed_out=seeds[i])
             dpreP, dpreb = make_planes(dpre, B * T, cout, want_colsum=True)
-            dw, db = conv_wgrad(inp, dpre, B, T, cin, cout, kw, shapes[i], x_planes=ctx.in_planes[i], dy_planes=dpreP, dbias=dpreb)
+            # the gradient of the masked pre-net output is zero beyond len, so dpre of layer i is exactly zero beyond len + halos[i]
+            dw, db = conv_wgrad(inp, dpre, B, T, cin, cout, kw, shapes[i], x_planes=ctx.in_planes[i], dy_planes=dpreP, dbias=dpreb,
+                                lens=lens, halo=halos[i])
             grads[4 * i: 4 * i + 4] = [dw, db, dg, de]
             if i > 0:
-                d = conv_gemm(dpre, wd, None, B, T, x_planes=dpreP)
-        return (None, *grads, None)
+                d = conv_gemm(dpre, wd, None, B, T, x_planes=dpreP, lens=lens, halo=halos[i - 1])
+        return (None, None, *grads, None)
 
 
 class FrameInput(torch.autograd.Function):
@@ -608,7 +621,7 @@ class MelProjection(torch.autograd.Function):
         B, T, D = x.shape
         M = w.shape[0]
         wp, wd = packed(w)
-        y = conv_gemm(x, wp, b, 1, B * T)
+        y = conv_gemm(x, wp, b, B, T, lens=lens)
         mel = torch.empty(B, M, T, device=x.device, dtype=torch.float32)
         _call('dx_mask_transpose_fwd', _p(y), _p(lens), _p(mel), B, T, M, _st())
         ctx.save_for_backward(x, lens)
@@ -624,8 +637,8 @@ class MelProjection(torch.autograd.Function):
         dmel = _check_input(dmel)
         dy = torch.empty(B, T, M, device=dmel.device, dtype=torch.float32)
         _call('dx_mask_transpose_bwd', _p(dmel), _p(lens), _p(dy), B, T, M, _st())
-        dx = conv_gemm(dy, wd, None, 1, B * T).view(B, T, D)
-        dw, db = conv_wgrad(x, dy, B, T, D, M, 1, wshape)
+        dx = conv_gemm(dy, wd, None, B, T, lens=lens)   # dy == 0 beyond len: exact
+        dw, db = conv_wgrad(x, dy, B, T, D, M, 1, wshape, lens=lens)
         return dx, None, dw, db
 
 
