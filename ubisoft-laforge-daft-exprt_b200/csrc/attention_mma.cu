@@ -33,8 +33,49 @@ __device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint3
     const float xr = x - __uint_as_float(hi << 16), yr = y - __uint_as_float(hi & 0xffff0000u);
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(yr), "f"(xr));
 }
-// exp(x) for x <= 0 through ex2 (2^-22 relative): softmax inputs only
-__device__ __forceinline__ float fast_exp(float x) { return exp2f(x * 1.4426950408889634f); }
+// exp(x) through ex2.approx (2^-22 relative): softmax inputs only.  exp2_fma(x, m2) = exp(x - m) with m2 = m * log2(e)
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_exp(float x) { return ex2(x * kLog2e); }
+__device__ __forceinline__ float exp2_fma(float x, float m2) { return ex2(fmaf(x, kLog2e, -m2)); }
+
+// ldmatrix / stmatrix: four 8x8 bf16 matrices per instruction; lane L passes the address of row L%8 of matrix L/8.
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void stsm_x4_trans(void* p, const uint32_t (&r)[4]) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};"
+                 ::"r"(a), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+// Lane -> (row, col) offsets of its ldmatrix.x4 address.
+//   A operand (16 rows x 16 k, smem [row][k]):      matrices (rows 0-7,k 0-7) (rows 8-15,k 0-7) (rows 0-7,k 8-15) (rows 8-15,k 8-15)
+//   B operand pair (2 n-tiles x 16 k, smem [n][k]): matrices (n 0-7,k 0-7) (n 0-7,k 8-15) (n 8-15,k 0-7) (n 8-15,k 8-15)
+struct LaneMap {
+    int a_r, a_c, b_r, b_c;
+    __device__ __forceinline__ explicit LaneMap(int lane)
+        : a_r(lane & 15), a_c((lane >> 4) << 3), b_r((lane & 7) + ((lane >> 4) << 3)), b_c(((lane >> 3) & 1) << 3) {}
+};
+// acc[2np], acc[2np+1] += A(hi|lo) * B^T with B = the n-tile pair at Bm[plane][16 np ..][k0 ..] (bf16x3: hi*hi + lo*hi + hi*lo)
+template <int BR, int BP>
+__device__ __forceinline__ void mma_pair(float (*acc)[4], int np, const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                         const __nv_bfloat16 (*Bm)[BR][BP], int k0, const LaneMap& lm) {
+    uint32_t bh[4], bl[4];
+    ldsm_x4(bh, &Bm[0][np * 16 + lm.b_r][k0 + lm.b_c]);
+    ldsm_x4(bl, &Bm[1][np * 16 + lm.b_r][k0 + lm.b_c]);
+    mma_bf16(acc[2 * np], ah, bh[0], bh[1]);
+    mma_bf16(acc[2 * np], al, bh[0], bh[1]);
+    mma_bf16(acc[2 * np], ah, bl[0], bl[1]);
+    mma_bf16(acc[2 * np + 1], ah, bh[2], bh[3]);
+    mma_bf16(acc[2 * np + 1], al, bh[2], bh[3]);
+    mma_bf16(acc[2 * np + 1], ah, bl[2], bl[3]);
+}
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -165,8 +206,12 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(AttnArgs p) {
 #pragma unroll
     for (int n = 0; n < ND; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-    const float inv_keep = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
+    const bool drop = p.dropout_p > 0.f;
+    const float inv_keep = drop ? 1.f / (1.f - p.dropout_p) : 1.f;   // folded into the final normalisation
     const unsigned long long bh = ((unsigned long long)b * p.H + h) * (unsigned long long)p.S;
+    const uint32_t thresh = drop_threshold(p.dropout_p);
+    const uint32_t rk0 = hash_u32(p.seed, bh + r0), rk1 = hash_u32(p.seed, bh + r1);   // per-row dropout keys
+    const LaneMap lm(lane);
 
     int stage = 0;
     for (int k0 = 0; k0 < len; k0 += 64, stage ^= 1) {
@@ -180,24 +225,20 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(AttnArgs p) {
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
+            for (int np = 0; np < 4; ++np) mma_pair<64, SM::KP>(s, np, qh[ks], ql[ks], sm.K[stage], ks * 16, lm);
+        }
+        // key padding -> -inf (last tile only), online softmax (rows g and g+8; a row's 64 scores live in the 4 lanes of a quad)
+        if (k0 + 64 > len) {
+#pragma unroll
             for (int n = 0; n < 8; ++n) {
-                const int key = n * 8 + g, c = ks * 16 + 2 * t;
-                const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&sm.K[stage][0][key][c]);
-                const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&sm.K[stage][0][key][c + 8]);
-                const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&sm.K[stage][1][key][c]);
-                const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&sm.K[stage][1][key][c + 8]);
-                mma_bf16(s[n], qh[ks], bh0, bh1);
-                mma_bf16(s[n], ql[ks], bh0, bh1);
-                mma_bf16(s[n], qh[ks], bl0, bl1);
+                const int key = k0 + n * 8 + 2 * t;
+                if (key >= len) { s[n][0] = -INFINITY; s[n][2] = -INFINITY; }
+                if (key + 1 >= len) { s[n][1] = -INFINITY; s[n][3] = -INFINITY; }
             }
         }
-        // key padding -> -inf, online softmax (rows g and g+8; a row's 64 scores live in the 4 lanes of a quad)
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            const int key = k0 + n * 8 + 2 * t;
-            if (key >= len) { s[n][0] = -INFINITY; s[n][2] = -INFINITY; }
-            if (key + 1 >= len) { s[n][1] = -INFINITY; s[n][3] = -INFINITY; }
             mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
             mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
         }
@@ -205,20 +246,20 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(AttnArgs p) {
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
         const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite: every processed tile has >= 1 valid key
         const float c0 = fast_exp(m0 - mn0), c1 = fast_exp(m1 - mn1);
+        const float mn0l = mn0 * kLog2e, mn1l = mn1 * kLog2e;
         float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            s[n][0] = fast_exp(s[n][0] - mn0); s[n][1] = fast_exp(s[n][1] - mn0);
-            s[n][2] = fast_exp(s[n][2] - mn1); s[n][3] = fast_exp(s[n][3] - mn1);
+            s[n][0] = exp2_fma(s[n][0], mn0l); s[n][1] = exp2_fma(s[n][1], mn0l);
+            s[n][2] = exp2_fma(s[n][2], mn1l); s[n][3] = exp2_fma(s[n][3], mn1l);
             rs0 += s[n][0] + s[n][1];
             rs1 += s[n][2] + s[n][3];
-            if (p.dropout_p > 0.f) {   // dropout on the attention weights: applied to what multiplies V, not to the row sum
-                const unsigned long long kk = (unsigned long long)(k0 + n * 8 + 2 * t);
-                const unsigned long long i0 = (bh + r0) * (unsigned long long)p.S + kk, i1 = (bh + r1) * (unsigned long long)p.S + kk;
-                s[n][0] *= dropout_scale(p.seed, i0, p.dropout_p, inv_keep);
-                s[n][1] *= dropout_scale(p.seed, i0 + 1, p.dropout_p, inv_keep);
-                s[n][2] *= dropout_scale(p.seed, i1, p.dropout_p, inv_keep);
-                s[n][3] *= dropout_scale(p.seed, i1 + 1, p.dropout_p, inv_keep);
+            if (drop) {   // dropout on the attention weights: applied to what multiplies V, not to the row sum
+                const uint32_t ka = drop_col_term((uint32_t)(k0 + n * 8 + 2 * t)), kb = drop_col_term((uint32_t)(k0 + n * 8 + 2 * t + 1));
+                s[n][0] = drop_keep(rk0, ka, thresh) ? s[n][0] : 0.f;
+                s[n][1] = drop_keep(rk0, kb, thresh) ? s[n][1] : 0.f;
+                s[n][2] = drop_keep(rk1, ka, thresh) ? s[n][2] : 0.f;
+                s[n][3] = drop_keep(rk1, kb, thresh) ? s[n][3] : 0.f;
             }
         }
         rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
@@ -237,21 +278,12 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(AttnArgs p) {
             split_pair(s[2 * j + 1][0], s[2 * j + 1][1], ph[2], pl[2]);
             split_pair(s[2 * j + 1][2], s[2 * j + 1][3], ph[3], pl[3]);
 #pragma unroll
-            for (int n = 0; n < ND; ++n) {
-                const int d = n * 8 + g, c = j * 16 + 2 * t;
-                const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&sm.Vt[stage][0][d][c]);
-                const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&sm.Vt[stage][0][d][c + 8]);
-                const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&sm.Vt[stage][1][d][c]);
-                const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&sm.Vt[stage][1][d][c + 8]);
-                mma_bf16(o[n], ph, bh0, bh1);
-                mma_bf16(o[n], pl, bh0, bh1);
-                mma_bf16(o[n], ph, bl0, bl1);
-            }
+            for (int np = 0; np < ND / 2; ++np) mma_pair<DH, SM::VP>(o, np, ph, pl, sm.Vt[stage], j * 16, lm);
         }
     }
 
     const bool v0 = r0 < len, v1 = r1 < len;
-    const float i0 = v0 ? 1.f / l0 : 0.f, i1 = v1 ? 1.f / l1 : 0.f;
+    const float i0 = v0 ? inv_keep / l0 : 0.f, i1 = v1 ? inv_keep / l1 : 0.f;
 #pragma unroll
     for (int n = 0; n < ND; ++n) {
         const int c = n * 8 + 2 * t;
@@ -280,41 +312,30 @@ struct BwdSmem {
     __nv_bfloat16 K[2][64][RP], V[2][64][RP], Kt[2][DH][TP];
     __nv_bfloat16 Q[2][64][RP], G[2][64][RP], Qt[2][DH][TP], Gt[2][DH][TP];
     __nv_bfloat16 dS[2][64][TP];
-    float lse[64], delta[64];
+    float lse2[64], delta[64];   // lse * log2(e), delta
+    uint32_t rk[64];             // per-query-row dropout keys
 };
 
 // acc[n] (16 x 8 each, n < NT) += A(16 x 16*KSTEPS, rows a_row0.., from smem [row][k]) * B^T (B from smem [n][k])
 template <int KSTEPS, int NT, int AP, int BP>
 __device__ __forceinline__ void mma_smem_ab(float (*acc)[4], const __nv_bfloat16 (*A)[64][AP], int a_row0,
-                                            const __nv_bfloat16 (*Bm)[64][BP], int g, int t) {
+                                            const __nv_bfloat16 (*Bm)[64][BP], const LaneMap& lm) {
 #pragma unroll
     for (int ks = 0; ks < KSTEPS; ++ks) {
         uint32_t ah[4], al[4];
-        const int c = ks * 16 + 2 * t;
-        ah[0] = *reinterpret_cast<const uint32_t*>(&A[0][a_row0 + g][c]);
-        ah[1] = *reinterpret_cast<const uint32_t*>(&A[0][a_row0 + g + 8][c]);
-        ah[2] = *reinterpret_cast<const uint32_t*>(&A[0][a_row0 + g][c + 8]);
-        ah[3] = *reinterpret_cast<const uint32_t*>(&A[0][a_row0 + g + 8][c + 8]);
-        al[0] = *reinterpret_cast<const uint32_t*>(&A[1][a_row0 + g][c]);
-        al[1] = *reinterpret_cast<const uint32_t*>(&A[1][a_row0 + g + 8][c]);
-        al[2] = *reinterpret_cast<const uint32_t*>(&A[1][a_row0 + g][c + 8]);
-        al[3] = *reinterpret_cast<const uint32_t*>(&A[1][a_row0 + g + 8][c + 8]);
+        ldsm_x4(ah, &A[0][a_row0 + lm.a_r][ks * 16 + lm.a_c]);
+        ldsm_x4(al, &A[1][a_row0 + lm.a_r][ks * 16 + lm.a_c]);
 #pragma unroll
-        for (int n = 0; n < NT; ++n) {
-            const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&Bm[0][n * 8 + g][c]);
-            const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&Bm[0][n * 8 + g][c + 8]);
-            const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&Bm[1][n * 8 + g][c]);
-            const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&Bm[1][n * 8 + g][c + 8]);
-            mma_bf16(acc[n], ah, bh0, bh1);
-            mma_bf16(acc[n], al, bh0, bh1);
-            mma_bf16(acc[n], ah, bl0, bl1);
-        }
+        for (int np = 0; np < NT / 2; ++np) mma_pair<64, BP>(acc, np, ah, al, Bm, ks * 16, lm);
     }
 }
 
-// acc[n] (n < NT) += A (from score C-fragments sc[8][4], 64 columns = 4 k-steps) * B^T (B from smem [n][k], pitch BP)
-template <int NT, int BP, int BR>
-__device__ __forceinline__ void mma_frag_b(float (*acc)[4], const float (*sc)[4], const __nv_bfloat16 (*Bm)[BR][BP], int g, int t) {
+// acc[n] (n < NT) += A (from score C-fragments sc[8][4], 64 columns = 4 k-steps) * B^T (B from smem [n][k], pitch BP).
+// With STAGE, the split fragments are also stored TRANSPOSED (stmatrix.trans) into dst[plane][64][TP] at columns col0.. :
+// the C-fragment of a [16 keys][64 q] tile lands q-major, ready to be the A operand of the dQ product.
+template <int NT, int BP, int BR, bool STAGE, int TP>
+__device__ __forceinline__ void mma_frag_b(float (*acc)[4], const float (*sc)[4], const __nv_bfloat16 (*Bm)[BR][BP], const LaneMap& lm,
+                                           __nv_bfloat16 (*dst)[64][TP], int col0, int lane) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         uint32_t ah[4], al[4];
@@ -322,17 +343,13 @@ __device__ __forceinline__ void mma_frag_b(float (*acc)[4], const float (*sc)[4]
         split_pair(sc[2 * j][2], sc[2 * j][3], ah[1], al[1]);
         split_pair(sc[2 * j + 1][0], sc[2 * j + 1][1], ah[2], al[2]);
         split_pair(sc[2 * j + 1][2], sc[2 * j + 1][3], ah[3], al[3]);
-        const int c = j * 16 + 2 * t;
-#pragma unroll
-        for (int n = 0; n < NT; ++n) {
-            const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&Bm[0][n * 8 + g][c]);
-            const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&Bm[0][n * 8 + g][c + 8]);
-            const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&Bm[1][n * 8 + g][c]);
-            const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&Bm[1][n * 8 + g][c + 8]);
-            mma_bf16(acc[n], ah, bh0, bh1);
-            mma_bf16(acc[n], al, bh0, bh1);
-            mma_bf16(acc[n], ah, bl0, bl1);
+        if (STAGE) {   // matrices: (n = 2j, keys +0) (n = 2j, keys +8) (n = 2j+1, keys +0) (n = 2j+1, keys +8)
+            const int row = (2 * j + (lane >> 4)) * 8 + (lane & 7), col = col0 + (((lane >> 3) & 1) << 3);
+            stsm_x4_trans(&dst[0][row][col], ah);
+            stsm_x4_trans(&dst[1][row][col], al);
         }
+#pragma unroll
+        for (int np = 0; np < NT / 2; ++np) mma_pair<BR, BP>(acc, np, ah, al, Bm, j * 16, lm);
     }
 }
 
@@ -352,8 +369,11 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(AttnArgs p) {
     const float* lse = p.lse + ((size_t)b * p.H + h) * p.S;
     const float* delta = p.delta + ((size_t)b * p.H + h) * p.S;
     const float scale = rsqrtf((float)DH);
-    const float inv_keep = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
+    const bool drop = p.dropout_p > 0.f;
+    const float inv_keep = drop ? 1.f / (1.f - p.dropout_p) : 1.f;
     const unsigned long long bh = ((unsigned long long)b * p.H + h) * (unsigned long long)p.S;
+    const uint32_t thresh = drop_threshold(p.dropout_p);
+    const LaneMap lm(lane);
 
     const size_t plane = (size_t)p.B * NH * Sp * DH, gplane = (size_t)p.B * p.H * Sp * DH;
     const __nv_bfloat16* Qr = p.R + ((size_t)b * NH + h) * Sp * DH;
@@ -386,11 +406,13 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(AttnArgs p) {
 #pragma unroll
     for (int n = 0; n < ND; ++n) { dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f; dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f; }
     const int key0 = k0 + warp * 16 + g, key1 = key0 + 8;   // this lane's two key rows
+    const uint32_t kc0 = drop_col_term((uint32_t)key0), kc1 = drop_col_term((uint32_t)key1);
 
     for (int q0 = 0; q0 < len; q0 += 64) {
         if (tid < 64) {
-            sm.lse[tid] = (q0 + tid < len) ? lse[q0 + tid] : 0.f;
+            sm.lse2[tid] = (q0 + tid < len) ? lse[q0 + tid] * kLog2e : 0.f;
             sm.delta[tid] = (q0 + tid < len) ? delta[q0 + tid] : 0.f;
+            if (drop) sm.rk[tid] = hash_u32(p.seed, bh + q0 + tid);
         }
         cp_async_wait<0>();
         __syncthreads();   // (A) this query tile's operands (and, first trip, K/V/Kt) landed; lse/delta visible
@@ -398,42 +420,30 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(AttnArgs p) {
         float st[8][4], dp[8][4];
 #pragma unroll
         for (int n = 0; n < 8; ++n) { st[n][0] = st[n][1] = st[n][2] = st[n][3] = 0.f; dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f; }
-        mma_smem_ab<KS, 8, SM::RP, SM::RP>(st, sm.K, warp * 16, sm.Q, g, t);   // S^T  [16 keys][64 q]
-        mma_smem_ab<KS, 8, SM::RP, SM::RP>(dp, sm.V, warp * 16, sm.G, g, t);   // dP^T [16 keys][64 q]
+        mma_smem_ab<KS, 8, SM::RP, SM::RP>(st, sm.K, warp * 16, sm.Q, lm);   // S^T  [16 keys][64 q]
+        mma_smem_ab<KS, 8, SM::RP, SM::RP>(dp, sm.V, warp * 16, sm.G, lm);   // dP^T [16 keys][64 q]
 
-        // P^T (dropped) in st, dS^T in dp
+        // P^T (dropped, WITHOUT the 1/keep factor: dV is scaled once at the end) in st, dS^T in dp
+        const bool edge = (q0 + 64 > len) || (k0 + 64 > len);   // only edge tiles hold padded rows / keys
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
+            const int ql = n * 8 + 2 * t;
+            const float2 ls = *reinterpret_cast<const float2*>(&sm.lse2[ql]);
+            const float2 dl = *reinterpret_cast<const float2*>(&sm.delta[ql]);
+            uint2 rk = make_uint2(0u, 0u);
+            if (drop) rk = *reinterpret_cast<const uint2*>(&sm.rk[ql]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int ql = n * 8 + 2 * t + (e & 1), q = q0 + ql;
-                const int key = (e < 2) ? key0 : key1;
-                float pd = 0.f, ds = 0.f;
-                if (q < len && key < len) {
-                    const float pv = fast_exp(st[n][e] - sm.lse[ql]);
-                    float dm = 1.f;
-                    if (p.dropout_p > 0.f) dm = dropout_scale(p.seed, (bh + q) * (unsigned long long)p.S + key, p.dropout_p, inv_keep);
-                    pd = pv * dm;
-                    ds = pv * (dp[n][e] * dm - sm.delta[ql]);
-                }
-                st[n][e] = pd;
-                dp[n][e] = ds;
+                const bool odd = e & 1, second = e >= 2;
+                float pv = exp2_fma(st[n][e], odd ? ls.y : ls.x);
+                if (edge && !(q0 + ql + (e & 1) < len && (second ? key1 : key0) < len)) pv = 0.f;
+                const bool keep = !drop || drop_keep(odd ? rk.y : rk.x, second ? kc1 : kc0, thresh);
+                st[n][e] = keep ? pv : 0.f;
+                dp[n][e] = pv * ((keep ? dp[n][e] * inv_keep : 0.f) - (odd ? dl.y : dl.x));
             }
         }
-        mma_frag_b<ND, SM::TP, DH>(dv, st, sm.Gt, g, t);   // dV += P^T dO
-        mma_frag_b<ND, SM::TP, DH>(dk, dp, sm.Qt, g, t);   // dK += dS^T Q   (Q carries 1/sqrt(dh))
-        // dS, q-major, for the dQ product
-#pragma unroll
-        for (int n = 0; n < 8; ++n) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int ql = n * 8 + 2 * t + (e & 1);
-                const int kl = warp * 16 + g + ((e < 2) ? 0 : 8);
-                const __nv_bfloat16 hi = __float2bfloat16_rn(dp[n][e]);
-                sm.dS[0][ql][kl] = hi;
-                sm.dS[1][ql][kl] = __float2bfloat16_rn(dp[n][e] - __bfloat162float(hi));
-            }
-        }
+        mma_frag_b<ND, SM::TP, DH, false, SM::TP>(dv, st, sm.Gt, lm, sm.dS, 0, lane);          // dV += P^T dO
+        mma_frag_b<ND, SM::TP, DH, true, SM::TP>(dk, dp, sm.Qt, lm, sm.dS, warp * 16, lane);   // dK += dS^T Q (Q carries 1/sqrt(dh)); dS staged q-major
         __syncthreads();   // (B) dS complete; nobody reads Q/G/Qt/Gt of this tile any more
         if (q0 + 64 < len) issue_q(q0 + 64);   // overlaps with the dQ product below
         // dQ[16 q rows of this warp][DH] = dS[q][64 keys] K[64 keys][DH]  (B = K^T tile [d][key])
@@ -443,25 +453,10 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(AttnArgs p) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
             uint32_t ah[4], al[4];
-            const int c = ks * 16 + 2 * t, r = warp * 16 + g;
-            ah[0] = *reinterpret_cast<const uint32_t*>(&sm.dS[0][r][c]);
-            ah[1] = *reinterpret_cast<const uint32_t*>(&sm.dS[0][r + 8][c]);
-            ah[2] = *reinterpret_cast<const uint32_t*>(&sm.dS[0][r][c + 8]);
-            ah[3] = *reinterpret_cast<const uint32_t*>(&sm.dS[0][r + 8][c + 8]);
-            al[0] = *reinterpret_cast<const uint32_t*>(&sm.dS[1][r][c]);
-            al[1] = *reinterpret_cast<const uint32_t*>(&sm.dS[1][r + 8][c]);
-            al[2] = *reinterpret_cast<const uint32_t*>(&sm.dS[1][r][c + 8]);
-            al[3] = *reinterpret_cast<const uint32_t*>(&sm.dS[1][r + 8][c + 8]);
+            ldsm_x4(ah, &sm.dS[0][warp * 16 + lm.a_r][ks * 16 + lm.a_c]);
+            ldsm_x4(al, &sm.dS[1][warp * 16 + lm.a_r][ks * 16 + lm.a_c]);
 #pragma unroll
-            for (int n = 0; n < ND; ++n) {
-                const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&sm.Kt[0][n * 8 + g][c]);
-                const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&sm.Kt[0][n * 8 + g][c + 8]);
-                const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&sm.Kt[1][n * 8 + g][c]);
-                const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&sm.Kt[1][n * 8 + g][c + 8]);
-                mma_bf16(dq[n], ah, bh0, bh1);
-                mma_bf16(dq[n], al, bh0, bh1);
-                mma_bf16(dq[n], ah, bl0, bl1);
-            }
+            for (int np = 0; np < ND / 2; ++np) mma_pair<DH, SM::TP>(dq, np, ah, al, sm.Kt, ks * 16, lm);
         }
         const int qa = q0 + warp * 16 + g, qb = qa + 8;
 #pragma unroll
@@ -477,11 +472,11 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(AttnArgs p) {
         const int c = n * 8 + 2 * t;
         if (key0 < len) {
             *reinterpret_cast<float2*>(dbase + (size_t)key0 * ld + D + c) = make_float2(dk[n][0], dk[n][1]);
-            *reinterpret_cast<float2*>(dbase + (size_t)key0 * ld + 2 * D + c) = make_float2(dv[n][0], dv[n][1]);
+            *reinterpret_cast<float2*>(dbase + (size_t)key0 * ld + 2 * D + c) = make_float2(dv[n][0] * inv_keep, dv[n][1] * inv_keep);
         }
         if (key1 < len) {
             *reinterpret_cast<float2*>(dbase + (size_t)key1 * ld + D + c) = make_float2(dk[n][2], dk[n][3]);
-            *reinterpret_cast<float2*>(dbase + (size_t)key1 * ld + 2 * D + c) = make_float2(dv[n][2], dv[n][3]);
+            *reinterpret_cast<float2*>(dbase + (size_t)key1 * ld + 2 * D + c) = make_float2(dv[n][2] * inv_keep, dv[n][3] * inv_keep);
         }
     }
 }
