@@ -188,6 +188,18 @@ int dx_pitch_shift(float* pitch, const float* factors, const int64_t* spk, const
 /* model.py:836-864 */
 int dx_pitch_multiply(float* pitch, const float* factors, int B, int L, void* stream);
 
+/* ---- CUDA-graph support: per-step scalars read from DEVICE memory ---------------------------------------------------------
+ * A captured training step (forward + loss + backward + Adam, ~600 launches replayed as one graph) must not bake per-step
+ * scalars into kernel arguments.  dx_set_step_state(ptr) registers a device block of dx_step_state_bytes() = 32 bytes
+ *     { uint64 seed_epoch; float w_adv; float lr; float bc1; float bc2_sqrt; float pad[2]; }
+ * that the host rewrites (one 32-byte H2D copy on the same stream) before every replay.  While registered:
+ *   - every dropout kernel (dx_ln_fwd/bwd, dx_attention_fwd/bwd) uses seed + seed_epoch * 0x9E3779B97F4A7C15,
+ *   - dx_loss_fwd/bwd read the adversarial weight w_adv (loss.py:30-38) from the block instead of their argument,
+ *   - dx_adam_step reads lr and the bias corrections 1 - beta1^t, sqrt(1 - beta2^t) from the block instead of lr / step.
+ * ptr == NULL restores the by-value behaviour.  Process-global, like the GEMM backend. */
+int dx_set_step_state(const void* device_state);
+size_t dx_step_state_bytes(void);
+
 /* ---- optimiser: fused Adam over a flat buffer (train.py:299-301,401) ---------------------------------------------------*/
 int dx_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
                  float weight_decay, int step, float grad_scale, void* stream);

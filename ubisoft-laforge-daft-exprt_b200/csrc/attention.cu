@@ -41,6 +41,7 @@ __device__ __forceinline__ void load_tile(float (*dst)[DH + 1], const float* __r
 
 template <int DH>
 __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnArgs p) {
+    const unsigned long long seed = dyn_seed(p.seed, p.dyn);
     constexpr int CN = DH / 16;
     extern __shared__ __align__(16) float smem[];
     float (*Qs)[DH + 1] = reinterpret_cast<float (*)[DH + 1]>(smem);
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnArgs p) {
                 float pv = expf(s[i][j] - m_new);
                 rs += pv;
                 if (p.dropout_p > 0.f)
-                    pv *= dropout_scale(p.seed, (bh + qrow) * (unsigned long long)p.S + (k0 + tx + 16 * j), p.dropout_p, inv_keep);
+                    pv *= dropout_scale(seed, (bh + qrow) * (unsigned long long)p.S + (k0 + tx + 16 * j), p.dropout_p, inv_keep);
                 Ps[ty * 4 + i][tx + 16 * j] = pv;
             }
             rs = half_warp_sum(rs);
@@ -174,6 +175,7 @@ __global__ void attn_delta_kernel(AttnArgs p) {
 // One block per (key tile, head, utterance): dK, dV accumulate in registers over all query tiles; dQ via fp32 atomics.
 template <int DH>
 __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnArgs p) {
+    const unsigned long long seed = dyn_seed(p.seed, p.dyn);
     constexpr int CN = DH / 16;
     extern __shared__ __align__(16) float smem[];
     float (*Ks)[DH + 1] = reinterpret_cast<float (*)[DH + 1]>(smem);
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnArgs p) {
                 if (q < len && k < len) {
                     pv = expf(s[i][j] - li);
                     float dm = 1.f;
-                    if (p.dropout_p > 0.f) dm = dropout_scale(p.seed, (bh + q) * (unsigned long long)p.S + k, p.dropout_p, inv_keep);
+                    if (p.dropout_p > 0.f) dm = dropout_scale(seed, (bh + q) * (unsigned long long)p.S + k, p.dropout_p, inv_keep);
                     pd = pv * dm;                          // dropped probabilities (what multiplied V)
                     dsv = pv * (dp[i][j] * dm - di);       // dS
                 }

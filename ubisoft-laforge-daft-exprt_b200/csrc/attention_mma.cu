@@ -153,6 +153,7 @@ struct FwdSmem {
 
 template <int DH>
 __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(AttnArgs p) {
+    const unsigned long long seed = dyn_seed(p.seed, p.dyn);
     using SM = FwdSmem<DH>;
     constexpr int KS = DH / 16, ND = DH / 8;
     extern __shared__ __align__(16) uint8_t fwd_smem_raw[];
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(AttnArgs p) {
     const float inv_keep = drop ? 1.f / (1.f - p.dropout_p) : 1.f;   // folded into the final normalisation
     const unsigned long long bh = ((unsigned long long)b * p.H + h) * (unsigned long long)p.S;
     const uint32_t thresh = drop_threshold(p.dropout_p);
-    const uint32_t rk0 = hash_u32(p.seed, bh + r0), rk1 = hash_u32(p.seed, bh + r1);   // per-row dropout keys
+    const uint32_t rk0 = hash_u32(seed, bh + r0), rk1 = hash_u32(seed, bh + r1);   // per-row dropout keys
     const LaneMap lm(lane);
 
     int stage = 0;
@@ -355,6 +356,7 @@ __device__ __forceinline__ void mma_frag_b(float (*acc)[4], const float (*sc)[4]
 
 template <int DH>
 __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(AttnArgs p) {
+    const unsigned long long seed = dyn_seed(p.seed, p.dyn);
     using SM = BwdSmem<DH>;
     constexpr int KS = DH / 16, ND = DH / 8;
     extern __shared__ __align__(16) uint8_t bwd_smem_raw[];
@@ -412,7 +414,7 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(AttnArgs p) {
         if (tid < 64) {
             sm.lse2[tid] = (q0 + tid < len) ? lse[q0 + tid] * kLog2e : 0.f;
             sm.delta[tid] = (q0 + tid < len) ? delta[q0 + tid] : 0.f;
-            if (drop) sm.rk[tid] = hash_u32(p.seed, bh + q0 + tid);
+            if (drop) sm.rk[tid] = hash_u32(seed, bh + q0 + tid);
         }
         cp_async_wait<0>();
         __syncthreads();   // (A) this query tile's operands (and, first trip, K/V/Kt) landed; lse/delta visible

@@ -10,6 +10,7 @@ namespace dx {
 
 static thread_local char g_err[1024] = "";
 static int g_backend = DX_GEMM_FP32_CUDA_CORES;
+static const StepState* g_step_state = nullptr;   // graph mode: device block of per-step scalars (dx_set_step_state)
 static unsigned long long g_launches = 0;   // kernels launched by this library (every launch goes through check_launch)
 
 void set_last_error(const char* fmt, ...) {
@@ -40,6 +41,11 @@ extern "C" {
 const char* dx_last_error(void) { return g_err; }
 int dx_abi_version(void) { return DX_ABI_VERSION; }
 uint64_t dx_launch_count(void) { return g_launches; }
+int dx_set_step_state(const void* device_state) {
+    g_step_state = static_cast<const StepState*>(device_state);
+    return DX_OK;
+}
+size_t dx_step_state_bytes(void) { return sizeof(StepState); }
 
 int dx_device_check(void) {
     int dev = 0;
@@ -155,6 +161,7 @@ int dx_attention_fwd(const float* qkv, const int64_t* lens, float* ctx, float* l
     memset(&a, 0, sizeof(a));
     a.qkv = qkv; a.lens = (cll)lens; a.ctx = ctx; a.lse = lse; a.B = B; a.S = S; a.H = H; a.dh = dh;
     a.dropout_p = dropout_p; a.seed = seed;
+    a.dyn = g_step_state;
     if (g_backend != DX_GEMM_FP32_CUDA_CORES && attention_mma_supported(a)) return attention_fwd_mma(a, planes, ST(stream));
     return attention_fwd(a, ST(stream));
 }
@@ -166,6 +173,7 @@ int dx_attention_bwd(const float* qkv, const void* planes, const int64_t* lens, 
     memset(&a, 0, sizeof(a));
     a.qkv = qkv; a.lens = (cll)lens; a.ctx = (float*)ctx; a.lse = (float*)lse; a.dctx = dctx; a.dqkv = dqkv;
     a.B = B; a.S = S; a.H = H; a.dh = dh; a.dropout_p = dropout_p; a.seed = seed;
+    a.dyn = g_step_state;
     DX_REQUIRE(scratch != nullptr, "dx_attention_bwd: scratch (dx_attention_bwd_scratch_bytes) required");
     if (g_backend != DX_GEMM_FP32_CUDA_CORES && attention_mma_supported(a))
         return attention_bwd_mma(a, (void*)planes, scratch, ST(stream));
@@ -181,6 +189,7 @@ int dx_ln_fwd(const float* a_, const float* res, const float* ln_w, const float*
     a.a = a_; a.res = res; a.ln_w = ln_w; a.ln_b = ln_b; a.film = film; a.film_stride = film_stride; a.lens = (cll)lens;
     a.y = y; a.xhat = xhat; a.rstd = rstd; a.B = B; a.S = S; a.D = D;
     a.p_in = p_in; a.p_out = p_out; a.seed_in = seed_in; a.seed_out = seed_out;
+    a.dyn = g_step_state;
     return ln_fwd(a, ST(stream));
 }
 
@@ -192,6 +201,7 @@ int dx_ln_bwd(const float* dy, const float* xhat, const float* rstd, const float
     a.dy = dy; a.xhat = (float*)xhat; a.rstd = (float*)rstd; a.ln_w = ln_w; a.ln_b = ln_b; a.film = film;
     a.film_stride = film_stride; a.lens = (cll)lens; a.relu_src = relu_src; a.dv = dv; a.da = da; a.dln_w = dln_w; a.dln_b = dln_b; a.dfilm = dfilm;
     a.B = B; a.S = S; a.D = D; a.p_in = p_in; a.p_out = p_out; a.seed_in = seed_in; a.seed_out = seed_out;
+    a.dyn = g_step_state;
     DX_REQUIRE(!(p_in > 0.f) || da, "dx_ln_bwd: da must be provided when p_in > 0");
     if (!(p_in > 0.f)) a.da = nullptr;
     return ln_bwd(a, ST(stream));
@@ -310,6 +320,7 @@ static LossArgs loss_args(const float* spk_logits, const int64_t* spk_ids, const
     a.pitch_p = pitch_p; a.dur_t = dur_t; a.energy_t = energy_t; a.pitch_t = pitch_t; a.mel_p = mel_p; a.mel_t = mel_t;
     a.in_lens = (cll)in_lens; a.out_lens = (cll)out_lens; a.B = B; a.L = L; a.T = T; a.M = M; a.NS = NS; a.NP = NP;
     a.w_adv = w_adv; a.w_post = w_post; a.w_dur = w_dur; a.w_energy = w_energy; a.w_pitch = w_pitch; a.w_mel = w_mel;
+    a.dyn = g_step_state;
     return a;
 }
 int dx_loss_fwd(const float* spk_logits, const int64_t* spk_ids, const float* post, const float* dur_p, const float* energy_p,
@@ -352,7 +363,7 @@ int dx_pitch_multiply(float* pitch, const float* factors, int B, int L, void* st
 }
 int dx_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
                  float weight_decay, int step, float grad_scale, void* stream) {
-    return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, ST(stream));
+    return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, g_step_state, ST(stream));
 }
 
 }  // extern "C"

@@ -61,6 +61,21 @@ __device__ __forceinline__ float round_tf32(float x) {
     return __uint_as_float(r);
 }
 
+// Per-step scalars that a CUDA-graph replay must read from DEVICE memory instead of baked kernel arguments (see
+// dx_set_step_state in include/daft_exprt_b200.h).  32 bytes, written by the host before every replay.
+struct StepState {
+    unsigned long long seed_epoch;   // mixed into every dropout seed: fresh masks per replay, same masks in forward and backward
+    float w_adv;                     // adversarial speaker-loss weight of this iteration (loss.py:30-38)
+    float lr;                        // Adam learning rate
+    float bc1, bc2_sqrt;             // Adam bias corrections 1 - beta1^t, sqrt(1 - beta2^t)
+    float pad[2];
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long dyn_seed(unsigned long long seed, const StepState* d) {
+    return d ? seed + d->seed_epoch * 0x9E3779B97F4A7C15ull : seed;
+}
+#endif
+
 // Stateless counter-based dropout: the same (seed, index) gives the same decision in forward and backward, so masks are
 // never stored.  32-bit murmur3-style finaliser over (index, seed): ~10 integer instructions per element (the attention
 // kernels evaluate it once per score).  keep <=> hash >= p * 2^32.

@@ -78,6 +78,7 @@ struct AttnArgs {
     int B, S, H, dh;
     float dropout_p;
     unsigned long long seed;
+    const StepState* dyn;   // nullable: graph mode (dx_set_step_state)
     // tensor-core path: per-head bf16 hi|lo operand planes (attention_mma.cu), S padded to Sp (multiple of 64)
     const __nv_bfloat16 *R, *Tr;     // of qkv:  [2][B][3H][Sp][dh] row-major / [2][B][3H][dh][Sp] transposed
     const __nv_bfloat16 *GR, *GTr;   // of dctx: [2][B][H][Sp][dh] / [2][B][H][dh][Sp]
@@ -107,6 +108,7 @@ struct LnArgs {
     int B, S, D, film_stride;
     float p_in, p_out;
     unsigned long long seed_in, seed_out;
+    const StepState* dyn;   // nullable: graph mode
     // backward
     const float* dy;
     const float* relu_src;  // nullable [B,S,D]: dv/da are multiplied by (relu_src > 0) (ReLU feeding the LN, pre-net/predictor)
@@ -200,6 +202,7 @@ struct LossArgs {
     const long long* out_lens;
     int B, L, T, M, NS, NP;
     float w_adv, w_post, w_dur, w_energy, w_pitch, w_mel;
+    const StepState* dyn;       // nullable: graph mode, w_adv is read from here
     float* acc;                 // scratch [B, 8]
     float* out;                 // [8]
     // backward
@@ -220,6 +223,6 @@ int pitch_multiply(float* pitch, const float* factors, int B, int L, cudaStream_
 
 // fused Adam step over a flat parameter buffer (optim.cu): torch.optim.Adam semantics (L2 weight decay added to grad)
 int adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
-              float weight_decay, int step, float grad_scale, cudaStream_t st);
+              float weight_decay, int step, float grad_scale, const StepState* dyn, cudaStream_t st);
 
 }  // namespace dx

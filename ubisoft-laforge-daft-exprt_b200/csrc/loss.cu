@@ -82,7 +82,7 @@ __global__ void loss_finalize_kernel(LossArgs p) {
         float pn = 0.f;
         if (p.post)
             for (int k = 0; k < p.NP; ++k) pn += p.post[k] * p.post[k];
-        p.out[0] = p.w_adv * s[0] * invB;
+        p.out[0] = (p.dyn ? p.dyn->w_adv : p.w_adv) * s[0] * invB;
         p.out[1] = p.post ? p.w_post * sqrtf(pn) : 0.f;
         p.out[2] = p.w_dur * s[1] * invB;
         p.out[3] = p.w_energy * s[2] * invB;
@@ -137,7 +137,7 @@ __global__ void loss_bwd_small_kernel(LossArgs p) {
         for (int k = 0; k < p.NS; ++k) se += expf(lg[k] - mx);
         long long id = p.spk_ids[i];
         id = id < 0 ? 0 : (id >= p.NS ? p.NS - 1 : id);
-        const float sc = g * p.w_adv / (float)p.B;
+        const float sc = g * (p.dyn ? p.dyn->w_adv : p.w_adv) / (float)p.B;
         for (int k = 0; k < p.NS; ++k) p.dspk_logits[(size_t)i * p.NS + k] = sc * (expf(lg[k] - mx) / se - (k == id ? 1.f : 0.f));
     }
     if (i == 0 && p.post && p.dpost) {

@@ -14,6 +14,8 @@ namespace dx {
 
 template <int VPT>  // values per lane, D = 32 * VPT
 __global__ void __launch_bounds__(256) ln_fwd_kernel(LnArgs p) {
+    const unsigned long long seed_in = dyn_seed(p.seed_in, p.dyn), seed_out = dyn_seed(p.seed_out, p.dyn);
+    (void)seed_in; (void)seed_out;
     constexpr int D = 32 * VPT, NV = VPT / 4;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -43,7 +45,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(LnArgs p) {
         v[j * 4 + 0] = t.x; v[j * 4 + 1] = t.y; v[j * 4 + 2] = t.z; v[j * 4 + 3] = t.w;
         if (p.p_in > 0.f) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[j * 4 + e] *= dropout_scale(p.seed_in, (unsigned long long)row * D + c + e, p.p_in, inv_keep_in);
+            for (int e = 0; e < 4; ++e) v[j * 4 + e] *= dropout_scale(seed_in, (unsigned long long)row * D + c + e, p.p_in, inv_keep_in);
         }
         if (p.res) {
             const float4 r = *reinterpret_cast<const float4*>(p.res + (size_t)row * D + c);
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(LnArgs p) {
         }
         if (p.p_out > 0.f) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] *= dropout_scale(p.seed_out, (unsigned long long)row * D + c + e, p.p_out, inv_keep_out);
+            for (int e = 0; e < 4; ++e) o[e] *= dropout_scale(seed_out, (unsigned long long)row * D + c + e, p.p_out, inv_keep_out);
         }
         if (p.film) {
             const float4 g = *reinterpret_cast<const float4*>(p.film + (size_t)b * p.film_stride + c);
@@ -89,6 +91,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(LnArgs p) {
 // grad wrt v:  g = dy * mask * drop_out * film_gamma * w ;  dv = rstd * (g - mean(g) - xhat * mean(g * xhat))
 template <int VPT>
 __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(LnArgs p) {
+    const unsigned long long seed_in = dyn_seed(p.seed_in, p.dyn), seed_out = dyn_seed(p.seed_out, p.dyn);
+    (void)seed_in; (void)seed_out;
     constexpr int D = 32 * VPT, NV = VPT / 4;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(LnArgs p) {
         h[j * 4 + 0] = hh.x; h[j * 4 + 1] = hh.y; h[j * 4 + 2] = hh.z; h[j * 4 + 3] = hh.w;
         if (p.p_out > 0.f) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) dv[e] *= dropout_scale(p.seed_out, (unsigned long long)row * D + c + e, p.p_out, inv_keep_out);
+            for (int e = 0; e < 4; ++e) dv[e] *= dropout_scale(seed_out, (unsigned long long)row * D + c + e, p.p_out, inv_keep_out);
         }
         if (p.film) {
             const float4 fg = *reinterpret_cast<const float4*>(p.film + (size_t)b * p.film_stride + c);
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(LnArgs p) {
         *reinterpret_cast<float4*>(dvrow + c) = make_float4(o[0], o[1], o[2], o[3]);
         if (darow) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] *= dropout_scale(p.seed_in, (unsigned long long)row * D + c + e, p.p_in, inv_keep_in);
+            for (int e = 0; e < 4; ++e) o[e] *= dropout_scale(seed_in, (unsigned long long)row * D + c + e, p.p_in, inv_keep_in);
             *reinterpret_cast<float4*>(darow + c) = make_float4(o[0], o[1], o[2], o[3]);
         }
     }
@@ -160,6 +164,8 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(LnArgs p) {
 // dfilm_gamma[b][c] += sum_s e*drop_out(xhat*w+b), dfilm_beta[b][c] += sum_s e  with e = dy*mask.
 // Block = 32 columns x 8 row lanes over a row chunk inside one utterance; cross-block accumulation with fp32 atomics.
 __global__ void __launch_bounds__(256) ln_bwd_param_kernel(LnArgs p, int rows_per_chunk) {
+    const unsigned long long seed_in = dyn_seed(p.seed_in, p.dyn), seed_out = dyn_seed(p.seed_out, p.dyn);
+    (void)seed_in; (void)seed_out;
     __shared__ float sm[4][8][33];
     const int D = p.D;
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
@@ -174,7 +180,7 @@ __global__ void __launch_bounds__(256) ln_bwd_param_kernel(LnArgs p, int rows_pe
         for (int s = s0 + rl; s < s1; s += 8) {
             const size_t i = ((size_t)b * p.S + s) * D + c;
             const float e = p.dy[i];
-            const float dm = p.p_out > 0.f ? dropout_scale(p.seed_out, i, p.p_out, inv_keep_out) : 1.f;
+            const float dm = p.p_out > 0.f ? dropout_scale(seed_out, i, p.p_out, inv_keep_out) : 1.f;
             const float h = p.xhat[i];
             ag += e * dm * (h * w + bb);
             abe += e;

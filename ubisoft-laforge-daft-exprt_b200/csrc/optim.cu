@@ -8,7 +8,8 @@ namespace dx {
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             size_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
-                            float grad_scale) {
+                            float grad_scale, const StepState* dyn) {
+    if (dyn) { lr = dyn->lr; bc1 = dyn->bc1; bc2_sqrt = dyn->bc2_sqrt; }   // graph replay: per-step scalars from device memory
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float pi = p[i];
         const float gi = g[i] * grad_scale + wd * pi;
@@ -22,12 +23,12 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 
 int adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
-              float weight_decay, int step, float grad_scale, cudaStream_t st) {
+              float weight_decay, int step, float grad_scale, const StepState* dyn, cudaStream_t st) {
     DX_REQUIRE(step >= 1, "adam_step: step must be >= 1");
     const float bc1 = 1.f - powf(beta1, (float)step);
     const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
     adam_kernel<<<grid_1d(n), 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
-                                                                            bc1, bc2_sqrt, grad_scale);
+                                                                            bc1, bc2_sqrt, grad_scale, dyn);
     return check_launch("adam_step");
 }
 
