@@ -49,6 +49,11 @@ __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
 __device__ __forceinline__ void stsm_x4_trans(void* p, const uint32_t (&r)[4]) {
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
     asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};"
@@ -62,6 +67,8 @@ struct LaneMap {
     __device__ __forceinline__ explicit LaneMap(int lane)
         : a_r(lane & 15), a_c((lane >> 4) << 3), b_r((lane & 7) + ((lane >> 4) << 3)), b_c(((lane >> 3) & 1) << 3) {}
 };
+//   B operand pair from a K-MAJOR tile (smem [k][n], e.g. V[key][d] for P*V): ldmatrix.trans with the A-style lane map,
+//   matrices (k 0-7,n 0-7) (k 8-15,n 0-7) (k 0-7,n 8-15) (k 8-15,n 8-15) -> no transposed copies of any operand are needed.
 // acc[2np], acc[2np+1] += A(hi|lo) * B^T with B = the n-tile pair at Bm[plane][16 np ..][k0 ..] (bf16x3: hi*hi + lo*hi + hi*lo)
 template <int BR, int BP>
 __device__ __forceinline__ void mma_pair(float (*acc)[4], int np, const uint32_t (&ah)[4], const uint32_t (&al)[4],
@@ -69,6 +76,20 @@ __device__ __forceinline__ void mma_pair(float (*acc)[4], int np, const uint32_t
     uint32_t bh[4], bl[4];
     ldsm_x4(bh, &Bm[0][np * 16 + lm.b_r][k0 + lm.b_c]);
     ldsm_x4(bl, &Bm[1][np * 16 + lm.b_r][k0 + lm.b_c]);
+    mma_bf16(acc[2 * np], ah, bh[0], bh[1]);
+    mma_bf16(acc[2 * np], al, bh[0], bh[1]);
+    mma_bf16(acc[2 * np], ah, bl[0], bl[1]);
+    mma_bf16(acc[2 * np + 1], ah, bh[2], bh[3]);
+    mma_bf16(acc[2 * np + 1], al, bh[2], bh[3]);
+    mma_bf16(acc[2 * np + 1], ah, bl[2], bl[3]);
+}
+// same with B = T^T, T = the k-major tile T[plane][k0 ..][16 np ..]
+template <int BR, int BP>
+__device__ __forceinline__ void mma_pair_t(float (*acc)[4], int np, const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                           const __nv_bfloat16 (*T)[BR][BP], int k0, const LaneMap& lm) {
+    uint32_t bh[4], bl[4];
+    ldsm_x4_trans(bh, &T[0][k0 + lm.a_r][np * 16 + lm.a_c]);
+    ldsm_x4_trans(bl, &T[1][k0 + lm.a_r][np * 16 + lm.a_c]);
     mma_bf16(acc[2 * np], ah, bh[0], bh[1]);
     mma_bf16(acc[2 * np], al, bh[0], bh[1]);
     mma_bf16(acc[2 * np], ah, bl[0], bl[1]);
@@ -146,9 +167,9 @@ __device__ __forceinline__ void tile_async(__nv_bfloat16* smem, int sp, const __
 // =====================================================================================================================
 template <int DH>
 struct FwdSmem {
-    static constexpr int KP = DH + 8, VP = 64 + 8;
+    static constexpr int KP = DH + 8;
     __nv_bfloat16 K[2][2][64][KP];    // [stage][plane][key][d]
-    __nv_bfloat16 Vt[2][2][DH][VP];   // [stage][plane][d][key]
+    __nv_bfloat16 V[2][2][64][KP];    // [stage][plane][key][d]  (B operand of P*V through ldmatrix.trans)
 };
 
 template <int DH>
@@ -178,13 +199,13 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(AttnArgs p) {
     const size_t plane = (size_t)p.B * NH * Sp * DH;
     const __nv_bfloat16* Qr = p.R + ((size_t)b * NH + h) * Sp * DH;                 // [Sp][DH]
     const __nv_bfloat16* Kr = p.R + ((size_t)b * NH + p.H + h) * Sp * DH;
-    const __nv_bfloat16* Vtr = p.Tr + ((size_t)b * NH + 2 * p.H + h) * DH * Sp;     // [DH][Sp]
+    const __nv_bfloat16* Vr = p.R + ((size_t)b * NH + 2 * p.H + h) * Sp * DH;
 
     auto issue = [&](int stage, int k0) {
         tile_async<64, DH>(&sm.K[stage][0][0][0], SM::KP, Kr + (size_t)k0 * DH, DH);
         tile_async<64, DH>(&sm.K[stage][1][0][0], SM::KP, Kr + plane + (size_t)k0 * DH, DH);
-        tile_async<DH, 64>(&sm.Vt[stage][0][0][0], SM::VP, Vtr + k0, Sp);
-        tile_async<DH, 64>(&sm.Vt[stage][1][0][0], SM::VP, Vtr + plane + k0, Sp);
+        tile_async<64, DH>(&sm.V[stage][0][0][0], SM::KP, Vr + (size_t)k0 * DH, DH);
+        tile_async<64, DH>(&sm.V[stage][1][0][0], SM::KP, Vr + plane + (size_t)k0 * DH, DH);
         cp_async_commit();
     };
     issue(0, 0);
@@ -279,7 +300,7 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(AttnArgs p) {
             split_pair(s[2 * j + 1][0], s[2 * j + 1][1], ph[2], pl[2]);
             split_pair(s[2 * j + 1][2], s[2 * j + 1][3], ph[3], pl[3]);
 #pragma unroll
-            for (int np = 0; np < ND / 2; ++np) mma_pair<DH, SM::VP>(o, np, ph, pl, sm.Vt[stage], j * 16, lm);
+            for (int np = 0; np < ND / 2; ++np) mma_pair_t<64, SM::KP>(o, np, ph, pl, sm.V[stage], j * 16, lm);
         }
     }
 
@@ -308,10 +329,10 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(AttnArgs p) {
 // =====================================================================================================================
 template <int DH>
 struct BwdSmem {
-    static constexpr int RP = DH + 8;   // row pitch of [row][d] tiles
-    static constexpr int TP = 64 + 8;   // row pitch of [d][row] and [q][key] tiles
-    __nv_bfloat16 K[2][64][RP], V[2][64][RP], Kt[2][DH][TP];
-    __nv_bfloat16 Q[2][64][RP], G[2][64][RP], Qt[2][DH][TP], Gt[2][DH][TP];
+    static constexpr int RP = DH + 8;   // row pitch of the [row][d] operand tiles
+    static constexpr int TP = 64 + 8;   // row pitch of the [q][key] dS tile
+    __nv_bfloat16 K[2][64][RP], V[2][64][RP];   // [plane][key][d]
+    __nv_bfloat16 Q[2][64][RP], G[2][64][RP];   // [plane][q][d]   (G = dO)
     __nv_bfloat16 dS[2][64][TP];
     float lse2[64], delta[64];   // lse * log2(e), delta
     uint32_t rk[64];             // per-query-row dropout keys
@@ -331,11 +352,11 @@ __device__ __forceinline__ void mma_smem_ab(float (*acc)[4], const __nv_bfloat16
     }
 }
 
-// acc[n] (n < NT) += A (from score C-fragments sc[8][4], 64 columns = 4 k-steps) * B^T (B from smem [n][k], pitch BP).
+// acc[n] (n < NT) += A (from score C-fragments sc[8][4], 64 columns = 4 k-steps) * B (B = k-major tile in smem [k][n], pitch BP).
 // With STAGE, the split fragments are also stored TRANSPOSED (stmatrix.trans) into dst[plane][64][TP] at columns col0.. :
 // the C-fragment of a [16 keys][64 q] tile lands q-major, ready to be the A operand of the dQ product.
-template <int NT, int BP, int BR, bool STAGE, int TP>
-__device__ __forceinline__ void mma_frag_b(float (*acc)[4], const float (*sc)[4], const __nv_bfloat16 (*Bm)[BR][BP], const LaneMap& lm,
+template <int NT, int BP, bool STAGE, int TP>
+__device__ __forceinline__ void mma_frag_b(float (*acc)[4], const float (*sc)[4], const __nv_bfloat16 (*Bm)[64][BP], const LaneMap& lm,
                                            __nv_bfloat16 (*dst)[64][TP], int col0, int lane) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -350,12 +371,12 @@ __device__ __forceinline__ void mma_frag_b(float (*acc)[4], const float (*sc)[4]
             stsm_x4_trans(&dst[1][row][col], al);
         }
 #pragma unroll
-        for (int np = 0; np < NT / 2; ++np) mma_pair<BR, BP>(acc, np, ah, al, Bm, j * 16, lm);
+        for (int np = 0; np < NT / 2; ++np) mma_pair_t<64, BP>(acc, np, ah, al, Bm, j * 16, lm);
     }
 }
 
 template <int DH>
-__global__ void __launch_bounds__(128) attn_bwd_mma_kernel(AttnArgs p) {
+__global__ void __launch_bounds__(128, DH == 16 ? 4 : 2) attn_bwd_mma_kernel(AttnArgs p) {
     const unsigned long long seed = dyn_seed(p.seed, p.dyn);
     using SM = BwdSmem<DH>;
     constexpr int KS = DH / 16, ND = DH / 8;
@@ -381,18 +402,13 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(AttnArgs p) {
     const __nv_bfloat16* Qr = p.R + ((size_t)b * NH + h) * Sp * DH;
     const __nv_bfloat16* Kr = p.R + ((size_t)b * NH + p.H + h) * Sp * DH;
     const __nv_bfloat16* Vr = p.R + ((size_t)b * NH + 2 * p.H + h) * Sp * DH;
-    const __nv_bfloat16* Qtr = p.Tr + ((size_t)b * NH + h) * DH * Sp;
-    const __nv_bfloat16* Ktr = p.Tr + ((size_t)b * NH + p.H + h) * DH * Sp;
     const __nv_bfloat16* Gr = p.GR + ((size_t)b * p.H + h) * Sp * DH;
-    const __nv_bfloat16* Gtr = p.GTr + ((size_t)b * p.H + h) * DH * Sp;
 
     auto issue_q = [&](int q0) {
 #pragma unroll
         for (int pl = 0; pl < 2; ++pl) {
             tile_async<64, DH>(&sm.Q[pl][0][0], SM::RP, Qr + pl * plane + (size_t)q0 * DH, DH);
             tile_async<64, DH>(&sm.G[pl][0][0], SM::RP, Gr + pl * gplane + (size_t)q0 * DH, DH);
-            tile_async<DH, 64>(&sm.Qt[pl][0][0], SM::TP, Qtr + pl * plane + q0, Sp);
-            tile_async<DH, 64>(&sm.Gt[pl][0][0], SM::TP, Gtr + pl * gplane + q0, Sp);
         }
         cp_async_commit();
     };
@@ -400,7 +416,6 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(AttnArgs p) {
     for (int pl = 0; pl < 2; ++pl) {
         tile_async<64, DH>(&sm.K[pl][0][0], SM::RP, Kr + pl * plane + (size_t)k0 * DH, DH);
         tile_async<64, DH>(&sm.V[pl][0][0], SM::RP, Vr + pl * plane + (size_t)k0 * DH, DH);
-        tile_async<DH, 64>(&sm.Kt[pl][0][0], SM::TP, Ktr + pl * plane + k0, Sp);
     }
     issue_q(0);
 
@@ -444,11 +459,11 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(AttnArgs p) {
                 dp[n][e] = pv * ((keep ? dp[n][e] * inv_keep : 0.f) - (odd ? dl.y : dl.x));
             }
         }
-        mma_frag_b<ND, SM::TP, DH, false, SM::TP>(dv, st, sm.Gt, lm, sm.dS, 0, lane);          // dV += P^T dO
-        mma_frag_b<ND, SM::TP, DH, true, SM::TP>(dk, dp, sm.Qt, lm, sm.dS, warp * 16, lane);   // dK += dS^T Q (Q carries 1/sqrt(dh)); dS staged q-major
+        mma_frag_b<ND, SM::RP, false, SM::TP>(dv, st, sm.G, lm, sm.dS, 0, lane);          // dV += P^T dO
+        mma_frag_b<ND, SM::RP, true, SM::TP>(dk, dp, sm.Q, lm, sm.dS, warp * 16, lane);   // dK += dS^T Q (Q carries 1/sqrt(dh)); dS staged q-major
         __syncthreads();   // (B) dS complete; nobody reads Q/G/Qt/Gt of this tile any more
         if (q0 + 64 < len) issue_q(q0 + 64);   // overlaps with the dQ product below
-        // dQ[16 q rows of this warp][DH] = dS[q][64 keys] K[64 keys][DH]  (B = K^T tile [d][key])
+        // dQ[16 q rows of this warp][DH] = dS[q][64 keys] K[64 keys][DH]  (B = the K tile itself, k-major)
         float dq[ND][4];
 #pragma unroll
         for (int n = 0; n < ND; ++n) { dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f; }
@@ -458,7 +473,7 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(AttnArgs p) {
             ldsm_x4(ah, &sm.dS[0][warp * 16 + lm.a_r][ks * 16 + lm.a_c]);
             ldsm_x4(al, &sm.dS[1][warp * 16 + lm.a_r][ks * 16 + lm.a_c]);
 #pragma unroll
-            for (int np = 0; np < ND / 2; ++np) mma_pair<DH, SM::TP>(dq, np, ah, al, sm.Kt, ks * 16, lm);
+            for (int np = 0; np < ND / 2; ++np) mma_pair_t<64, SM::RP>(dq, np, ah, al, sm.K, ks * 16, lm);
         }
         const int qa = q0 + warp * 16 + g, qb = qa + 8;
 #pragma unroll
@@ -520,10 +535,9 @@ inline int pad64(int s) { return (s + 63) / 64 * 64; }
 
 void bind_planes(AttnArgs& a, void* planes) {
     uint8_t* base = (uint8_t*)(((uintptr_t)planes + 255) & ~(uintptr_t)255);
-    const size_t half = (size_t)2 * a.B * 3 * a.H * pad64(a.S) * a.dh * 2;
     a.Sp = pad64(a.S);
     a.R = (const __nv_bfloat16*)base;
-    a.Tr = (const __nv_bfloat16*)(base + half);
+    a.Tr = nullptr;   // no transposed planes: the kernels transpose on the fly with ldmatrix.trans
 }
 
 }  // namespace
@@ -532,11 +546,11 @@ bool attention_mma_supported(const AttnArgs& a) {
     return (a.dh == 16 || a.dh == 32 || a.dh == 64) && ((a.H * a.dh) % 64 == 0);
 }
 
-// qkv planes: R and Tr, 2 planes each, [B][3H][Sp][dh] bf16
-size_t attention_planes_bytes(int B, int S, int H, int dh) { return (size_t)4 * B * 3 * H * pad64(S) * dh * 2 + 256; }
-// backward scratch: dO planes (R and Tr) + delta [B,H,S] fp32
+// qkv planes: hi|lo, [2][B][3H][Sp][dh] bf16
+size_t attention_planes_bytes(int B, int S, int H, int dh) { return (size_t)2 * B * 3 * H * pad64(S) * dh * 2 + 256; }
+// backward scratch: dO planes (hi|lo) + delta [B,H,S] fp32
 size_t attention_bwd_scratch_bytes(int B, int S, int H, int dh) {
-    return (size_t)4 * B * H * pad64(S) * dh * 2 + (size_t)B * H * S * 4 + 512;
+    return (size_t)2 * B * H * pad64(S) * dh * 2 + (size_t)B * H * S * 4 + 512;
 }
 
 int attention_fwd_mma(const AttnArgs& a_in, void* planes, cudaStream_t st) {
@@ -562,8 +576,8 @@ int attention_bwd_mma(const AttnArgs& a_in, void* planes, void* scratch, cudaStr
     uint8_t* sb = (uint8_t*)(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
     const size_t ghalf = (size_t)2 * a.B * a.H * a.Sp * a.dh * 2;
     a.GR = (const __nv_bfloat16*)sb;
-    a.GTr = (const __nv_bfloat16*)(sb + ghalf);
-    a.delta = (float*)(sb + 2 * ghalf);
+    a.GTr = nullptr;
+    a.delta = (float*)(sb + ghalf);
     const int D = a.H * a.dh;
     int rc = attention_bwd_prepare(a, st);   // delta + zero dqkv
     if (rc) return rc;
