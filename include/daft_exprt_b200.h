@@ -50,6 +50,11 @@ int dx_debug_set_trace(void* buf);
  * same pass (what dx_split_weight_planes would produce). */
 int dx_pack_conv_weight(const float* w, float* fwd, float* dgrad, void* fwd_planes, void* dgrad_planes, int Cout, int Cin, int KW,
                         int round_tf32, void* stream);
+/* The same repack for MANY weights in ONE launch (an optimiser step makes every pack stale at once).  descs_device: device
+ * array of n_desc 64-byte descriptors { const float* w; float* fwd; float* dgrad; void* fwd_planes; void* dgrad_planes;
+ * int Cout, Cin, KW, block0; int64 pad } (KW <= 4), block0 = running sum of ceil(Cout/32)*ceil(Cin/32) over the previous
+ * descriptors, total_blocks = that sum over all of them. */
+int dx_pack_conv_weights_batched(const void* descs_device, int n_desc, int total_blocks, int round_tf32, void* stream);
 /* y[b,s,n] = epi(alpha * sum_{tap,c} x[b, s+tap-(KW-1)/2, c] * w[tap][n][c] + bias[n]); zero padding at s<0, s>=S only.
  * epi: relu, then multiply by (relu_src > 0) when relu_src != NULL (ReLU backward fused into a dgrad), then + add_src
  * (same layout as y; residual / gradient accumulation) when != NULL, then optional tf32 rounding of the stored value.  backend < 0 selects the global default. */

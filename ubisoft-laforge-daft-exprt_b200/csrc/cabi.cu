@@ -74,6 +74,10 @@ int dx_pack_conv_weight(const float* w, float* fwd, float* dgrad, void* fwd_plan
     return pack_conv_weight(w, fwd, dgrad, fwd_planes, dgrad_planes, Cout, Cin, KW, round_tf32, ST(stream));
 }
 
+int dx_pack_conv_weights_batched(const void* descs_device, int n_desc, int total_blocks, int round_tf32, void* stream) {
+    return pack_conv_weights_batched(descs_device, n_desc, total_blocks, round_tf32, ST(stream));
+}
+
 static ConvGemmArgs gemm_args(const float* x, const void* x_planes, const float* w_packed, const void* w_planes, const float* bias,
                               const float* relu_src, const float* add_src, float* y, void* ws, size_t wsb, int B, int S, int Cin,
                               int Cout, int KW, int ldx, int ldy, float alpha, int relu, int round_tf32,

@@ -287,6 +287,79 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, float* __re
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// batched repack: ALL stale weights of the model in one launch (one optimiser step invalidates ~60 packs at once).
+// One block = one 32 (co) x 32 (ci) tile of one weight, all taps, transposed through shared memory so that the source reads
+// and both packed layouts' writes are coalesced.
+// ---------------------------------------------------------------------------------------------------------------------
+struct PackDesc {   // 64 bytes, mirrored by ops.py (struct '<5Q4i8x')
+    const float* w;
+    float* fwd;
+    float* dgrad;
+    __nv_bfloat16* fwd_planes;
+    __nv_bfloat16* dgrad_planes;
+    int Cout, Cin, KW, block0;   // block0: index of this weight's first block in the launch
+    long long pad;
+};
+static_assert(sizeof(PackDesc) == 64, "PackDesc is part of the C-ABI (dx_pack_conv_weights_batched)");
+
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackDesc* __restrict__ descs, int n_desc, int round) {
+    __shared__ float tile[4][32][33];
+    int lo = 0, hi = n_desc - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (descs[mid].block0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const PackDesc d = descs[lo];
+    const int KW = d.KW, tiles_ci = (d.Cin + 31) / 32, local = (int)blockIdx.x - d.block0;
+    const int co0 = (local / tiles_ci) * 32, ci0 = (local % tiles_ci) * 32;
+    const int seg = min(32, d.Cin - ci0) * KW;   // contiguous source floats per output channel
+    for (int idx = threadIdx.x; idx < 32 * 32 * KW; idx += 256) {
+        const int r = idx / (32 * KW), j = idx - r * (32 * KW);
+        if (co0 + r < d.Cout && j < seg) {
+            float v = d.w[((size_t)(co0 + r) * d.Cin + ci0) * KW + j];
+            if (round) v = round_tf32(v);
+            tile[j % KW][r][j / KW] = v;
+        }
+    }
+    __syncthreads();
+    const size_t n = (size_t)d.Cout * d.Cin * KW;
+    for (int idx = threadIdx.x; idx < KW * 1024; idx += 256) {   // fwd [tap][co][ci]: ci fastest
+        const int tap = idx >> 10, r = (idx >> 5) & 31, c = idx & 31;
+        const int co = co0 + r, ci = ci0 + c;
+        if (co < d.Cout && ci < d.Cin) {
+            const float v = tile[tap][r][c];
+            const size_t of = ((size_t)tap * d.Cout + co) * d.Cin + ci;
+            if (d.fwd) d.fwd[of] = v;
+            if (d.fwd_planes) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                d.fwd_planes[of] = h;
+                d.fwd_planes[n + of] = __float2bfloat16_rn(v - __bfloat162float(h));
+            }
+        }
+    }
+    for (int idx = threadIdx.x; idx < KW * 1024; idx += 256) {   // dgrad [KW-1-tap][ci][co]: co fastest
+        const int tap = idx >> 10, c = (idx >> 5) & 31, r = idx & 31;
+        const int co = co0 + r, ci = ci0 + c;
+        if (co < d.Cout && ci < d.Cin) {
+            const float v = tile[tap][r][c];
+            const size_t od = ((size_t)(KW - 1 - tap) * d.Cin + ci) * d.Cout + co;
+            if (d.dgrad) d.dgrad[od] = v;
+            if (d.dgrad_planes) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                d.dgrad_planes[od] = h;
+                d.dgrad_planes[n + od] = __float2bfloat16_rn(v - __bfloat162float(h));
+            }
+        }
+    }
+}
+
+int pack_conv_weights_batched(const void* descs_device, int n_desc, int total_blocks, int round, cudaStream_t st) {
+    DX_REQUIRE(descs_device != nullptr && n_desc > 0 && total_blocks > 0, "pack_conv_weights_batched: empty descriptor table");
+    pack_weights_batched_kernel<<<total_blocks, 256, 0, st>>>(static_cast<const PackDesc*>(descs_device), n_desc, round);
+    return check_launch("pack_conv_weights_batched");
+}
+
 int pack_conv_weight(const float* w, float* fwd, float* dgrad, void* fwd_planes, void* dgrad_planes, int Cout, int Cin, int KW,
                      int round, cudaStream_t st) {
     const size_t n = (size_t)Cout * Cin * KW;

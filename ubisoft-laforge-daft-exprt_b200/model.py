@@ -284,10 +284,18 @@ class DaftExprt(nn.Module):
             return torch.stack([f.detach() for f in films], dim=1)
 
     # -- model.py:755-787 ------------------------------------------------------------------------------------------------
+    def _gemm_weights(self):
+        ws = self.__dict__.get('_gemm_weight_list')
+        if ws is None:
+            ws = [p for p in self.parameters() if p.dim() in (2, 3)]
+            self.__dict__['_gemm_weight_list'] = ws
+        return ws
+
     def forward(self, inputs):
         (symbols, durations_float, durations_int, symbols_energy, symbols_pitch, input_lengths, frames_energy, frames_pitch,
          mel_specs, output_lengths, speaker_ids) = inputs
         input_lengths, output_lengths = input_lengths.detach().contiguous(), output_lengths.detach().contiguous()
+        ops.prepack(self._gemm_weights())   # one launch refreshes every weight pack the optimiser step made stale
         prosody_embed, (enc_film, pp_film, dec_film) = self.prosody_encoder(frames_energy, frames_pitch, mel_specs,
                                                                              speaker_ids.contiguous(), output_lengths)
         spk_preds = self.speaker_classifier(prosody_embed)
@@ -346,6 +354,7 @@ class DaftExprt(nn.Module):
          speaker_ids) = inputs
         if pitch_transform not in ('add', 'multiply'):
             raise NotImplementedError
+        ops.prepack(self._gemm_weights())
         input_lengths, ref_lengths = input_lengths.contiguous(), ref_lengths.contiguous()
         speaker_ids = speaker_ids.contiguous()
         _, (enc_film, pp_film, dec_film) = self.prosody_encoder(energy_refs, pitch_refs, mel_spec_refs, speaker_ids, ref_lengths)

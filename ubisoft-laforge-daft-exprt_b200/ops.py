@@ -18,6 +18,7 @@ the fusions live below the ABI:
 """
 import ctypes
 import threading
+import struct
 import weakref
 
 import torch
@@ -27,6 +28,7 @@ from . import cabi
 _state = threading.local()
 _weights_epoch = 0
 _pack_cache = {}
+_desc_tables = {}
 _seed_counter = [0]
 _backend = [cabi.DX_GEMM_FP32_CUDA_CORES]
 launch_count = [0]   # number of C-ABI compute calls issued (each launches >= 1 of our kernels)
@@ -58,7 +60,10 @@ def invalidate_packed_weights():
     """Call after parameters were modified through raw pointers (e.g. dx_adam_step), which does not bump tensor versions."""
     global _weights_epoch
     _weights_epoch += 1
-    _pack_cache.clear()
+    for k in [k for k, hit in _pack_cache.items() if hit[3]() is None]:   # the pack buffers of live weights are kept and refilled
+        del _pack_cache[k]
+    if len(_desc_tables) > 16:
+        _desc_tables.clear()
 
 
 def _st():
@@ -107,22 +112,63 @@ def packed(weight):
     key = id(weight)
     ver = (w.data_ptr(), w._version, _weights_epoch, _backend[0])
     hit = _pack_cache.get(key)
-    if hit is not None and hit[0] == ver and hit[3]() is weight:   # id() can be recycled: check object identity too
+    if hit is not None and hit[3]() is not weight:   # id() can be recycled: check object identity too
+        hit = None
+    if hit is not None and hit[0] == ver:
         return hit[1], hit[2]
     w = _check_input(w)
     cout, cin = w.shape[0], w.shape[1]
     kw = w.shape[2] if w.dim() == 3 else 1
-    fwd = torch.empty(kw, cout, cin, device=w.device, dtype=torch.float32)
-    dgrad = torch.empty(kw, cin, cout, device=w.device, dtype=torch.float32)
     rnd = 1 if _backend[0] == cabi.DX_GEMM_TCGEN05_TF32 else 0
-    fp = dp = None
-    if _backend[0] == cabi.DX_GEMM_TCGEN05_BF16X3:
-        fp = torch.empty(2 * fwd.numel(), device=w.device, dtype=torch.bfloat16)
-        dp = torch.empty(2 * fwd.numel(), device=w.device, dtype=torch.bfloat16)
-    _call('dx_pack_conv_weight', _p(w), _p(fwd), _p(dgrad), _p(fp), _p(dp), cout, cin, kw, rnd, _st())
-    fwd, dgrad = PackedWeight(fwd, fp), PackedWeight(dgrad, dp)
+    if hit is not None and hit[0][3] == ver[3] and hit[1].w.device == w.device:
+        fwd, dgrad = hit[1], hit[2]                  # same weight, same backend: refill the existing buffers
+        _call('dx_pack_conv_weight', _p(w), _p(fwd.w), _p(dgrad.w), _p(fwd.planes), _p(dgrad.planes), cout, cin, kw, rnd, _st())
+    else:
+        fw = torch.empty(kw, cout, cin, device=w.device, dtype=torch.float32)
+        dg = torch.empty(kw, cin, cout, device=w.device, dtype=torch.float32)
+        fp = dp = None
+        if _backend[0] == cabi.DX_GEMM_TCGEN05_BF16X3:
+            fp = torch.empty(2 * fw.numel(), device=w.device, dtype=torch.bfloat16)
+            dp = torch.empty(2 * fw.numel(), device=w.device, dtype=torch.bfloat16)
+        _call('dx_pack_conv_weight', _p(w), _p(fw), _p(dg), _p(fp), _p(dp), cout, cin, kw, rnd, _st())
+        fwd, dgrad = PackedWeight(fw, fp), PackedWeight(dg, dp)
     _pack_cache[key] = (ver, fwd, dgrad, weakref.ref(weight))
     return fwd, dgrad
+
+
+def prepack(weights):
+    """Refresh, with ONE launch, every stale pack among `weights` that `packed()` has built before (an optimiser step makes
+    all ~60 of them stale at once).  Weights never seen by `packed()`, or whose storage moved, are left to `packed()`.
+    The pack buffers are refilled IN PLACE: a forward of a model invalidates the packs held by an older, not yet
+    back-propagated forward of the same model if the weights changed in between."""
+    stale = []
+    for wt in weights:
+        hit = _pack_cache.get(id(wt))
+        if hit is None or hit[3]() is not wt:
+            continue
+        w = wt.detach()
+        ver = (w.data_ptr(), w._version, _weights_epoch, _backend[0])
+        if hit[0] == ver or hit[0][0] != ver[0] or hit[0][3] != ver[3] or not w.is_contiguous() or hit[1].shape[0] > 4:
+            continue
+        stale.append((wt, w, ver, hit))
+    if len(stale) < 2:
+        return
+    key = tuple((w.data_ptr(), hit[1].w.data_ptr()) for _, w, _, hit in stale)
+    table = _desc_tables.get(key)
+    if table is None:
+        raw, block0 = bytearray(), 0
+        for _, w, _, hit in stale:
+            kw, cout, cin = hit[1].shape
+            raw += struct.pack('<5Q4i8x', w.data_ptr(), _p(hit[1].w) or 0, _p(hit[2].w) or 0, _p(hit[1].planes) or 0,
+                               _p(hit[2].planes) or 0, cout, cin, kw, block0)
+            block0 += ((cout + 31) // 32) * ((cin + 31) // 32)
+        dev_table = torch.frombuffer(raw, dtype=torch.uint8).to(stale[0][1].device)
+        table = (dev_table, block0)
+        _desc_tables[key] = table
+    rnd = 1 if _backend[0] == cabi.DX_GEMM_TCGEN05_TF32 else 0
+    _call('dx_pack_conv_weights_batched', _p(table[0]), len(stale), table[1], rnd, _st())
+    for wt, _, ver, hit in stale:
+        _pack_cache[id(wt)] = (ver, hit[1], hit[2], hit[3])
 
 
 def make_planes(x, rows, C, ld=None, want_colsum=False):
