@@ -65,10 +65,14 @@ int dx_pack_conv_weights_batched(const void* descs_device, int n_desc, int total
 /* lens (nullable, [B] int64) + halo: padding skip.  The caller asserts that output rows s >= len[b] + halo cannot reach any valid
  * result (they are masked downstream / beyond the receptive field of what follows); the tensor-core path then writes whole
  * 128-row tiles made of such rows as ZEROS without computing them (the fp32 backend computes everything). */
+/* Plane hand-over between GEMMs (tensor-core backends, Cout % 32 == 0): y_planes (nullable) receives the output as bf16 hi|lo
+ * planes [2][B*S][Cout] straight from the epilogue, so that the next GEMM consumes it as x_planes without a split pass; y may
+ * then be NULL (no fp32 copy at all).  x may be NULL when x_planes is given.  relu_src_hi (nullable): the ReLU mask taken from
+ * the bf16 hi plane [B*S][Cout] of the forward activation instead of an fp32 relu_src (hi > 0 <=> the fp32 value was > 0). */
 int dx_conv_gemm(const float* x, const void* x_planes, const float* w_packed, const void* w_planes, const float* bias,
-                 const float* relu_src, const float* add_src, float* y, void* workspace, size_t workspace_bytes,
-                 const int64_t* lens, int halo, int B, int S, int Cin, int Cout, int KW, int ldx, int ldy, float alpha, int relu,
-                 int round_tf32, int backend, void* stream);
+                 const float* relu_src, const void* relu_src_hi, const float* add_src, float* y, void* y_planes, void* workspace,
+                 size_t workspace_bytes, const int64_t* lens, int halo, int B, int S, int Cin, int Cout, int KW, int ldx, int ldy,
+                 float alpha, int relu, int round_tf32, int backend, void* stream);
 size_t dx_conv_gemm_workspace(int B, int S, int Cin, int Cout, int KW, int have_x_planes, int have_w_planes, int backend);
 /* colsum_out (nullable, [C]): column sums of x accumulated in the same pass (= the bias gradient when x is a dy) */
 int dx_split_planes(const float* x, int ld, void* planes, float* colsum_out, int rows, int C, void* stream);
@@ -80,6 +84,8 @@ int dx_conv_wgrad(const float* x, const void* x_planes, const float* dy, const v
                   void* workspace, size_t workspace_bytes, const int64_t* lens, int halo, int B, int S, int Cin, int Cout, int KW,
                   int ldx, float alpha, int backend, void* stream);
 int dx_colsum(const float* dy, float* db, int rows, int C, float alpha, void* stream);
+/* the same over bf16 hi|lo planes [2][rows][C] (db[c] = sum_r hi + lo): bias gradient of a dy that only exists as planes */
+int dx_colsum_planes(const void* planes, float* db, int rows, int C, void* stream);
 int dx_relu_bwd(const float* dy, const float* y, float* dx, size_t n, void* stream);
 int dx_scale_copy(const float* x, float* y, float alpha, size_t n, void* stream);
 

@@ -508,3 +508,34 @@ def test_graph_step_fresh_dropout_masks(dev):
     assert np.isfinite(a).all() and np.isfinite(b).all()
     assert abs(a[5] - b[5]) > 1e-6 * abs(a[5])          # different masks -> different mel loss
     assert abs(a[5] - b[5]) < 0.2 * abs(a[5])           # ... but the same model
+
+
+def test_gemm_plane_handover(dev):
+    """Epilogue-written operand planes (dx_conv_gemm y_planes / relu_src_hi) and dx_colsum_planes against the fp32 output path."""
+    from daft_exprt_b200 import ops
+    set_backend('bf16x3')
+    assert ops.plane_handover(128, 1024) and not ops.plane_handover(128, 80)
+    g = torch.Generator().manual_seed(5)
+    B, S, cin, cout = 3, 150, 128, 256
+    x = torch.randn(B, S, cin, generator=g).to(dev)
+    w = (torch.randn(cout, cin, 3, generator=g) * 0.1).to(dev)
+    b = torch.randn(cout, generator=g).to(dev)
+    lens = torch.tensor([150, 20, 97], device=dev)
+    wp, _ = ops.packed(w)
+    xP = ops.make_planes(x, B * S, cin)
+    y = ops.conv_gemm(x, wp, b, B, S, relu=True, x_planes=xP, lens=lens, halo=1)
+    y2, yP = ops.conv_gemm(None, wp, b, B, S, relu=True, x_planes=xP, lens=lens, halo=1, emit_planes=True, want_y=False)
+    assert y2 is None and yP.shape == (2, B * S, cout)
+    rec = (yP[0].float() + yP[1].float()).view(B, S, cout)
+    assert float((rec - y).abs().max()) <= 2.0 ** -15 * float(y.abs().max())
+    assert torch.equal(yP[0] > 0, (y > 0).view(B * S, cout))                # the hi plane carries the ReLU mask exactly
+    # ReLU mask from the hi plane == mask from the fp32 activation
+    dy = torch.randn(B, S, cout, generator=g).to(dev)
+    wq = (torch.randn(cout, cout, 1, generator=g) * 0.1).to(dev)
+    wqp, _ = ops.packed(wq)
+    dyP = ops.make_planes(dy, B * S, cout)
+    a = ops.conv_gemm(dy, wqp, None, B, S, relu_src=y, x_planes=dyP)
+    a2, aP = ops.conv_gemm(None, wqp, None, B, S, relu_src_hi=yP, x_planes=dyP, emit_planes=True)
+    assert torch.equal(a, a2)
+    cs = ops.colsum_planes(aP, B * S, cout)
+    np.testing.assert_allclose(cs.cpu().numpy(), a.view(-1, cout).sum(0).cpu().numpy(), rtol=1e-4, atol=1e-3)

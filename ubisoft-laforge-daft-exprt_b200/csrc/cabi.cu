@@ -81,9 +81,9 @@ int dx_pack_conv_weights_batched(const void* descs_device, int n_desc, int total
 static ConvGemmArgs gemm_args(const float* x, const void* x_planes, const float* w_packed, const void* w_planes, const float* bias,
                               const float* relu_src, const float* add_src, float* y, void* ws, size_t wsb, int B, int S, int Cin,
                               int Cout, int KW, int ldx, int ldy, float alpha, int relu, int round_tf32,
-                              const int64_t* lens = nullptr, int halo = 0) {
+                              const int64_t* lens = nullptr, int halo = 0, const void* relu_src_hi = nullptr, void* y_planes = nullptr) {
     ConvGemmArgs a;
-    a.lens = (cll)lens; a.halo = halo;
+    a.lens = (cll)lens; a.halo = halo; a.relu_src_hi = relu_src_hi; a.y_planes = y_planes;
     a.x = x; a.w = w_packed; a.bias = bias; a.relu_src = relu_src; a.add_src = add_src; a.y = y;
     a.B = B; a.S = S; a.Cin = Cin; a.Cout = Cout; a.KW = KW; a.ldx = ldx; a.ldy = ldy;
     a.alpha = alpha; a.relu = relu; a.round_tf32 = round_tf32;
@@ -108,14 +108,15 @@ size_t dx_conv_gemm_workspace(int B, int S, int Cin, int Cout, int KW, int have_
 }
 
 int dx_conv_gemm(const float* x, const void* x_planes, const float* w_packed, const void* w_planes, const float* bias,
-                 const float* relu_src, const float* add_src, float* y, void* workspace, size_t workspace_bytes,
-                 const int64_t* lens, int halo, int B, int S, int Cin, int Cout, int KW, int ldx, int ldy, float alpha, int relu,
-                 int round_tf32, int backend, void* stream) {
+                 const float* relu_src, const void* relu_src_hi, const float* add_src, float* y, void* y_planes, void* workspace,
+                 size_t workspace_bytes, const int64_t* lens, int halo, int B, int S, int Cin, int Cout, int KW, int ldx, int ldy,
+                 float alpha, int relu, int round_tf32, int backend, void* stream) {
     ConvGemmArgs a = gemm_args(x, x_planes, w_packed, w_planes, bias, relu_src, add_src, y, workspace, workspace_bytes, B, S, Cin,
-                               Cout, KW, ldx, ldy, alpha, relu, round_tf32, lens, halo);
+                               Cout, KW, ldx, ldy, alpha, relu, round_tf32, lens, halo, relu_src_hi, y_planes);
     DX_REQUIRE(B > 0 && S > 0 && Cin > 0 && Cout > 0 && (KW == 1 || KW == 3), "dx_conv_gemm: bad shape B=%d S=%d Cin=%d Cout=%d KW=%d", B, S, Cin, Cout, KW);
     const int be = backend < 0 ? g_backend : backend;
     if (be != DX_GEMM_FP32_CUDA_CORES && conv_gemm_tc_supported(a)) return conv_gemm_tc(a, ST(stream));
+    DX_REQUIRE(!relu_src_hi && !y_planes && y && x, "dx_conv_gemm: y_planes / relu_src_hi / plane-only operands need the tensor-core path (Cin=%d Cout=%d)", Cin, Cout);
     return conv_gemm_simt(a, ST(stream));
 }
 
@@ -153,6 +154,7 @@ int dx_conv_wgrad(const float* x, const void* x_planes, const float* dy, const v
 }
 
 int dx_colsum(const float* dy, float* db, int rows, int C, float alpha, void* stream) { return colsum(dy, db, rows, C, alpha, ST(stream)); }
+int dx_colsum_planes(const void* planes, float* db, int rows, int C, void* stream) { return colsum_planes(planes, db, rows, C, ST(stream)); }
 int dx_relu_bwd(const float* dy, const float* y, float* dx_, size_t n, void* stream) { return relu_bwd(dy, y, dx_, n, ST(stream)); }
 int dx_scale_copy(const float* x, float* y, float alpha, size_t n, void* stream) { return scale_copy(x, y, alpha, n, ST(stream)); }
 

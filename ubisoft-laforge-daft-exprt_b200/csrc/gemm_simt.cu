@@ -224,6 +224,44 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
     }
 }
 
+// db[c] = sum_r (hi[r][c] + lo[r][c]) over bf16 hi|lo planes (the bias gradient when only the planes of a dy exist).
+// One block = 64 columns (bf16x2 per thread) x 8 row lanes.
+__global__ void __launch_bounds__(256) colsum_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                                            float* __restrict__ db, int R, int C, int rows_per_chunk) {
+    __shared__ float2 sm[8][33];
+    const int c = blockIdx.x * 64 + 2 * (threadIdx.x & 31), lane_r = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * rows_per_chunk, r1 = min(R, r0 + rows_per_chunk);
+    float2 s = make_float2(0.f, 0.f);
+    if (c < C) {
+        for (int r = r0 + lane_r; r < r1; r += 8) {
+            const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hi + (size_t)r * C + c));
+            const float2 l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(lo + (size_t)r * C + c));
+            s.x += h.x + l.x;
+            s.y += h.y + l.y;
+        }
+    }
+    sm[lane_r][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (lane_r == 0 && c < C) {
+        float2 tot = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { tot.x += sm[k][threadIdx.x].x; tot.y += sm[k][threadIdx.x].y; }
+        atomicAdd(db + c, tot.x);
+        atomicAdd(db + c + 1, tot.y);
+    }
+}
+
+int colsum_planes(const void* planes, float* db, int R, int C, cudaStream_t st) {
+    DX_REQUIRE(C % 2 == 0 && (((uintptr_t)planes) & 3) == 0, "colsum_planes: C must be even (C = %d)", C);
+    DX_CUDA(cudaMemsetAsync(db, 0, (size_t)C * sizeof(float), st));
+    const int chunks = max(1, min(ceil_div(R, 256), 148 * 8 / max(1, ceil_div(C, 64))));
+    const int rpc = ceil_div(R, chunks);
+    dim3 grid(ceil_div(C, 64), ceil_div(R, rpc));
+    const __nv_bfloat16* hi = static_cast<const __nv_bfloat16*>(planes);
+    colsum_planes_kernel<<<grid, 256, 0, st>>>(hi, hi + (size_t)R * C, db, R, C, rpc);
+    return check_launch("colsum_planes");
+}
+
 size_t conv_wgrad_simt_workspace(const ConvWgradArgs& a, int* nsplit_out) {
     const int tiles = ceil_div(a.Cout, BM) * ceil_div(a.Cin, BN) * a.KW;
     const int R = a.B * a.S;

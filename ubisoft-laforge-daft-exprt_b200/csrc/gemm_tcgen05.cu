@@ -136,6 +136,10 @@ struct TcParams {
     const float* bias;
     const float* relu_src;
     const float* add_src;
+    const __nv_bfloat16* relu_src_hi;   // ReLU mask from a bf16 hi plane [B*S][Cout] (Cout % 32 == 0)
+    __nv_bfloat16* y_planes;            // optional: output as bf16 hi|lo planes [2][B*S][Cout] (Cout % 32 == 0)
+    long long y_plane_elems;            // B*S*Cout
+    int skip_y;                         // no fp32 output (planes only)
     int B, S, Cin, Cout, KW, ldy;
     int tiles_m_per_b, tiles_n, num_tiles, k_chunks;   // CONV: tiles over (b, s) x n;  WGRAD: tiles_m = co tiles, tiles_n = ci tiles
     int nsplit;                                         // WGRAD: batch ranges
@@ -153,6 +157,13 @@ struct TileCoord {
     int o0, o1, o2;   // output coordinates of column chunk 0
     int tap, k_begin, k_end;   // K iterations [k_begin, k_end): k -> (outer = k / k_chunks, chunk = k % k_chunks)
 };
+
+// (x, y) -> packed bf16 pairs {lo16 = x, hi16 = y}: hi = bf16(v), lo = bf16(v - hi)
+__device__ __forceinline__ void split_pair_u32(float x, float y, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(y), "f"(x));
+    const float xr = x - __uint_as_float(hi << 16), yr = y - __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(yr), "f"(xr));
+}
 
 template <int MODE>
 __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int tile) {
@@ -406,6 +417,19 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                                 if (nb + i < p.Cout) o[i] = __ldg(src + i) > 0.f ? o[i] : 0.f;
                         }
                     }
+                    if (p.relu_src_hi && row_ok) {   // mask from the bf16 hi plane of the forward activation: hi > 0 <=> fp32 value > 0
+                        const uint4* src = reinterpret_cast<const uint4*>(p.relu_src_hi + grow * p.Cout + nb);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const uint4 m = __ldg(src + c);
+                            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                o[8 * c + 2 * k] = (short)(mw[k] & 0xffffu) > 0 ? o[8 * c + 2 * k] : 0.f;
+                                o[8 * c + 2 * k + 1] = ((int)mw[k] >> 16) > 0 ? o[8 * c + 2 * k + 1] : 0.f;
+                            }
+                        }
+                    }
                     if (p.add_src && row_ok) {
                         const float* src = p.add_src + grow * p.ldy + nb;
                         if (full) {
@@ -425,6 +449,21 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                         for (int i = 0; i < 32; ++i) o[i] = round_tf32(o[i]);
                     }
                 }
+                if (MODE == MODE_CONV && p.y_planes && row_ok) {
+                    // the consumer GEMMs read bf16 hi|lo operand planes: emit them here (64 contiguous bytes per row and plane)
+                    // instead of a later split pass over an fp32 copy
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) split_pair_u32(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
+                    uint4* dh = reinterpret_cast<uint4*>(p.y_planes + grow * p.Cout + nb);
+                    uint4* dl = reinterpret_cast<uint4*>(p.y_planes + p.y_plane_elems + grow * p.Cout + nb);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        dh[c] = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                        dl[c] = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                    }
+                }
+                if (p.skip_y) continue;
                 // each epilogue warp stages and stores its own 32 rows x 32 columns (4 KB, two buffers per warp): no
                 // cross-warp barrier.  Buffer (j & 1): the TMA store that last read it (2 chunks ago) must be done reading.
                 if (lane == 0) tma_store_wait_read<1>();
@@ -639,6 +678,13 @@ size_t conv_gemm_tc_workspace(const ConvGemmArgs& a) {
 int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     TcParams p;
     p.bias = a.bias; p.relu_src = a.relu_src; p.add_src = a.add_src;
+    p.relu_src_hi = (const __nv_bfloat16*)a.relu_src_hi;
+    p.y_planes = (__nv_bfloat16*)a.y_planes;
+    p.y_plane_elems = (long long)a.B * a.S * a.Cout;
+    p.skip_y = a.y == nullptr;
+    DX_REQUIRE(a.y || a.y_planes, "conv_gemm_tc: no output (y and y_planes are both NULL)");
+    DX_REQUIRE(!(a.y_planes || a.relu_src_hi) || (a.Cout % 32 == 0 && (((uintptr_t)a.y_planes | (uintptr_t)a.relu_src_hi) & 15) == 0),
+               "conv_gemm_tc: y_planes / relu_src_hi need Cout %% 32 == 0 and 16-byte alignment (Cout = %d)", a.Cout);
     p.B = a.B; p.S = a.S; p.Cin = a.Cin; p.Cout = a.Cout; p.KW = a.KW; p.ldy = a.ldy;
     p.tiles_m_per_b = ceil_div(a.S, TM);
     p.tiles_n = ceil_div(a.Cout, TN);
@@ -650,7 +696,8 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     p.trace = g_trace;
     CUtensorMap mxh, mxl, mwh, mwl, my;
     int rc;
-    if ((rc = make_map_3d(&my, a.y, 4, a.Cout, a.S, a.B, (uint64_t)a.ldy * 4, (uint64_t)a.S * a.ldy * 4, 32, 32, 1))) return rc;
+    // planes-only output: the store map is never used, but the encoder wants a valid base address
+    if ((rc = make_map_3d(&my, a.y ? (void*)a.y : a.y_planes, 4, a.Cout, a.S, a.B, (uint64_t)a.ldy * 4, (uint64_t)a.S * a.ldy * 4, 32, 32, 1))) return rc;
     if (g_prec == PREC_TF32) {
         p.k_chunks = ceil_div(a.Cin, Cfg<PREC_TF32>::TKB);
         if ((rc = make_map_3d(&mxh, a.x, 4, a.Cin, a.S, a.B, (uint64_t)a.ldx * 4, (uint64_t)a.S * a.ldx * 4, 32, TM, 1))) return rc;
@@ -775,6 +822,7 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
     }
     TcParams p;
     p.bias = nullptr; p.relu_src = nullptr; p.add_src = nullptr;
+    p.relu_src_hi = nullptr; p.y_planes = nullptr; p.y_plane_elems = 0; p.skip_y = 0;
     p.B = a.B; p.S = a.S; p.Cin = a.Cin; p.Cout = a.Cout; p.KW = a.KW; p.ldy = a.Cin;
     p.tiles_m_per_b = ceil_div(a.Cout, TM);
     p.tiles_n = ceil_div(a.Cin, TN);

@@ -16,7 +16,9 @@ struct ConvGemmArgs {
     const float* bias;      // [Cout] or nullptr
     const float* relu_src;  // [B, S, Cout] or nullptr
     const float* add_src;   // [B, S, ldy] or nullptr: added after the epilogue (residual / gradient accumulation)
-    float* y;               // [B, S, ldy]
+    float* y;               // [B, S, ldy]; nullable when y_planes is given (tensor-core path: no fp32 copy is written)
+    void* y_planes;         // optional (tensor-core path, Cout % 32 == 0): the output as bf16 hi|lo planes [2][B*S][Cout], written by the epilogue
+    const void* relu_src_hi;  // optional (tensor-core path, Cout % 32 == 0): ReLU mask source as the bf16 hi plane [B*S][Cout] of the forward activation
     int B, S, Cin, Cout, KW;
     int ldx, ldy;
     float alpha;
@@ -51,6 +53,7 @@ int conv_gemm_simt(const ConvGemmArgs& a, cudaStream_t st);
 int conv_wgrad_simt(const ConvWgradArgs& a, cudaStream_t st);
 size_t conv_wgrad_simt_workspace(const ConvWgradArgs& a, int* nsplit_out);
 int colsum(const float* dy, float* db, int R, int C, float alpha, cudaStream_t st);
+int colsum_planes(const void* planes, float* db, int R, int C, cudaStream_t st);
 int pack_conv_weights_batched(const void* descs_device, int n_desc, int total_blocks, int round, cudaStream_t st);
 int pack_conv_weight(const float* w, float* fwd, float* dgrad, void* fwd_planes, void* dgrad_planes, int Cout, int Cin, int KW,
                      int round, cudaStream_t st);

@@ -184,19 +184,33 @@ def make_planes(x, rows, C, ld=None, want_colsum=False):
 
 
 def conv_gemm(x, wp, bias, B, S, relu=False, relu_src=None, add_src=None, alpha=1.0, round_out=False, ldx=None, x_planes=None,
-              lens=None, halo=0):
+              lens=None, halo=0, relu_src_hi=None, emit_planes=False, want_y=True):
     """x [B,S,Cin] (row stride ldx) · packed weight [KW,Cout,Cin] -> [B,S,Cout].
-    lens/halo: padding skip — output rows s >= lens[b] + halo are declared irrelevant by the caller (written as zeros)."""
+    lens/halo: padding skip — output rows s >= lens[b] + halo are declared irrelevant by the caller (written as zeros).
+    Plane hand-over (`plane_handover()`): emit_planes -> returns (y, planes [2, B*S, Cout] bf16 hi|lo written by the epilogue);
+    want_y=False drops the fp32 copy; x may be None when x_planes is given; relu_src_hi = hi plane used as the ReLU mask."""
     kw, cout, cin = wp.shape
     dev = wp.w.device
-    y = torch.empty(B, S, cout, device=dev, dtype=torch.float32)
+    y = torch.empty(B, S, cout, device=dev, dtype=torch.float32) if want_y else None
+    yP = torch.empty(2, B * S, cout, device=dev, dtype=torch.bfloat16) if emit_planes else None
     rnd = 1 if (round_out and _backend[0] == cabi.DX_GEMM_TCGEN05_TF32) else 0
     nbytes = lib().dx_conv_gemm_workspace(B, S, cin, cout, kw, int(x_planes is not None), int(wp.planes is not None), -1)
     ws = torch.empty(nbytes + 256, device=dev, dtype=torch.uint8) if nbytes else None
-    _call('dx_conv_gemm', _p(x), _p(x_planes), _p(wp.w), _p(wp.planes), _p(bias), _p(relu_src), _p(add_src), _p(y), _p(ws),
-          ws.numel() if ws is not None else 0, _p(lens), int(halo), B, S, cin, cout, kw, cin if ldx is None else ldx, cout,
-          float(alpha), int(relu), rnd, -1, _st())
-    return y
+    _call('dx_conv_gemm', _p(x), _p(x_planes), _p(wp.w), _p(wp.planes), _p(bias), _p(relu_src), _p(relu_src_hi), _p(add_src), _p(y),
+          _p(yP), _p(ws), ws.numel() if ws is not None else 0, _p(lens), int(halo), B, S, cin, cout, kw, cin if ldx is None else ldx,
+          cout, float(alpha), int(relu), rnd, -1, _st())
+    return (y, yP) if emit_planes else y
+
+
+def plane_handover(cin, cout):
+    """True when a GEMM [.., cin] -> [.., cout] can hand its output to the next GEMM as bf16 hi|lo planes (no fp32 copy)."""
+    return _backend[0] == cabi.DX_GEMM_TCGEN05_BF16X3 and cin % 8 == 0 and cin >= 16 and cout % 32 == 0
+
+
+def colsum_planes(planes, rows, C):
+    db = torch.empty(C, device=planes.device, dtype=torch.float32)
+    _call('dx_colsum_planes', _p(planes), _p(db), rows, C, _st())
+    return db
 
 
 def linear_rows(x2d, wp, bias, **kw):
@@ -208,12 +222,13 @@ def linear_rows(x2d, wp, bias, **kw):
 def conv_wgrad(x, dy, B, S, cin, cout, kw, shape, want_bias=True, ldx=None, alpha=1.0, x_planes=None, dy_planes=None, dbias=None,
                lens=None, halo=0):
     """-> (dw in the parameter's own layout `shape`, dbias [Cout] or None).  `dbias`: already computed (fused into make_planes)."""
-    dw = torch.empty(tuple(shape), device=dy.device, dtype=torch.float32)
+    dev = (dy if dy is not None else dy_planes).device   # x / dy may be None when their planes are handed over
+    dw = torch.empty(tuple(shape), device=dev, dtype=torch.float32)
     if dbias is not None:
         want_bias = False
-    db = torch.empty(cout, device=dy.device, dtype=torch.float32) if want_bias else None
+    db = torch.empty(cout, device=dev, dtype=torch.float32) if want_bias else None
     nbytes = lib().dx_conv_wgrad_workspace(B, S, cin, cout, kw, int(x_planes is not None), int(dy_planes is not None), -1)
-    ws = torch.empty(max(nbytes, 16) // 4 + 4, device=dy.device, dtype=torch.float32)
+    ws = torch.empty(max(nbytes, 16) // 4 + 4, device=dev, dtype=torch.float32)
     _call('dx_conv_wgrad', _p(x), _p(x_planes), _p(dy), _p(dy_planes), _p(dw), _p(db), _p(ws), ws.numel() * 4, _p(lens), int(halo),
           B, S, cin, cout, kw, cin if ldx is None else ldx, float(alpha), -1, _st())
     return dw, (dbias if dbias is not None else db)
@@ -304,8 +319,14 @@ class ConvFFSubLayer(torch.autograd.Function):
         w2p, w2d = packed(w2)
         C = w1.shape[0]
         xP = make_planes(x, B * S, D)
-        h = conv_gemm(x, w1p, b1, B, S, relu=True, round_out=True, x_planes=xP, lens=lens, halo=(w2.shape[2] - 1) // 2)
-        hP = make_planes(h, B * S, C)
+        k2 = (w2.shape[2] - 1) // 2
+        if plane_handover(D, C) and xP is not None:
+            # the hidden activation (8x wider than the model) only ever feeds GEMMs: it exists as operand planes only,
+            # written by conv1's epilogue; its ReLU mask in backward is read from the hi plane
+            h, hP = conv_gemm(x, w1p, b1, B, S, relu=True, x_planes=xP, lens=lens, halo=k2, emit_planes=True, want_y=False)
+        else:
+            h = conv_gemm(x, w1p, b1, B, S, relu=True, round_out=True, x_planes=xP, lens=lens, halo=k2)
+            hP = make_planes(h, B * S, C)
         o = conv_gemm(h, w2p, b2, B, S, x_planes=hP, lens=lens)   # rows >= len are masked by the LayerNorm kernel
         seed = next_seed() if p_drop > 0 else 0
         if film is not None:
@@ -327,9 +348,13 @@ class ConvFFSubLayer(torch.autograd.Function):
                                              want_film=film is not None)
         doP, dob = make_planes(do, B * S, D, want_colsum=True)
         k2 = (w2_shape[2] - 1) // 2
-        dh = conv_gemm(do, w2d, None, B, S, relu_src=h, round_out=True, x_planes=doP, lens=lens, halo=k2)   # do == 0 beyond len: exact
+        if h is None:   # plane hand-over: dh exists as planes only; its column sums (conv1 bias gradient) are taken from them
+            dh, dhP = conv_gemm(do, w2d, None, B, S, relu_src_hi=hP, x_planes=doP, lens=lens, halo=k2, emit_planes=True, want_y=False)
+            dhb = colsum_planes(dhP, B * S, C)
+        else:
+            dh = conv_gemm(do, w2d, None, B, S, relu_src=h, round_out=True, x_planes=doP, lens=lens, halo=k2)   # do == 0 beyond len: exact
+            dhP, dhb = make_planes(dh, B * S, C, want_colsum=True)
         dw2, db2 = conv_wgrad(h, do, B, S, C, D, w2_shape[2], w2_shape, x_planes=hP, dy_planes=doP, dbias=dob, lens=lens)
-        dhP, dhb = make_planes(dh, B * S, C, want_colsum=True)
         dx = conv_gemm(dh, w1d, None, B, S, add_src=dv, x_planes=dhP, lens=lens)   # rows >= len are masked by the producer's LN bwd
         dw1, db1 = conv_wgrad(x, dh, B, S, D, C, w1_shape[2], w1_shape, x_planes=xP, dy_planes=dhP, dbias=dhb, lens=lens, halo=k2)
         return dx, None, dw1, db1, dw2, db2, dln_w, dln_b, dfilm, None
