@@ -449,21 +449,46 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                         for (int i = 0; i < 32; ++i) o[i] = round_tf32(o[i]);
                     }
                 }
-                if (MODE == MODE_CONV && p.y_planes && row_ok) {
-                    // the consumer GEMMs read bf16 hi|lo operand planes: emit them here (64 contiguous bytes per row and plane)
-                    // instead of a later split pass over an fp32 copy
+                if (MODE == MODE_CONV && p.y_planes) {
+                    // the consumer GEMMs read bf16 hi|lo operand planes: emit them here instead of a later split pass over an
+                    // fp32 copy (32 columns = 64 bytes per row and plane)
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) split_pair_u32(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
-                    uint4* dh = reinterpret_cast<uint4*>(p.y_planes + grow * p.Cout + nb);
-                    uint4* dl = reinterpret_cast<uint4*>(p.y_planes + p.y_plane_elems + grow * p.Cout + nb);
+                    if (p.skip_y) {
+                        // planes only: stage hi | lo tiles (2 KB each) in this warp's buffer and TMA-store both (map_y is the
+                        // bf16 planes map; rows >= S are clipped by the store)
+                        if (lane == 0) tma_store_wait_read<1>();
+                        __syncwarp();
+                        const uint32_t wbuf = sOut + (quad * 2 + (j & 1)) * (32 * 128);
+                        const uint32_t rbuf = wbuf + lane * 64;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        dh[c] = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-                        dl[c] = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                        for (int c = 0; c < 4; ++c) {   // SWIZZLE_64B: 16-byte chunk c of row r lands at chunk c ^ ((r >> 1) & 3)
+                            const uint32_t off = (uint32_t)((c ^ ((lane >> 1) & 3)) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbuf + off), "r"(hi[4 * c]), "r"(hi[4 * c + 1]),
+                                         "r"(hi[4 * c + 2]), "r"(hi[4 * c + 3]) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbuf + 2048 + off), "r"(lo[4 * c]),
+                                         "r"(lo[4 * c + 1]), "r"(lo[4 * c + 2]), "r"(lo[4 * c + 3]) : "memory");
+                        }
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0 && !(p.debug & 8)) {
+                            tma_store_3d(&map_y, wbuf, nb, t.o1 + quad * 32, t.o2);
+                            tma_store_3d(&map_y, wbuf + 2048, nb, t.o1 + quad * 32, p.B + t.o2);
+                            tma_store_commit();
+                        }
+                        continue;
+                    }
+                    if (row_ok) {   // fp32 output AND planes requested: direct (slower) global stores for the planes
+                        uint4* dh = reinterpret_cast<uint4*>(p.y_planes + grow * p.Cout + nb);
+                        uint4* dl = reinterpret_cast<uint4*>(p.y_planes + p.y_plane_elems + grow * p.Cout + nb);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            dh[c] = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                            dl[c] = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                        }
                     }
                 }
-                if (p.skip_y) continue;
                 // each epilogue warp stages and stores its own 32 rows x 32 columns (4 KB, two buffers per warp): no
                 // cross-warp barrier.  Buffer (j & 1): the TMA store that last read it (2 chunks ago) must be done reading.
                 if (lane == 0) tma_store_wait_read<1>();
@@ -584,9 +609,9 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 3-D tensor (d0 contiguous), box (b0, b1, b2), SWIZZLE_128B, zero OOB fill.  esz = 4 (fp32) or 2 (bf16).
+// 3-D tensor (d0 contiguous), box (b0, b1, b2), SWIZZLE_128B (or 64B), zero OOB fill.  esz = 4 (fp32) or 2 (bf16).
 int make_map_3d(CUtensorMap* map, const void* ptr, int esz, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
-                uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
+                uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, bool swizzle64 = false) {
     EncodeTiledFn enc = get_encode();
     DX_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[3] = {d0, d1, d2};
@@ -595,7 +620,8 @@ int make_map_3d(CUtensorMap* map, const void* ptr, int esz, uint64_t d0, uint64_
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                      const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) esz=%d dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u,%u)",
                (int)r, esz, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
                (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes, b0, b1, b2);
@@ -696,8 +722,14 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     p.trace = g_trace;
     CUtensorMap mxh, mxl, mwh, mwl, my;
     int rc;
-    // planes-only output: the store map is never used, but the encoder wants a valid base address
-    if ((rc = make_map_3d(&my, a.y ? (void*)a.y : a.y_planes, 4, a.Cout, a.S, a.B, (uint64_t)a.ldy * 4, (uint64_t)a.S * a.ldy * 4, 32, 32, 1))) return rc;
+    if (a.y) {
+        if ((rc = make_map_3d(&my, a.y, 4, a.Cout, a.S, a.B, (uint64_t)a.ldy * 4, (uint64_t)a.S * a.ldy * 4, 32, 32, 1))) return rc;
+    } else {
+        // planes-only output: ONE bf16 map over [2][B*S][Cout] seen as (Cout, S, 2B): the lo plane is utterance index B + b;
+        // 32 x 32 boxes of 64-byte rows, SWIZZLE_64B (the epilogue writes the staging tile with the matching xor)
+        if ((rc = make_map_3d(&my, a.y_planes, 2, a.Cout, a.S, 2 * (uint64_t)a.B, (uint64_t)a.Cout * 2, (uint64_t)a.S * a.Cout * 2, 32, 32, 1, true)))
+            return rc;
+    }
     if (g_prec == PREC_TF32) {
         p.k_chunks = ceil_div(a.Cin, Cfg<PREC_TF32>::TKB);
         if ((rc = make_map_3d(&mxh, a.x, 4, a.Cin, a.S, a.B, (uint64_t)a.ldx * 4, (uint64_t)a.S * a.ldx * 4, 32, TM, 1))) return rc;
