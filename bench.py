@@ -142,7 +142,8 @@ def run_reference_arm(args):
 
 def time_dominant_kernel(dev, iters=20):
     """Roofline of the dominant kernel: the FFT-block conv1 GEMM (32x1000 rows, 128 -> 1024 channels, k=3) through the
-    C-ABI, CUDA events around each launch on the launching stream, L2 flushed between launches."""
+    C-ABI exactly as the training step issues it (operand planes in, bias + ReLU, hidden activation handed over as bf16
+    hi|lo planes), CUDA events around each launch on the launching stream, L2 flushed between launches."""
     from daft_exprt_b200 import ops
     B, S, Cin, Cout, KW = B_PER_GPU, T_MAX, 128, 1024, 3
     x = torch.randn(B, S, Cin, device=dev)
@@ -150,17 +151,19 @@ def time_dominant_kernel(dev, iters=20):
     bias = torch.randn(Cout, device=dev)
     wp, _ = ops.packed(w)
     flush = torch.empty(512 * 1024 * 1024 // 4, device=dev)
+    xP = ops.make_planes(x, B * S, Cin)
+    run = lambda: ops.conv_gemm(None, wp, bias, B, S, relu=True, x_planes=xP, emit_planes=True, want_y=False)
     for _ in range(3):
-        ops.conv_gemm(x, wp, bias, B, S, relu=True)
+        run()
     torch.cuda.synchronize()
     # enqueue everything first (the 512 MB flush kernels give the host time to run ahead), then read the events:
-    # e0 -> e1 brackets only this library's kernels of one launch (operand split + tcgen05 GEMM)
+    # e0 -> e1 brackets exactly one launch of gemm_tc_kernel
     evs = []
     for _ in range(iters):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.conv_gemm(x, wp, bias, B, S, relu=True)
+        run()
         e1.record()
         evs.append((e0, e1))
     torch.cuda.synchronize()
@@ -179,6 +182,7 @@ def main():
     ap.add_argument('--backend', default='bf16x3', choices=['bf16x3', 'tf32', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--eval', action='store_true', help='eval mode (dropout off)')
+    ap.add_argument('--profile-step', action='store_true', help='bracket ONE extra step with cudaProfilerStart/Stop (for ncu --profile-from-start off)')
     ap.add_argument('--no-graph', action='store_true', help='issue the ~640 launches of a step eagerly instead of replaying the captured CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -273,6 +277,12 @@ def main():
         sampler.start()
     ms_step, launches = timed(step_resident, args.steps, max(args.warmup, 3))
     ms_e2e, _ = timed(step_e2e, max(2, args.steps // 2), 1)
+    if args.profile_step:   # not timed: one step of the same workload for the ncu launch list
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step_resident(10 ** 6)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=3)

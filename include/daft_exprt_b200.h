@@ -74,6 +74,12 @@ int dx_conv_gemm(const float* x, const void* x_planes, const float* w_packed, co
                  size_t workspace_bytes, const int64_t* lens, int halo, int B, int S, int Cin, int Cout, int KW, int ldx, int ldy,
                  float alpha, int relu, int round_tf32, int backend, void* stream);
 size_t dx_conv_gemm_workspace(int B, int S, int Cin, int Cout, int KW, int have_x_planes, int have_w_planes, int backend);
+/* Deferred split-K reduction (tensor-core backends).  dx_wgrad_defer(1): every following dx_conv_wgrad only RECORDS the
+ * reduction of its split-K partials into dw (the caller must then keep each call's workspace alive and must not read dw);
+ * dx_wgrad_flush performs all recorded reductions with ONE launch (also issued automatically when 72 are pending).
+ * dx_wgrad_defer(0) restores reduce-per-call (the default); both drop anything still pending. */
+int dx_wgrad_defer(int on);
+int dx_wgrad_flush(void* stream);
 /* colsum_out (nullable, [C]): column sums of x accumulated in the same pass (= the bias gradient when x is a dy) */
 int dx_split_planes(const float* x, int ld, void* planes, float* colsum_out, int rows, int C, void* stream);
 int dx_split_weight_planes(const float* w_packed, void* planes, size_t n, void* stream);

@@ -154,6 +154,8 @@ int dx_conv_wgrad(const float* x, const void* x_planes, const float* dy, const v
 }
 
 int dx_colsum(const float* dy, float* db, int rows, int C, float alpha, void* stream) { return colsum(dy, db, rows, C, alpha, ST(stream)); }
+int dx_wgrad_defer(int on) { wgrad_reduce_defer(on != 0); return DX_OK; }
+int dx_wgrad_flush(void* stream) { return wgrad_reduce_flush(ST(stream)); }
 int dx_colsum_planes(const void* planes, float* db, int rows, int C, void* stream) { return colsum_planes(planes, db, rows, C, ST(stream)); }
 int dx_relu_bwd(const float* dy, const float* y, float* dx_, size_t n, void* stream) { return relu_bwd(dy, y, dx_, n, ST(stream)); }
 int dx_scale_copy(const float* x, float* y, float alpha, size_t n, void* stream) { return scale_copy(x, y, alpha, n, ST(stream)); }

@@ -819,6 +819,63 @@ __global__ void wgrad_reduce_tc_kernel(const float* __restrict__ part, float* __
     }
 }
 
+// ---- deferred, batched split-K reduction ------------------------------------------------------------------------------
+// A backward pass issues ~58 weight-gradient GEMMs, each followed by a tiny (latency-bound, ~9 us) reduction of its split-K
+// partials into the parameter layout.  With deferral on, the reductions are only RECORDED (descriptor = kernel-parameter data,
+// so a CUDA-graph capture needs no side memory) and one launch performs all of them before the gradients are consumed.
+struct ReduceDesc {
+    const float* part;
+    float* dw;
+    int nsplit, KW, Cout, Cin;
+    float alpha;
+    int block0;
+};
+constexpr int kMaxReduce = 72;          // 72 * 40 B < the 4 KB kernel-parameter space
+constexpr int kReduceChunk = 1024;      // elements per block
+struct ReduceBatch {
+    ReduceDesc d[kMaxReduce];
+    int n;
+};
+bool g_defer_reduce = false;
+ReduceBatch g_reduce = {};
+int g_reduce_blocks = 0;
+
+__global__ void __launch_bounds__(256) wgrad_reduce_batched_kernel(const __grid_constant__ ReduceBatch b) {
+    int lo = 0, hi = b.n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (b.d[mid].block0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const ReduceDesc& d = b.d[lo];
+    const size_t per = (size_t)d.KW * d.Cout * d.Cin;
+    const size_t i0 = (size_t)((int)blockIdx.x - d.block0) * kReduceChunk;
+#pragma unroll
+    for (int j = 0; j < kReduceChunk / 256; ++j) {
+        const size_t i = i0 + threadIdx.x + 256 * j;
+        if (i >= per) break;
+        float s = 0.f;
+        for (int k = 0; k < d.nsplit; ++k) s += d.part[(size_t)k * per + i];
+        const int ci = (int)(i % d.Cin);
+        const size_t q = i / d.Cin;
+        const int co = (int)(q % d.Cout), tap = (int)(q / d.Cout);
+        d.dw[((size_t)co * d.Cin + ci) * d.KW + tap] = d.alpha * s;
+    }
+}
+
+int wgrad_reduce_flush(cudaStream_t st) {
+    if (g_reduce.n == 0) return DX_OK;
+    wgrad_reduce_batched_kernel<<<g_reduce_blocks, 256, 0, st>>>(g_reduce);
+    g_reduce.n = 0;
+    g_reduce_blocks = 0;
+    return check_launch("wgrad_reduce_batched");
+}
+
+void wgrad_reduce_defer(bool on) {
+    g_defer_reduce = on;
+    g_reduce.n = 0;   // anything still pending belongs to an aborted pass
+    g_reduce_blocks = 0;
+}
+
 int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
     const size_t need = conv_wgrad_tc_workspace(a);
     DX_REQUIRE(a.workspace && a.workspace_bytes >= need, "conv_wgrad_tc: workspace %zu < %zu bytes", a.workspace_bytes, need);
@@ -876,8 +933,16 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
         return rc;
     if ((rc = launch<PREC_BF16X3, MODE_WGRAD>(mah, mal, mbh, mbl, my, p, st))) return rc;
     const size_t per = (size_t)a.KW * a.Cout * a.Cin;
-    wgrad_reduce_tc_kernel<<<grid_1d(per, 256, 148 * 8), 256, 0, st>>>(part, a.dw, nsplit, a.KW, a.Cout, a.Cin, a.alpha);
-    if ((rc = check_launch("wgrad_reduce_tc"))) return rc;
+    if (g_defer_reduce) {   // the caller keeps the workspace alive until dx_wgrad_flush
+        if (g_reduce.n == kMaxReduce && (rc = wgrad_reduce_flush(st))) return rc;
+        ReduceDesc& d = g_reduce.d[g_reduce.n++];
+        d.part = part; d.dw = a.dw; d.nsplit = nsplit; d.KW = a.KW; d.Cout = a.Cout; d.Cin = a.Cin; d.alpha = a.alpha;
+        d.block0 = g_reduce_blocks;
+        g_reduce_blocks += (int)((per + kReduceChunk - 1) / kReduceChunk);
+    } else {
+        wgrad_reduce_tc_kernel<<<grid_1d(per, 256, 148 * 8), 256, 0, st>>>(part, a.dw, nsplit, a.KW, a.Cout, a.Cin, a.alpha);
+        if ((rc = check_launch("wgrad_reduce_tc"))) return rc;
+    }
     if (a.dbias) return colsum(a.dy, a.dbias, a.B * a.S, a.Cout, a.alpha, st);
     return DX_OK;
 }

@@ -53,6 +53,8 @@ int conv_gemm_simt(const ConvGemmArgs& a, cudaStream_t st);
 int conv_wgrad_simt(const ConvWgradArgs& a, cudaStream_t st);
 size_t conv_wgrad_simt_workspace(const ConvWgradArgs& a, int* nsplit_out);
 int colsum(const float* dy, float* db, int R, int C, float alpha, cudaStream_t st);
+int wgrad_reduce_flush(cudaStream_t st);
+void wgrad_reduce_defer(bool on);
 int colsum_planes(const void* planes, float* db, int R, int C, cudaStream_t st);
 int pack_conv_weights_batched(const void* descs_device, int n_desc, int total_blocks, int round, cudaStream_t st);
 int pack_conv_weight(const float* w, float* fwd, float* dgrad, void* fwd_planes, void* dgrad_planes, int Cout, int Cin, int KW,

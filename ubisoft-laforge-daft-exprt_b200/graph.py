@@ -76,6 +76,7 @@ class GraphedTrainStep:
         self.seed = torch.initial_seed() if seed is None else seed
         self.cache = OrderedDict()
         self.world = sync.world_size()
+        assert sync.mode == 'gather', 'GraphedTrainStep needs FlatGradSync(mode="gather") (deferred weight-gradient reduction)'
         self.launches_replayed = 0   # kernels of libdaftexprt_b200.so executed through graph replays
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -90,8 +91,13 @@ class GraphedTrainStep:
 
     def _body_backward(self, inputs, targets):
         self.opt.zero_grad()
-        out = self.criterion.forward_device(self.model(inputs), targets, 0)   # w_adv comes from the device block
-        out[7].backward()
+        ops.set_wgrad_deferral(True)   # gather mode: no gradient is read before sync.gather(), so reduce them all at once
+        try:
+            out = self.criterion.forward_device(self.model(inputs), targets, 0)   # w_adv comes from the device block
+            out[7].backward()
+            ops.flush_wgrad()
+        finally:
+            ops.set_wgrad_deferral(False)
         self.sync.gather()
         return out
 

@@ -202,6 +202,24 @@ def conv_gemm(x, wp, bias, B, S, relu=False, relu_src=None, add_src=None, alpha=
     return (y, yP) if emit_planes else y
 
 
+_wgrad_deferred = [False]
+_wgrad_keepalive = []
+
+
+def set_wgrad_deferral(on):
+    """Opt-in (gather-mode gradient buckets only: nobody may read a weight gradient before `flush_wgrad()`): the ~58 split-K
+    reductions of a backward pass are recorded and executed by ONE launch."""
+    _call('dx_wgrad_defer', int(bool(on)))
+    _wgrad_deferred[0] = bool(on)
+    _wgrad_keepalive.clear()
+
+
+def flush_wgrad():
+    if _wgrad_deferred[0]:
+        _call('dx_wgrad_flush', _st())
+        _wgrad_keepalive.clear()
+
+
 def plane_handover(cin, cout):
     """True when a GEMM [.., cin] -> [.., cout] can hand its output to the next GEMM as bf16 hi|lo planes (no fp32 copy)."""
     return _backend[0] == cabi.DX_GEMM_TCGEN05_BF16X3 and cin % 8 == 0 and cin >= 16 and cout % 32 == 0
@@ -231,6 +249,8 @@ def conv_wgrad(x, dy, B, S, cin, cout, kw, shape, want_bias=True, ldx=None, alph
     ws = torch.empty(max(nbytes, 16) // 4 + 4, device=dev, dtype=torch.float32)
     _call('dx_conv_wgrad', _p(x), _p(x_planes), _p(dy), _p(dy_planes), _p(dw), _p(db), _p(ws), ws.numel() * 4, _p(lens), int(halo),
           B, S, cin, cout, kw, cin if ldx is None else ldx, float(alpha), -1, _st())
+    if _wgrad_deferred[0]:
+        _wgrad_keepalive.append(ws)   # the split-K partials are reduced by flush_wgrad()
     return dw, (dbias if dbias is not None else db)
 
 
