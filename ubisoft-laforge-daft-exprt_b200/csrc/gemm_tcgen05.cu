@@ -16,11 +16,11 @@
 //   TF32    fp32 tiles are consumed directly by `tcgen05.mma kind::tf32` (10-bit mantissa): one pass at half the bf16 rate,
 //           ~1e-3 per GEMM.  Forward/dgrad only.
 //
-// CTA = 192 threads, persistent over 128 x 128 output tiles, one CTA per SM:
+// CTA = 320 threads, persistent over 128 x 128 output tiles, one CTA per SM:
 //   warp 0    TMA producer: ring of K-stages (128-byte rows, SWIZZLE_128B), mbarrier complete_tx
 //   warp 1    MMA issuer (one thread): UMMA M128 N128, tcgen05.commit frees the stage; two TMEM accumulators (2 x 128
 //             columns) so the epilogue of tile i overlaps the MMAs of tile i+1
-//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns) -> registers -> bias / ReLU / ReLU-mask / residual add ->
+//   warps 2-9 epilogue (two per SM sub-partition; 32 lanes x 64 columns each): tcgen05.ld -> registers -> bias / ReLU / ReLU-mask / residual add ->
 //             128B-swizzled smem staging -> TMA store (clips partial tiles)
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -34,18 +34,30 @@ namespace dx {
 namespace {
 
 enum { PREC_TF32 = 0, PREC_BF16X3 = 1 };
-enum { MODE_CONV = 0, MODE_WGRAD = 1 };
+enum { MODE_CONV = 0, MODE_WGRAD = 1, MODE_HALO = 2 };
+// MODE_HALO = MODE_CONV for KW = 3 (BF16X3 only): the three taps are three row-shifted views of ONE activation tile, so the
+// tile is fetched once per channel chunk with its halo (rows s0-1 .. s0+128) and each tap's MMAs read it through a UMMA
+// descriptor whose start address is advanced by tap rows.  A traffic drops 3x, total operand traffic by a third.
 
 constexpr int TM = 128, TN = 128;
 constexpr int TILE_BYTES = 128 * 128;                 // one operand tile: 128 rows x 128 bytes
 constexpr int OUT_BYTES = TM * 32 * 4;                // one 128 x 32 fp32 staging chunk
 constexpr int TMEM_COLS = 256;
+constexpr int NUM_EPI_WARPS = 8;                      // two per SM sub-partition
+constexpr int NTHREADS = 64 + 32 * NUM_EPI_WARPS;     // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. = epilogue
 
 template <int PREC> struct Cfg;
 template <> struct Cfg<PREC_TF32>   { static constexpr int TKB = 32, PLANES = 1, NSTAGE = 5; };
 template <> struct Cfg<PREC_BF16X3> { static constexpr int TKB = 64, PLANES = 2, NSTAGE = 3; };
 template <int PREC> constexpr int stage_bytes() { return 2 * Cfg<PREC>::PLANES * TILE_BYTES; }
-template <int PREC> constexpr int smem_bytes() { return Cfg<PREC>::NSTAGE * stage_bytes<PREC>() + 2 * OUT_BYTES + 256 + 1024; }
+constexpr int HALO_ROWS = TM + 2;                      // KW = 3
+constexpr int A_HALO_BYTES = 17 * 1024;                // 130 rows x 128 B rounded up to the 1024-byte swizzle repeat
+constexpr int HALO_A_STAGES = 2, HALO_B_STAGES = 3;
+constexpr int HALO_A_STAGE_BYTES = 2 * A_HALO_BYTES, HALO_B_STAGE_BYTES = 2 * TILE_BYTES;
+template <int PREC, int MODE> constexpr int smem_bytes() {
+    return (MODE == MODE_HALO ? HALO_A_STAGES * HALO_A_STAGE_BYTES + HALO_B_STAGES * HALO_B_STAGE_BYTES
+                              : Cfg<PREC>::NSTAGE * stage_bytes<PREC>()) + 2 * OUT_BYTES + 256 + 1024;
+}
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -91,6 +103,12 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// same, start address `rows` rows (128 B each) past a 1024-byte aligned tile.  Measured on B200: the 128B swizzle is applied
+// to the absolute shared-memory address bits (exactly like the TMA write that filled the tile), so a row-shifted start
+// address needs NO matrix base offset (bits 49-51 stay 0); setting base offset = rows gives wrong products.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128_rows(uint32_t tile, uint32_t rows) {
+    return umma_desc_k_sw128(tile + rows * 128u);
+}
 // MN-major operand tile (K = rows): 64-element (128-byte) MN chunks, each chunk = [K rows][128 B] with SWIZZLE_128B;
 // LBO = distance between MN chunks (8192 B: one 64-row TMA box), SBO = distance between 8-row K groups (1024 B).
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
@@ -119,7 +137,7 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
@@ -129,7 +147,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
           "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// completes the tcgen05.ld's above; the 32 registers are tied to the wait so no consumer can be scheduled ahead of it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                   "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                   "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :: "memory");
 }
 
 struct TcParams {
@@ -148,7 +174,8 @@ struct TcParams {
     float alpha;
     int relu, round_tf32;
     long long* trace;   // optional [4][256] clock64 trace of block 0 (DX_TC_TRACE), else nullptr
-    int debug;   // bring-up bisection mask (DX_TC_DEBUG): 1 no MMA, 2 no TMA loads, 4 no TMEM loads, 8 no TMA store, 16 no TMEM alloc
+    int debug;   // bring-up bisection mask (DX_TC_DEBUG): 1 no MMA, 2 no TMA loads, 4 no TMEM loads, 8 no TMA store, 16 no TMEM alloc,
+                 // 64 no proxy fence before the TMA store, 256 no bias loads (timing probes: results are wrong under any bit)
 };
 
 struct TileCoord {
@@ -168,7 +195,7 @@ __device__ __forceinline__ void split_pair_u32(float x, float y, uint32_t& hi, u
 template <int MODE>
 __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int tile) {
     TileCoord t;
-    if constexpr (MODE == MODE_CONV) {
+    if constexpr (MODE != MODE_WGRAD) {
         const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
         const int b = tm / p.tiles_m_per_b, s0 = (tm % p.tiles_m_per_b) * TM, n0 = tn * TN;
         t.a0 = 0; t.a1 = s0; t.a2 = b;
@@ -200,7 +227,7 @@ __device__ __forceinline__ int live_rows(const TcParams& p, int b) { return min(
 
 template <int MODE>
 __device__ __forceinline__ bool k_dead(const TcParams& p, int k) {   // WGRAD only
-    if (MODE == MODE_CONV || p.lens == nullptr) return false;
+    if (MODE != MODE_WGRAD || p.lens == nullptr) return false;
     const int b = k / p.k_chunks, kc = k - b * p.k_chunks;
     return kc * 64 >= live_rows(p, b);
 }
@@ -208,7 +235,7 @@ __device__ __forceinline__ bool k_dead(const TcParams& p, int k) {   // WGRAD on
 template <int MODE>
 __device__ __forceinline__ bool tile_dead(const TcParams& p, const TileCoord& t) {
     if (p.lens == nullptr) return false;
-    if (MODE == MODE_CONV) return t.a1 >= live_rows(p, t.a2);
+    if (MODE != MODE_WGRAD) return t.a1 >= live_rows(p, t.a2);
     for (int b = t.k_begin / p.k_chunks; b <= (t.k_end - 1) / p.k_chunks; ++b) {
         const int kc_lo = max(t.k_begin - b * p.k_chunks, 0);
         if (kc_lo * 64 < live_rows(p, b)) return false;
@@ -217,19 +244,23 @@ __device__ __forceinline__ bool tile_dead(const TcParams& p, const TileCoord& t)
 }
 
 template <int PREC, int MODE>
-__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                                                          const __grid_constant__ CUtensorMap map_a_lo,
                                                          const __grid_constant__ CUtensorMap map_b_hi,
                                                          const __grid_constant__ CUtensorMap map_b_lo,
                                                          const __grid_constant__ CUtensorMap map_y, TcParams p) {
     constexpr int NSTAGE = Cfg<PREC>::NSTAGE, PLANES = Cfg<PREC>::PLANES, TKB = Cfg<PREC>::TKB;
     constexpr int STAGE_BYTES = stage_bytes<PREC>();
+    static_assert(MODE != MODE_HALO || PREC == PREC_BF16X3, "MODE_HALO is a BF16X3 variant");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
-    const uint32_t sOut = base + NSTAGE * STAGE_BYTES;
+    const uint32_t baseB = base + HALO_A_STAGES * HALO_A_STAGE_BYTES;   // MODE_HALO: A ring, then B ring
+    const uint32_t sOut = MODE == MODE_HALO ? baseB + HALO_B_STAGES * HALO_B_STAGE_BYTES : base + NSTAGE * STAGE_BYTES;
     const uint32_t bars = sOut + 2 * OUT_BYTES;
     const uint32_t full0 = bars, empty0 = bars + 8 * NSTAGE, tfull0 = bars + 16 * NSTAGE, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
+    const uint32_t afull0 = bars + 96, aempty0 = bars + 112;   // MODE_HALO: full0/empty0 are the B ring (NSTAGE = HALO_B_STAGES = 3)
+    static_assert(MODE != MODE_HALO || Cfg<PREC>::NSTAGE == HALO_B_STAGES, "B ring shares the full/empty barrier slots");
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -237,7 +268,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+        for (int i = 0; i < HALO_A_STAGES; ++i) { mbar_init(afull0 + 8 * i, 1); mbar_init(aempty0 + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -253,7 +285,85 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp == 0) {
+    if (MODE == MODE_HALO && warp == 0) {
+        if (lane == 0) {
+            int bs = 0, bph = 0, as = 0, aph = 0, gk = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const TileCoord t = tile_coord<MODE>(p, tile);
+                if (tile_dead<MODE>(p, t)) continue;
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    mbar_wait(aempty0 + 8 * as, aph ^ 1);
+                    const uint32_t sa = base + as * HALO_A_STAGE_BYTES, abar = afull0 + 8 * as;
+                    if (p.debug & 2) {
+                        mbar_arrive(abar);
+                    } else {   // rows s0-1 .. s0+128 of this channel chunk, both planes (out-of-range rows arrive as zeros)
+                        mbar_expect_tx(abar, 2 * HALO_ROWS * 128);
+                        tma_load_3d(sa, &map_a_hi, abar, kc * TKB, t.a1 - 1, t.a2);
+                        tma_load_3d(sa + A_HALO_BYTES, &map_a_lo, abar, kc * TKB, t.a1 - 1, t.a2);
+                    }
+                    if (++as == HALO_A_STAGES) { as = 0; aph ^= 1; }
+                    for (int tap = 0; tap < 3; ++tap) {
+                        mbar_wait(empty0 + 8 * bs, bph ^ 1);
+                        const uint32_t sb = baseB + bs * HALO_B_STAGE_BYTES, bbar = full0 + 8 * bs;
+                        if (p.debug & 2) {
+                            mbar_arrive(bbar);
+                        } else {
+                            mbar_expect_tx(bbar, HALO_B_STAGE_BYTES);
+                            tma_load_3d(sb, &map_b_hi, bbar, kc * TKB, t.b1, tap);
+                            tma_load_3d(sb + TILE_BYTES, &map_b_lo, bbar, kc * TKB, t.b1, tap);
+                        }
+                        if (p.trace && blockIdx.x == 0 && gk < 256) p.trace[0 * 256 + gk] = clock64();
+                        ++gk;
+                        if (++bs == HALO_B_STAGES) { bs = 0; bph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (MODE == MODE_HALO && warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(1, TM, TN, 0);
+            int bs = 0, bph = 0, as = 0, aph = 0, it = 0, gk = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const TileCoord t = tile_coord<MODE>(p, tile);
+                if (tile_dead<MODE>(p, t)) continue;
+                const int acc = it & 1, acc_phase = (it >> 1) & 1;
+                ++it;
+                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * TN;
+                uint32_t started = 0;
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    mbar_wait(afull0 + 8 * as, aph);
+                    const uint32_t sa = base + as * HALO_A_STAGE_BYTES;
+                    for (uint32_t tap = 0; tap < 3; ++tap) {
+                        mbar_wait(full0 + 8 * bs, bph);
+                        if (p.trace && blockIdx.x == 0 && gk < 256) p.trace[1 * 256 + gk] = clock64();
+                        ++gk;
+                        tc_fence_after();
+                        const uint32_t sb = baseB + bs * HALO_B_STAGE_BYTES;
+                        const uint64_t a_hi = umma_desc_k_sw128_rows(sa, tap);
+                        const uint64_t a_lo = umma_desc_k_sw128_rows(sa + A_HALO_BYTES, tap);
+                        const uint64_t b_hi = umma_desc_k_sw128(sb), b_lo = b_hi + (TILE_BYTES >> 4);
+#pragma unroll
+                        for (int kk = 0; kk < ((p.debug & 1) ? 0 : 4); ++kk) {
+                            umma<PREC>(tmem_d, a_hi + 2 * kk, b_hi + 2 * kk, idesc, started | (uint32_t)kk);
+                            umma<PREC>(tmem_d, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1u);
+                            umma<PREC>(tmem_d, a_hi + 2 * kk, b_lo + 2 * kk, idesc, 1u);
+                        }
+                        started = 1;
+                        if (p.debug & 1) mbar_arrive(empty0 + 8 * bs);
+                        else umma_commit(empty0 + 8 * bs);
+                        if (++bs == HALO_B_STAGES) { bs = 0; bph ^= 1; }
+                    }
+                    if (p.debug & 1) mbar_arrive(aempty0 + 8 * as);
+                    else umma_commit(aempty0 + 8 * as);          // the halo tile is free once all three taps have retired
+                    if (++as == HALO_A_STAGES) { as = 0; aph ^= 1; }
+                }
+                if (p.debug & 1) mbar_arrive(tfull0 + 8 * acc);
+                else umma_commit(tfull0 + 8 * acc);
+            }
+        }
+    } else if (warp == 0) {
         if (lane == 0) {
             int stage = 0, phase = 0, gk = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -269,14 +379,14 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                         if (p.debug & 2) { mbar_arrive(bar); if (++stage == NSTAGE) { stage = 0; phase ^= 1; } continue; }
                         mbar_expect_tx(bar, STAGE_BYTES);
                         int a0, a1, a2, b0, b1, b2;
-                        if constexpr (MODE == MODE_CONV) {      // o = tap
+                        if constexpr (MODE != MODE_WGRAD) {      // o = tap
                             a0 = kc * TKB; a1 = t.a1 + o - pad; a2 = t.a2;
                             b0 = kc * TKB; b1 = t.b1; b2 = o;
                         } else {                                // o = utterance; K = 64 rows of s; operands are (c, s, b) boxes
                             a0 = t.a2; a1 = kc * TKB; a2 = o;
                             b0 = t.b2; b1 = kc * TKB + t.tap - pad; b2 = o;
                         }
-                        if constexpr (MODE == MODE_CONV) {
+                        if constexpr (MODE != MODE_WGRAD) {
                             tma_load_3d(sa, &map_a_hi, bar, a0, a1, a2);
                             tma_load_3d(sb, &map_b_hi, bar, b0, b1, b2);
                             if constexpr (PLANES == 2) {
@@ -343,49 +453,57 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
             }
         }
     } else {
-        // epilogue: warp w may only touch TMEM lanes [32*(w%4), +32); thread <-> output row
+        // epilogue: NUM_EPI_WARPS = 8 warps, two per SM sub-partition so one warp's TMEM / shared-memory / TMA latencies are
+        // covered by the other.  Warp w may only touch TMEM lanes [32*(w%4), +32) (thread <-> output row); the two warps of
+        // a lane quarter split the 128 accumulator columns (64 each = two 32-column chunks, both loaded up front so the
+        // accumulator goes back to the MMA warp before any arithmetic starts).
         const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = quad * 32 + lane;
-        const int et = threadIdx.x - 64;          // 0..127
+        const uint32_t wbuf = sOut + (uint32_t)(warp - 2) * 4096u;   // one 4 KB staging buffer per epilogue warp
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const TileCoord t = tile_coord<MODE>(p, tile);
             const bool dead = tile_dead<MODE>(p, t);             // dead tiles are stored as zeros, no accumulator involved
             const int acc = it & 1, acc_phase = (it >> 1) & 1;
+            uint32_t v[64];
             if (!dead) {
                 mbar_wait(tfull0 + 8 * acc, acc_phase);
-                if (p.trace && blockIdx.x == 0 && et == 0 && it < 256) p.trace[2 * 256 + it] = clock64();
+                if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && it < 256) p.trace[2 * 256 + it] = clock64();
                 tc_fence_after();
             }
-            const int s = t.o1 + row;
-            const bool row_ok = MODE == MODE_CONV && s < p.S;
-            const size_t grow = (size_t)t.o2 * p.S + s;
-#pragma unroll 1
-            for (int j = 0; j < TN / 32; ++j) {
-                uint32_t v[32];
-                if (dead || (p.debug & 4)) {
+            if (dead || (p.debug & 4)) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = 0u;
-                } else {
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN + j * 32, v);
-                }
-                if (!dead && j == TN / 32 - 1) {   // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-                }
-                const int nb = t.o0 + j * 32;
+                for (int i = 0; i < 64; ++i) v[i] = 0u;
+            } else {
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN + half * 64;
+                tmem_ld32_nowait(taddr, v);
+                tmem_ld32_nowait(taddr + 32, v + 32);
+                tmem_ld_wait(v);
+                tmem_ld_wait(v + 32);
+            }
+            if (!dead) {   // all TMEM reads of this warp are done: hand the accumulator back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            }
+            const int s = t.o1 + row;
+            const bool row_ok = MODE != MODE_WGRAD && s < p.S;
+            const size_t grow = (size_t)t.o2 * p.S + s;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int nb = t.o0 + (half * 2 + jj) * 32;
                 float o[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]);
-                if (MODE == MODE_CONV && !dead) {
+                for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[jj * 32 + i]);
+                if (MODE != MODE_WGRAD && !dead) {
                     // every condition below is warp-uniform except row_ok; columns >= Cout are clipped by the TMA store
                     const bool full = nb + 32 <= p.Cout;
                     if (p.alpha != 1.f) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) o[i] *= p.alpha;
                     }
-                    if (p.bias) {
+                    if (p.bias && !(p.debug & 256)) {
                         if (full) {
 #pragma unroll
                             for (int c = 0; c < 8; ++c) {
@@ -449,7 +567,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                         for (int i = 0; i < 32; ++i) o[i] = round_tf32(o[i]);
                     }
                 }
-                if (MODE == MODE_CONV && p.y_planes) {
+                if (MODE != MODE_WGRAD && p.y_planes) {
                     // the consumer GEMMs read bf16 hi|lo operand planes: emit them here instead of a later split pass over an
                     // fp32 copy (32 columns = 64 bytes per row and plane)
                     uint32_t hi[16], lo[16];
@@ -457,10 +575,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                     for (int i = 0; i < 16; ++i) split_pair_u32(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
                     if (p.skip_y) {
                         // planes only: stage hi | lo tiles (2 KB each) in this warp's buffer and TMA-store both (map_y is the
-                        // bf16 planes map; rows >= S are clipped by the store)
-                        if (lane == 0) tma_store_wait_read<1>();
+                        // bf16 planes map; rows >= S are clipped by the store).  The arithmetic above ran while the previous
+                        // store was still reading the buffer.
+                        if (lane == 0) tma_store_wait_read<0>();
                         __syncwarp();
-                        const uint32_t wbuf = sOut + (quad * 2 + (j & 1)) * (32 * 128);
                         const uint32_t rbuf = wbuf + lane * 64;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {   // SWIZZLE_64B: 16-byte chunk c of row r lands at chunk c ^ ((r >> 1) & 3)
@@ -470,7 +588,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbuf + 2048 + off), "r"(lo[4 * c]),
                                          "r"(lo[4 * c + 1]), "r"(lo[4 * c + 2]), "r"(lo[4 * c + 3]) : "memory");
                         }
-                        fence_async_smem();
+                        if (!(p.debug & 64)) fence_async_smem();
                         __syncwarp();
                         if (lane == 0 && !(p.debug & 8)) {
                             tma_store_3d(&map_y, wbuf, nb, t.o1 + quad * 32, t.o2);
@@ -489,11 +607,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                         }
                     }
                 }
-                // each epilogue warp stages and stores its own 32 rows x 32 columns (4 KB, two buffers per warp): no
-                // cross-warp barrier.  Buffer (j & 1): the TMA store that last read it (2 chunks ago) must be done reading.
-                if (lane == 0) tma_store_wait_read<1>();
+                // each epilogue warp stages and stores its own 32 rows x 32 columns (4 KB): no cross-warp barrier.  The TMA
+                // store that last read the buffer (previous chunk) must be done reading before it is overwritten.
+                if (lane == 0) tma_store_wait_read<0>();
                 __syncwarp();
-                const uint32_t wbuf = sOut + (quad * 2 + (j & 1)) * (32 * 128);
                 const uint32_t obuf = wbuf + lane * 128;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {   // 16-byte chunk c of this row lands at chunk (c ^ (row & 7)): SWIZZLE_128B
@@ -501,14 +618,14 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o[4 * c]), "f"(o[4 * c + 1]),
                                  "f"(o[4 * c + 2]), "f"(o[4 * c + 3]) : "memory");
                 }
-                fence_async_smem();
+                if (!(p.debug & 64)) fence_async_smem();
                 __syncwarp();
                 if (lane == 0 && !(p.debug & 8)) {
                     tma_store_3d(&map_y, wbuf, nb, t.o1 + quad * 32, t.o2);
                     tma_store_commit();
                 }
             }
-            if (p.trace && blockIdx.x == 0 && et == 0 && it < 256) p.trace[3 * 256 + it] = clock64();
+            if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && it < 256) p.trace[3 * 256 + it] = clock64();
             if (!dead) ++it;
         }
         if (lane == 0) tma_store_wait_all();
@@ -645,11 +762,11 @@ int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, 
            const TcParams& p, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        DX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<PREC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<PREC>()));
+        DX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<PREC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<PREC, MODE>()));
         configured = true;
     }
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    gemm_tc_kernel<PREC, MODE><<<grid, 192, smem_bytes<PREC>(), st>>>(ah, al, bh, bl, my, p);
+    gemm_tc_kernel<PREC, MODE><<<grid, NTHREADS, smem_bytes<PREC, MODE>(), st>>>(ah, al, bh, bl, my, p);
     return check_launch("gemm_tc");
 }
 
@@ -662,6 +779,15 @@ int tc_debug_mask() {
         mask = e ? atoi(e) : 0;
     }
     return mask;
+}
+
+bool halo_enabled() {   // DX_TC_HALO=0 falls back to per-tap activation loads (bring-up / A-B timing)
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("DX_TC_HALO");
+        on = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return on == 1;
 }
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -769,10 +895,13 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     p.k_chunks = ceil_div(a.Cin, Cfg<PREC_BF16X3>::TKB);
     const uint64_t xs1 = (uint64_t)a.Cin * 2, xs2 = (uint64_t)a.S * a.Cin * 2;
     const uint64_t ws1 = (uint64_t)a.Cin * 2, ws2 = (uint64_t)a.Cout * a.Cin * 2;
-    if ((rc = make_map_3d(&mxh, xh, 2, a.Cin, a.S, a.B, xs1, xs2, 64, TM, 1))) return rc;
-    if ((rc = make_map_3d(&mxl, xl, 2, a.Cin, a.S, a.B, xs1, xs2, 64, TM, 1))) return rc;
+    const bool halo_mode = a.KW == 3 && halo_enabled();
+    const uint32_t box_rows = halo_mode ? HALO_ROWS : TM;
+    if ((rc = make_map_3d(&mxh, xh, 2, a.Cin, a.S, a.B, xs1, xs2, 64, box_rows, 1))) return rc;
+    if ((rc = make_map_3d(&mxl, xl, 2, a.Cin, a.S, a.B, xs1, xs2, 64, box_rows, 1))) return rc;
     if ((rc = make_map_3d(&mwh, wh, 2, a.Cin, a.Cout, a.KW, ws1, ws2, 64, TN, 1))) return rc;
     if ((rc = make_map_3d(&mwl, wl, 2, a.Cin, a.Cout, a.KW, ws1, ws2, 64, TN, 1))) return rc;
+    if (halo_mode) return launch<PREC_BF16X3, MODE_HALO>(mxh, mxl, mwh, mwl, my, p, st);
     return launch<PREC_BF16X3, MODE_CONV>(mxh, mxl, mwh, mwl, my, p, st);
 }
 
