@@ -68,11 +68,13 @@ int dx_pack_conv_weights_batched(const void* descs_device, int n_desc, int total
 /* Plane hand-over between GEMMs (tensor-core backends, Cout % 32 == 0): y_planes (nullable) receives the output as bf16 hi|lo
  * planes [2][B*S][Cout] straight from the epilogue, so that the next GEMM consumes it as x_planes without a split pass; y may
  * then be NULL (no fp32 copy at all).  x may be NULL when x_planes is given.  relu_src_hi (nullable): the ReLU mask taken from
- * the bf16 hi plane [B*S][Cout] of the forward activation instead of an fp32 relu_src (hi > 0 <=> the fp32 value was > 0). */
+ * the bf16 hi plane [B*S][Cout] of the forward activation instead of an fp32 relu_src (hi > 0 <=> the fp32 value was > 0).
+ * y_colsum (nullable, tensor-core backends): [Cout] column sums of the stored output over all B*S rows, accumulated by the
+ * epilogue (when the output is a gradient dh this is the bias gradient of the layer below: no separate reduction pass). */
 int dx_conv_gemm(const float* x, const void* x_planes, const float* w_packed, const void* w_planes, const float* bias,
-                 const float* relu_src, const void* relu_src_hi, const float* add_src, float* y, void* y_planes, void* workspace,
-                 size_t workspace_bytes, const int64_t* lens, int halo, int B, int S, int Cin, int Cout, int KW, int ldx, int ldy,
-                 float alpha, int relu, int round_tf32, int backend, void* stream);
+                 const float* relu_src, const void* relu_src_hi, const float* add_src, float* y, void* y_planes, float* y_colsum,
+                 void* workspace, size_t workspace_bytes, const int64_t* lens, int halo, int B, int S, int Cin, int Cout, int KW,
+                 int ldx, int ldy, float alpha, int relu, int round_tf32, int backend, void* stream);
 size_t dx_conv_gemm_workspace(int B, int S, int Cin, int Cout, int KW, int have_x_planes, int have_w_planes, int backend);
 /* Deferred split-K reduction (tensor-core backends).  dx_wgrad_defer(1): every following dx_conv_wgrad only RECORDS the
  * reduction of its split-K partials into dw (the caller must then keep each call's workspace alive and must not read dw);
@@ -102,8 +104,10 @@ int dx_scale_copy(const float* x, float* y, float alpha, size_t n, void* stream)
  * the tensor-core kernels) and handed back to the backward; may be NULL with the fp32 backend. */
 size_t dx_attention_planes_bytes(int B, int S, int H, int dh);
 size_t dx_attention_bwd_scratch_bytes(int B, int S, int H, int dh);
-int dx_attention_fwd(const float* qkv, const int64_t* lens, float* ctx, float* lse, void* planes, int B, int S, int H, int dh,
-                     float dropout_p, uint64_t seed, void* stream);
+/* ctx_planes (nullable, tensor-core backends): ctx additionally as bf16 hi|lo operand planes [2][B*S][H*dh] for the
+ * out-projection GEMM (no split pass over ctx). */
+int dx_attention_fwd(const float* qkv, const int64_t* lens, float* ctx, float* lse, void* planes, void* ctx_planes, int B, int S,
+                     int H, int dh, float dropout_p, uint64_t seed, void* stream);
 /* scratch: dx_attention_bwd_scratch_bytes() bytes; dqkv [B,S,3*H*dh] is fully written */
 int dx_attention_bwd(const float* qkv, const void* planes, const int64_t* lens, const float* ctx, const float* lse,
                      const float* dctx, float* dqkv, void* scratch, int B, int S, int H, int dh, float dropout_p, uint64_t seed,
@@ -114,15 +118,19 @@ int dx_attention_bwd(const float* qkv, const void* planes, const int64_t* lens, 
  * replaces model.py:189-191,259 (attention epilogue), :226-235,262 (conv-FF epilogue + FiLM), the LayerNorm+Dropout pairs
  * of the pre-net (:347-348,354-355,361-362) and of the prosody predictor (:534-535,541-542,559-566).
  * film: gamma at film[b*film_stride + c], beta at film[b*film_stride + D + c] (NULL = no FiLM); lens NULL = no mask.
- * D in {128, 256, 1024}.  Saves xhat [B,S,D] and rstd [B*S] for backward. */
+ * D in {128, 256, 1024}.  Saves xhat [B,S,D] and rstd [B*S] for backward.
+ * y_planes (nullable): y additionally as bf16 hi|lo operand planes [2][B*S][D] for the GEMM that consumes it. */
 int dx_ln_fwd(const float* a, const float* res, const float* ln_w, const float* ln_b, const float* film, int film_stride,
-              const int64_t* lens, float* y, float* xhat, float* rstd, int B, int S, int D, float p_in, uint64_t seed_in,
-              float p_out, uint64_t seed_out, void* stream);
+              const int64_t* lens, float* y, float* xhat, float* rstd, void* y_planes, int B, int S, int D, float p_in,
+              uint64_t seed_in, float p_out, uint64_t seed_out, void* stream);
 /* relu_src (nullable, [B,S,D]): dv/da are multiplied by (relu_src > 0) — the ReLU that feeds the LN in the pre-net/predictor.
- * dv = grad wrt v (== grad wrt res); da (nullable) = grad wrt a when p_in > 0; dln_w/dln_b [D]; dfilm [B,2D] nullable */
+ * dv = grad wrt v (== grad wrt res); da (nullable) = grad wrt a when p_in > 0; dln_w/dln_b [D]; dfilm [B,2D] nullable.
+ * g_planes / g_colsum (nullable, D in {128, 256} only): the gradient that leaves through `a` (da when p_in > 0, else dv) as
+ * bf16 hi|lo operand planes [2][B*S][D] and its column sums [D] (= bias gradient of the GEMM that produced a). */
 int dx_ln_bwd(const float* dy, const float* xhat, const float* rstd, const float* ln_w, const float* ln_b, const float* film,
-              int film_stride, const int64_t* lens, const float* relu_src, float* dv, float* da, float* dln_w, float* dln_b, float* dfilm, int B,
-              int S, int D, float p_in, uint64_t seed_in, float p_out, uint64_t seed_out, void* stream);
+              int film_stride, const int64_t* lens, const float* relu_src, float* dv, float* da, float* dln_w, float* dln_b, float* dfilm,
+              void* g_planes, float* g_colsum, int B, int S, int D, float p_in, uint64_t seed_in, float p_out, uint64_t seed_out,
+              void* stream);
 
 /* ---- embeddings, positional encoding, masks ---------------------------------------------------------------------------
  * pe: the reference's sinusoid table (model.py:123-130), rows >= max(S) needed.  replaces model.py:497-504. */

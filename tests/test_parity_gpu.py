@@ -132,7 +132,11 @@ def test_attention_forward_backward(dev, cfg, backend):
     ctx = torch.empty(B, S, D, device=dev)
     lse = torch.empty(B, H, S, device=dev)
     planes = ops.attention_planes(B, S, H, dh, dev)
-    ops._call('dx_attention_fwd', qd.data_ptr(), ld.data_ptr(), ctx.data_ptr(), lse.data_ptr(), ops._p(planes), B, S, H, dh, 0.0, 0, ops._st())
+    ctxP = torch.empty(2, B * S, H * dh, device=dev, dtype=torch.bfloat16) if planes is not None else None
+    ops._call('dx_attention_fwd', qd.data_ptr(), ld.data_ptr(), ctx.data_ptr(), lse.data_ptr(), ops._p(planes), ops._p(ctxP), B, S, H, dh,
+              0.0, 0, ops._st())
+    if ctxP is not None:   # the operand planes written by the attention epilogue: hi + lo == ctx to 2^-16
+        assert scale_rel_err(ctxP.float().sum(0).view(B, S, H * dh), ctx) < 2e-5
     assert scale_rel_err(ctx, ctx_ref.detach()) < (2e-5 if backend == 'fp32' else 5e-5)
     dqkv = torch.empty(B, S, 3 * D, device=dev)
     scratch = torch.empty(ops.lib().dx_attention_bwd_scratch_bytes(B, S, H, dh), device=dev, dtype=torch.uint8)
@@ -166,6 +170,18 @@ def test_layernorm_film_mask_forward_backward(dev, D):
     assert scale_rel_err(dw, t64[2].grad) < 5e-5
     assert scale_rel_err(db, t64[3].grad) < 5e-5
     assert scale_rel_err(dfilm, t64[4].grad) < 5e-5
+    # operand planes written by the LayerNorm kernels themselves (plane fusion): hi + lo reproduces the fp32 tensor to 2^-16,
+    # the fused column sums are the bias gradient of the producing GEMM
+    ops.set_backend('bf16x3')
+    y2, xhat2, rstd2 = ops.ln_fwd(ad, rd, wd_, bd, fd, 2 * D, ld, B, S, D, emit_planes=True)
+    yP = ops.planes_of(y2, B * S, D)
+    assert yP is y2._dx_planes[0]
+    assert torch.equal(y2, y)
+    assert scale_rel_err(yP.float().sum(0).view(B, S, D), y) < 2e-5
+    out = ops.ln_bwd(dyd, xhat, rstd, wd_, bd, fd, 2 * D, ld, B, S, D, want_film=True, emit_planes=True)
+    assert scale_rel_err(out[0], t64[0].grad) < 5e-5 and scale_rel_err(out[2], t64[2].grad) < 5e-5
+    assert scale_rel_err(out[5].float().sum(0).view(B, S, D), out[1]) < 2e-5
+    assert scale_rel_err(out[6], out[1].sum((0, 1))) < 2e-5
 
 
 def test_gaussian_upsampling_integer_contract_and_values(dev):
@@ -421,7 +437,7 @@ def test_dropout_statistics_and_mask_consistency(dev):
     lens = torch.tensor([Sq, 70], device=dev)
     ctx = torch.empty(Bq, Sq, H * dh, device=dev); lse = torch.empty(Bq, H, Sq, device=dev)
     planes = ops.attention_planes(Bq, Sq, H, dh, dev)
-    ops._call('dx_attention_fwd', qkv.data_ptr(), lens.data_ptr(), ctx.data_ptr(), lse.data_ptr(), ops._p(planes), Bq, Sq, H, dh, 0.25, 777, ops._st())
+    ops._call('dx_attention_fwd', qkv.data_ptr(), lens.data_ptr(), ctx.data_ptr(), lse.data_ptr(), ops._p(planes), None, Bq, Sq, H, dh, 0.25, 777, ops._st())
     dctx = torch.randn(Bq, Sq, H * dh, generator=g).to(dev) * oracle.valid_mask(lens.cpu(), Sq).to(dev)[:, :, None]
     dqkv = torch.empty_like(qkv)
     scratch = torch.empty(ops.lib().dx_attention_bwd_scratch_bytes(Bq, Sq, H, dh), device=dev, dtype=torch.uint8)
@@ -431,7 +447,7 @@ def test_dropout_statistics_and_mask_consistency(dev):
     dV = torch.zeros_like(qkv); dV[:, :, 2 * H * dh:] = torch.randn(Bq, Sq, H * dh, generator=g).to(dev)
     ctx2 = torch.empty_like(ctx)
     planes2 = ops.attention_planes(Bq, Sq, H, dh, dev)
-    ops._call('dx_attention_fwd', (qkv + dV).data_ptr(), lens.data_ptr(), ctx2.data_ptr(), lse.data_ptr(), ops._p(planes2), Bq, Sq, H, dh, 0.25, 777, ops._st())
+    ops._call('dx_attention_fwd', (qkv + dV).data_ptr(), lens.data_ptr(), ctx2.data_ptr(), lse.data_ptr(), ops._p(planes2), None, Bq, Sq, H, dh, 0.25, 777, ops._st())
     lhs = ((ctx2 - ctx) * dctx).sum().item()
     rhs = (dqkv * dV).sum().item()
     assert abs(lhs - rhs) < 2e-3 * max(abs(lhs), abs(rhs), 1.0)

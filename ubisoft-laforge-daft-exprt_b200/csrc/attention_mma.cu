@@ -188,10 +188,19 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(AttnArgs p) {
     float* lse = p.lse + ((size_t)b * p.H + h) * p.S;
     const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;   // this lane's two query rows
 
+    // optional: ctx as bf16 hi|lo operand planes [2][B*S][D] for the out-projection GEMM
+    __nv_bfloat16* cph = p.ctx_planes ? (__nv_bfloat16*)p.ctx_planes + (size_t)b * p.S * D + h * DH : nullptr;
+    const size_t cplane = (size_t)p.B * p.S * D;
     if (q0 >= len) {   // whole tile is padding: zeros (their only consumer masks them, model.py:259)
         for (int idx = tid; idx < 64 * DH; idx += 128) {
             const int r = idx / DH, c = idx % DH;
-            if (q0 + r < p.S) ctx[(size_t)(q0 + r) * D + c] = 0.f;
+            if (q0 + r < p.S) {
+                ctx[(size_t)(q0 + r) * D + c] = 0.f;
+                if (cph) {
+                    cph[(size_t)(q0 + r) * D + c] = __float2bfloat16_rn(0.f);
+                    cph[cplane + (size_t)(q0 + r) * D + c] = __float2bfloat16_rn(0.f);
+                }
+            }
         }
         if (tid < 64 && q0 + tid < p.S) lse[q0 + tid] = 0.f;
         return;
@@ -309,8 +318,22 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(AttnArgs p) {
 #pragma unroll
     for (int n = 0; n < ND; ++n) {
         const int c = n * 8 + 2 * t;
-        if (r0 < p.S) *reinterpret_cast<float2*>(ctx + (size_t)r0 * D + c) = make_float2(v0 ? o[n][0] * i0 : 0.f, v0 ? o[n][1] * i0 : 0.f);
-        if (r1 < p.S) *reinterpret_cast<float2*>(ctx + (size_t)r1 * D + c) = make_float2(v1 ? o[n][2] * i1 : 0.f, v1 ? o[n][3] * i1 : 0.f);
+        const float a0 = v0 ? o[n][0] * i0 : 0.f, a1 = v0 ? o[n][1] * i0 : 0.f, b0 = v1 ? o[n][2] * i1 : 0.f, b1 = v1 ? o[n][3] * i1 : 0.f;
+        if (r0 < p.S) *reinterpret_cast<float2*>(ctx + (size_t)r0 * D + c) = make_float2(a0, a1);
+        if (r1 < p.S) *reinterpret_cast<float2*>(ctx + (size_t)r1 * D + c) = make_float2(b0, b1);
+        if (cph) {
+            uint32_t hi, lo;
+            if (r0 < p.S) {
+                split_pair(a0, a1, hi, lo);
+                *reinterpret_cast<uint32_t*>(cph + (size_t)r0 * D + c) = hi;
+                *reinterpret_cast<uint32_t*>(cph + cplane + (size_t)r0 * D + c) = lo;
+            }
+            if (r1 < p.S) {
+                split_pair(b0, b1, hi, lo);
+                *reinterpret_cast<uint32_t*>(cph + (size_t)r1 * D + c) = hi;
+                *reinterpret_cast<uint32_t*>(cph + cplane + (size_t)r1 * D + c) = lo;
+            }
+        }
     }
     if (t == 0) {
         if (r0 < p.S) lse[r0] = v0 ? m0 + logf(l0) : 0.f;

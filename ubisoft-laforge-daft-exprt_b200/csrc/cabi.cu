@@ -81,9 +81,10 @@ int dx_pack_conv_weights_batched(const void* descs_device, int n_desc, int total
 static ConvGemmArgs gemm_args(const float* x, const void* x_planes, const float* w_packed, const void* w_planes, const float* bias,
                               const float* relu_src, const float* add_src, float* y, void* ws, size_t wsb, int B, int S, int Cin,
                               int Cout, int KW, int ldx, int ldy, float alpha, int relu, int round_tf32,
-                              const int64_t* lens = nullptr, int halo = 0, const void* relu_src_hi = nullptr, void* y_planes = nullptr) {
+                              const int64_t* lens = nullptr, int halo = 0, const void* relu_src_hi = nullptr, void* y_planes = nullptr,
+                              float* y_colsum = nullptr) {
     ConvGemmArgs a;
-    a.lens = (cll)lens; a.halo = halo; a.relu_src_hi = relu_src_hi; a.y_planes = y_planes;
+    a.lens = (cll)lens; a.halo = halo; a.relu_src_hi = relu_src_hi; a.y_planes = y_planes; a.y_colsum = y_colsum;
     a.x = x; a.w = w_packed; a.bias = bias; a.relu_src = relu_src; a.add_src = add_src; a.y = y;
     a.B = B; a.S = S; a.Cin = Cin; a.Cout = Cout; a.KW = KW; a.ldx = ldx; a.ldy = ldy;
     a.alpha = alpha; a.relu = relu; a.round_tf32 = round_tf32;
@@ -108,15 +109,15 @@ size_t dx_conv_gemm_workspace(int B, int S, int Cin, int Cout, int KW, int have_
 }
 
 int dx_conv_gemm(const float* x, const void* x_planes, const float* w_packed, const void* w_planes, const float* bias,
-                 const float* relu_src, const void* relu_src_hi, const float* add_src, float* y, void* y_planes, void* workspace,
-                 size_t workspace_bytes, const int64_t* lens, int halo, int B, int S, int Cin, int Cout, int KW, int ldx, int ldy,
-                 float alpha, int relu, int round_tf32, int backend, void* stream) {
+                 const float* relu_src, const void* relu_src_hi, const float* add_src, float* y, void* y_planes, float* y_colsum,
+                 void* workspace, size_t workspace_bytes, const int64_t* lens, int halo, int B, int S, int Cin, int Cout, int KW,
+                 int ldx, int ldy, float alpha, int relu, int round_tf32, int backend, void* stream) {
     ConvGemmArgs a = gemm_args(x, x_planes, w_packed, w_planes, bias, relu_src, add_src, y, workspace, workspace_bytes, B, S, Cin,
-                               Cout, KW, ldx, ldy, alpha, relu, round_tf32, lens, halo, relu_src_hi, y_planes);
+                               Cout, KW, ldx, ldy, alpha, relu, round_tf32, lens, halo, relu_src_hi, y_planes, y_colsum);
     DX_REQUIRE(B > 0 && S > 0 && Cin > 0 && Cout > 0 && (KW == 1 || KW == 3), "dx_conv_gemm: bad shape B=%d S=%d Cin=%d Cout=%d KW=%d", B, S, Cin, Cout, KW);
     const int be = backend < 0 ? g_backend : backend;
     if (be != DX_GEMM_FP32_CUDA_CORES && conv_gemm_tc_supported(a)) return conv_gemm_tc(a, ST(stream));
-    DX_REQUIRE(!relu_src_hi && !y_planes && y && x, "dx_conv_gemm: y_planes / relu_src_hi / plane-only operands need the tensor-core path (Cin=%d Cout=%d)", Cin, Cout);
+    DX_REQUIRE(!relu_src_hi && !y_planes && !y_colsum && y && x, "dx_conv_gemm: y_planes / y_colsum / relu_src_hi / plane-only operands need the tensor-core path (Cin=%d Cout=%d)", Cin, Cout);
     return conv_gemm_simt(a, ST(stream));
 }
 
@@ -163,10 +164,12 @@ int dx_scale_copy(const float* x, float* y, float alpha, size_t n, void* stream)
 size_t dx_attention_planes_bytes(int B, int S, int H, int dh) { return attention_planes_bytes(B, S, H, dh); }
 size_t dx_attention_bwd_scratch_bytes(int B, int S, int H, int dh) { return attention_bwd_scratch_bytes(B, S, H, dh); }
 
-int dx_attention_fwd(const float* qkv, const int64_t* lens, float* ctx, float* lse, void* planes, int B, int S, int H, int dh,
-                     float dropout_p, uint64_t seed, void* stream) {
+int dx_attention_fwd(const float* qkv, const int64_t* lens, float* ctx, float* lse, void* planes, void* ctx_planes, int B, int S,
+                     int H, int dh, float dropout_p, uint64_t seed, void* stream) {
     AttnArgs a;
     memset(&a, 0, sizeof(a));
+    a.ctx_planes = ctx_planes;
+    DX_REQUIRE(!ctx_planes || (g_backend != DX_GEMM_FP32_CUDA_CORES && planes), "dx_attention_fwd: ctx_planes needs the tensor-core path");
     a.qkv = qkv; a.lens = (cll)lens; a.ctx = ctx; a.lse = lse; a.B = B; a.S = S; a.H = H; a.dh = dh;
     a.dropout_p = dropout_p; a.seed = seed;
     a.dyn = g_step_state;
@@ -190,10 +193,11 @@ int dx_attention_bwd(const float* qkv, const void* planes, const int64_t* lens, 
 }
 
 int dx_ln_fwd(const float* a_, const float* res, const float* ln_w, const float* ln_b, const float* film, int film_stride,
-              const int64_t* lens, float* y, float* xhat, float* rstd, int B, int S, int D, float p_in, uint64_t seed_in,
-              float p_out, uint64_t seed_out, void* stream) {
+              const int64_t* lens, float* y, float* xhat, float* rstd, void* y_planes, int B, int S, int D, float p_in,
+              uint64_t seed_in, float p_out, uint64_t seed_out, void* stream) {
     LnArgs a;
     memset(&a, 0, sizeof(a));
+    a.y_planes = y_planes;
     a.a = a_; a.res = res; a.ln_w = ln_w; a.ln_b = ln_b; a.film = film; a.film_stride = film_stride; a.lens = (cll)lens;
     a.y = y; a.xhat = xhat; a.rstd = rstd; a.B = B; a.S = S; a.D = D;
     a.p_in = p_in; a.p_out = p_out; a.seed_in = seed_in; a.seed_out = seed_out;
@@ -202,10 +206,12 @@ int dx_ln_fwd(const float* a_, const float* res, const float* ln_w, const float*
 }
 
 int dx_ln_bwd(const float* dy, const float* xhat, const float* rstd, const float* ln_w, const float* ln_b, const float* film,
-              int film_stride, const int64_t* lens, const float* relu_src, float* dv, float* da, float* dln_w, float* dln_b, float* dfilm, int B,
-              int S, int D, float p_in, uint64_t seed_in, float p_out, uint64_t seed_out, void* stream) {
+              int film_stride, const int64_t* lens, const float* relu_src, float* dv, float* da, float* dln_w, float* dln_b, float* dfilm,
+              void* g_planes, float* g_colsum, int B, int S, int D, float p_in, uint64_t seed_in, float p_out, uint64_t seed_out,
+              void* stream) {
     LnArgs a;
     memset(&a, 0, sizeof(a));
+    a.g_planes = g_planes; a.g_colsum = g_colsum;
     a.dy = dy; a.xhat = (float*)xhat; a.rstd = (float*)rstd; a.ln_w = ln_w; a.ln_b = ln_b; a.film = film;
     a.film_stride = film_stride; a.lens = (cll)lens; a.relu_src = relu_src; a.dv = dv; a.da = da; a.dln_w = dln_w; a.dln_b = dln_b; a.dfilm = dfilm;
     a.B = B; a.S = S; a.D = D; a.p_in = p_in; a.p_out = p_out; a.seed_in = seed_in; a.seed_out = seed_out;

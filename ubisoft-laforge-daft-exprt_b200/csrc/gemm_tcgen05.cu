@@ -163,6 +163,7 @@ struct TcParams {
     const float* relu_src;
     const float* add_src;
     const __nv_bfloat16* relu_src_hi;   // ReLU mask from a bf16 hi plane [B*S][Cout] (Cout % 32 == 0)
+    float* colsum;                      // optional [Cout]: column sums of the stored output (fp32 atomics, one per warp and chunk)
     __nv_bfloat16* y_planes;            // optional: output as bf16 hi|lo planes [2][B*S][Cout] (Cout % 32 == 0)
     long long y_plane_elems;            // B*S*Cout
     int skip_y;                         // no fp32 output (planes only)
@@ -567,6 +568,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
                         for (int i = 0; i < 32; ++i) o[i] = round_tf32(o[i]);
                     }
                 }
+                if (MODE != MODE_WGRAD && p.colsum && !dead) {
+                    // column sums of this warp's 32 rows x 32 columns by recursive halving across the lanes (31 shuffles):
+                    // afterwards lane l holds the sum of column l
+                    const float rk = row_ok ? 1.f : 0.f;
+                    float r16[16], r8[8], r4[4], r2[2];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const bool up = lane & 16;
+                        const float keep = (up ? o[i + 16] : o[i]) * rk, send = (up ? o[i] : o[i + 16]) * rk;
+                        r16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const bool up = lane & 8;
+                        r8[i] = (up ? r16[i + 8] : r16[i]) + __shfl_xor_sync(0xffffffffu, up ? r16[i] : r16[i + 8], 8);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const bool up = lane & 4;
+                        r4[i] = (up ? r8[i + 4] : r8[i]) + __shfl_xor_sync(0xffffffffu, up ? r8[i] : r8[i + 4], 4);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const bool up = lane & 2;
+                        r2[i] = (up ? r4[i + 2] : r4[i]) + __shfl_xor_sync(0xffffffffu, up ? r4[i] : r4[i + 2], 2);
+                    }
+                    const bool up1 = lane & 1;
+                    const float tot = (up1 ? r2[1] : r2[0]) + __shfl_xor_sync(0xffffffffu, up1 ? r2[0] : r2[1], 1);
+                    if (nb + lane < p.Cout) atomicAdd(p.colsum + nb + lane, tot);
+                }
                 if (MODE != MODE_WGRAD && p.y_planes) {
                     // the consumer GEMMs read bf16 hi|lo operand planes: emit them here instead of a later split pass over an
                     // fp32 copy (32 columns = 64 bytes per row and plane)
@@ -832,6 +863,8 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     p.bias = a.bias; p.relu_src = a.relu_src; p.add_src = a.add_src;
     p.relu_src_hi = (const __nv_bfloat16*)a.relu_src_hi;
     p.y_planes = (__nv_bfloat16*)a.y_planes;
+    p.colsum = a.y_colsum;
+    if (a.y_colsum) DX_CUDA(cudaMemsetAsync(a.y_colsum, 0, (size_t)a.Cout * sizeof(float), st));
     p.y_plane_elems = (long long)a.B * a.S * a.Cout;
     p.skip_y = a.y == nullptr;
     DX_REQUIRE(a.y || a.y_planes, "conv_gemm_tc: no output (y and y_planes are both NULL)");
@@ -1040,7 +1073,7 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
     }
     TcParams p;
     p.bias = nullptr; p.relu_src = nullptr; p.add_src = nullptr;
-    p.relu_src_hi = nullptr; p.y_planes = nullptr; p.y_plane_elems = 0; p.skip_y = 0;
+    p.relu_src_hi = nullptr; p.y_planes = nullptr; p.colsum = nullptr; p.y_plane_elems = 0; p.skip_y = 0;
     p.B = a.B; p.S = a.S; p.Cin = a.Cin; p.Cout = a.Cout; p.KW = a.KW; p.ldy = a.Cin;
     p.tiles_m_per_b = ceil_div(a.Cout, TM);
     p.tiles_n = ceil_div(a.Cin, TN);

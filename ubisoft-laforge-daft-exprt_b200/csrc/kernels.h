@@ -19,6 +19,7 @@ struct ConvGemmArgs {
     float* y;               // [B, S, ldy]; nullable when y_planes is given (tensor-core path: no fp32 copy is written)
     void* y_planes;         // optional (tensor-core path, Cout % 32 == 0): the output as bf16 hi|lo planes [2][B*S][Cout], written by the epilogue
     const void* relu_src_hi;  // optional (tensor-core path, Cout % 32 == 0): ReLU mask source as the bf16 hi plane [B*S][Cout] of the forward activation
+    float* y_colsum;        // optional (tensor-core path): [Cout] column sums of the stored output over all B*S rows (zeroed + accumulated inside)
     int B, S, Cin, Cout, KW;
     int ldx, ldy;
     float alpha;
@@ -78,6 +79,7 @@ struct AttnArgs {
     const long long* lens;  // [B] valid keys/queries per utterance
     float* ctx;
     float* lse;
+    void* ctx_planes;       // forward, tensor-core path, optional: ctx also as bf16 hi|lo operand planes [2][B*S][H*dh]
     const float* dctx;      // backward only
     float* dqkv;            // backward only, [B, S, 3*D]
     float* delta;           // backward scratch [B, H, S]
@@ -123,6 +125,10 @@ struct LnArgs {
     float* dln_w;   // [D]   (zeroed + accumulated inside)
     float* dln_b;   // [D]
     float* dfilm;   // [B, 2*D] contiguous (gamma | beta), nullable
+    // optional bf16 hi|lo operand planes [2][B*S][D] of the tensor the next GEMM consumes
+    void* y_planes;     // forward: planes of y
+    void* g_planes;     // backward (D in {128, 256}): planes of da (p_in > 0) or dv
+    float* g_colsum;    // backward (D in {128, 256}): [D] column sums of the same gradient (= bias gradient of the GEMM that produced a)
 };
 int ln_fwd(const LnArgs& a, cudaStream_t st);
 int ln_bwd(const LnArgs& a, cudaStream_t st);

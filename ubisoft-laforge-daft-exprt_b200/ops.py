@@ -184,22 +184,27 @@ def make_planes(x, rows, C, ld=None, want_colsum=False):
 
 
 def conv_gemm(x, wp, bias, B, S, relu=False, relu_src=None, add_src=None, alpha=1.0, round_out=False, ldx=None, x_planes=None,
-              lens=None, halo=0, relu_src_hi=None, emit_planes=False, want_y=True):
+              lens=None, halo=0, relu_src_hi=None, emit_planes=False, want_y=True, want_colsum=False):
     """x [B,S,Cin] (row stride ldx) · packed weight [KW,Cout,Cin] -> [B,S,Cout].
     lens/halo: padding skip — output rows s >= lens[b] + halo are declared irrelevant by the caller (written as zeros).
     Plane hand-over (`plane_handover()`): emit_planes -> returns (y, planes [2, B*S, Cout] bf16 hi|lo written by the epilogue);
-    want_y=False drops the fp32 copy; x may be None when x_planes is given; relu_src_hi = hi plane used as the ReLU mask."""
+    want_y=False drops the fp32 copy; x may be None when x_planes is given; relu_src_hi = hi plane used as the ReLU mask.
+    want_colsum (tensor-core backends): also returns the [Cout] column sums of the output, accumulated by the epilogue."""
     kw, cout, cin = wp.shape
     dev = wp.w.device
     y = torch.empty(B, S, cout, device=dev, dtype=torch.float32) if want_y else None
     yP = torch.empty(2, B * S, cout, device=dev, dtype=torch.bfloat16) if emit_planes else None
+    ycs = torch.empty(cout, device=dev, dtype=torch.float32) if want_colsum else None
     rnd = 1 if (round_out and _backend[0] == cabi.DX_GEMM_TCGEN05_TF32) else 0
     nbytes = lib().dx_conv_gemm_workspace(B, S, cin, cout, kw, int(x_planes is not None), int(wp.planes is not None), -1)
     ws = torch.empty(nbytes + 256, device=dev, dtype=torch.uint8) if nbytes else None
     _call('dx_conv_gemm', _p(x), _p(x_planes), _p(wp.w), _p(wp.planes), _p(bias), _p(relu_src), _p(relu_src_hi), _p(add_src), _p(y),
-          _p(yP), _p(ws), ws.numel() if ws is not None else 0, _p(lens), int(halo), B, S, cin, cout, kw, cin if ldx is None else ldx,
-          cout, float(alpha), int(relu), rnd, -1, _st())
-    return (y, yP) if emit_planes else y
+          _p(yP), _p(ycs), _p(ws), ws.numel() if ws is not None else 0, _p(lens), int(halo), B, S, cin, cout, kw,
+          cin if ldx is None else ldx, cout, float(alpha), int(relu), rnd, -1, _st())
+    out = (y, yP) if emit_planes else y
+    if want_colsum:
+        out = (out + (ycs,)) if emit_planes else (out, ycs)
+    return out
 
 
 _wgrad_deferred = [False]
@@ -261,25 +266,58 @@ def attention_planes(B, S, H, dh, device):
     return torch.empty(lib().dx_attention_planes_bytes(B, S, H, dh), device=device, dtype=torch.uint8)
 
 
-def ln_fwd(a, res, ln_w, ln_b, film, film_stride, lens, B, S, D, p_in=0.0, seed_in=0, p_out=0.0, seed_out=0):
+def _uses_planes(C):
+    return _backend[0] != cabi.DX_GEMM_FP32_CUDA_CORES and C % 8 == 0 and C >= 16
+
+
+def attach_planes(t, planes):
+    """Side channel between sub-layers: the producer of an activation already wrote its bf16 hi|lo operand planes."""
+    if planes is not None:
+        t._dx_planes = (planes, t._version)
+    return t
+
+
+def planes_of(x, rows, C):
+    """Operand planes of x: the ones its producer attached (LayerNorm / attention epilogues), else one split pass."""
+    tag = getattr(x, '_dx_planes', None)
+    if tag is not None and tag[1] == x._version and tuple(tag[0].shape) == (2, rows, C) and _uses_planes(C):
+        return tag[0]
+    return make_planes(x, rows, C)
+
+
+def ln_fwd(a, res, ln_w, ln_b, film, film_stride, lens, B, S, D, p_in=0.0, seed_in=0, p_out=0.0, seed_out=0, emit_planes=False):
+    """emit_planes: y is also written as bf16 hi|lo operand planes (attached to y for `planes_of`)."""
     y = torch.empty(B, S, D, device=a.device, dtype=torch.float32)
     xhat = torch.empty(B, S, D, device=a.device, dtype=torch.float32)
     rstd = torch.empty(B * S, device=a.device, dtype=torch.float32)
-    _call('dx_ln_fwd', _p(a), _p(res), _p(ln_w), _p(ln_b), _p(film), film_stride, _p(lens), _p(y), _p(xhat), _p(rstd),
+    yP = torch.empty(2, B * S, D, device=a.device, dtype=torch.bfloat16) if (emit_planes and _uses_planes(D)) else None
+    _call('dx_ln_fwd', _p(a), _p(res), _p(ln_w), _p(ln_b), _p(film), film_stride, _p(lens), _p(y), _p(xhat), _p(rstd), _p(yP),
           B, S, D, float(p_in), seed_in, float(p_out), seed_out, _st())
+    attach_planes(y, yP)
     return y, xhat, rstd
 
 
 def ln_bwd(dy, xhat, rstd, ln_w, ln_b, film, film_stride, lens, B, S, D, relu_src=None, p_in=0.0, seed_in=0, p_out=0.0,
-           seed_out=0, want_film=False):
+           seed_out=0, want_film=False, emit_planes=False):
+    """-> (dv, da, dln_w, dln_b, dfilm[, planes, colsum]).  emit_planes (D in {128, 256}): the fused kernel also writes the
+    operand planes and the column sums of da (the gradient entering the GEMM that produced `a`); (None, None) when the
+    backend has no planes."""
     dv = torch.empty(B, S, D, device=dy.device, dtype=torch.float32)
     da = torch.empty(B, S, D, device=dy.device, dtype=torch.float32) if p_in > 0 else None
     dw = torch.empty(D, device=dy.device, dtype=torch.float32)
     db = torch.empty(D, device=dy.device, dtype=torch.float32)
     dfilm = torch.empty(B, 2 * D, device=dy.device, dtype=torch.float32) if want_film else None
+    fuse = emit_planes and _uses_planes(D) and D in (128, 256)
+    gP = torch.empty(2, B * S, D, device=dy.device, dtype=torch.bfloat16) if fuse else None
+    gcs = torch.empty(D, device=dy.device, dtype=torch.float32) if fuse else None
     _call('dx_ln_bwd', _p(dy), _p(xhat), _p(rstd), _p(ln_w), _p(ln_b), _p(film), film_stride, _p(lens), _p(relu_src),
-          _p(dv), _p(da), _p(dw), _p(db), _p(dfilm), B, S, D, float(p_in), seed_in, float(p_out), seed_out, _st())
-    return dv, (da if da is not None else dv), dw, db, dfilm
+          _p(dv), _p(da), _p(dw), _p(db), _p(dfilm), _p(gP), _p(gcs), B, S, D, float(p_in), seed_in, float(p_out), seed_out, _st())
+    out = (dv, (da if da is not None else dv), dw, db, dfilm)
+    if emit_planes:
+        if not fuse:
+            gP, gcs = make_planes(out[1], B * S, D, want_colsum=True)
+        out = out + (gP, gcs)
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -293,16 +331,17 @@ class AttentionSubLayer(torch.autograd.Function):
         dh = D // nb_heads
         in_wp, in_wd = packed(in_w)
         out_wp, out_wd = packed(out_w)
-        xP = make_planes(x, B * S, D)
+        xP = planes_of(x, B * S, D)
         qkv = conv_gemm(x, in_wp, in_b, B, S, x_planes=xP, lens=lens)   # rows >= len: keys masked, queries skipped
         att = torch.empty(B, S, D, device=x.device, dtype=torch.float32)
         lse = torch.empty(B, nb_heads, S, device=x.device, dtype=torch.float32)
         seed_attn, seed_out = (next_seed(), next_seed()) if p_drop > 0 else (0, 0)
         planes = attention_planes(B, S, nb_heads, dh, x.device)
-        _call('dx_attention_fwd', _p(qkv), _p(lens), _p(att), _p(lse), _p(planes), B, S, nb_heads, dh, float(p_drop), seed_attn, _st())
-        attP = make_planes(att, B * S, D)
+        attP = torch.empty(2, B * S, D, device=x.device, dtype=torch.bfloat16) if (planes is not None and _uses_planes(D)) else None
+        _call('dx_attention_fwd', _p(qkv), _p(lens), _p(att), _p(lse), _p(planes), _p(attP), B, S, nb_heads, dh, float(p_drop), seed_attn,
+              _st())   # the kernel writes ctx and its operand planes
         proj = conv_gemm(att, out_wp, out_b, B, S, x_planes=attP, lens=lens)   # rows >= len are masked by the LayerNorm kernel
-        y, xhat, rstd = ln_fwd(proj, x, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p_drop, seed_in=seed_out)
+        y, xhat, rstd = ln_fwd(proj, x, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p_drop, seed_in=seed_out, emit_planes=True)
         ctx.save_for_backward(x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b, xP, attP, planes)
         ctx.packed = (in_wd, out_wd)
         ctx.cfg = (B, S, D, nb_heads, dh, float(p_drop), seed_attn, seed_out, in_w.shape, out_w.shape)
@@ -314,8 +353,8 @@ class AttentionSubLayer(torch.autograd.Function):
         in_wd, out_wd = ctx.packed
         B, S, D, H, dh, p, seed_attn, seed_out, in_shape, out_shape = ctx.cfg
         dy = _check_input(dy)
-        dv, dproj, dln_w, dln_b, _ = ln_bwd(dy, xhat, rstd, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p, seed_in=seed_out)
-        dprojP, dpb = make_planes(dproj, B * S, D, want_colsum=True)
+        dv, dproj, dln_w, dln_b, _, dprojP, dpb = ln_bwd(dy, xhat, rstd, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p, seed_in=seed_out,
+                                                         emit_planes=True)
         datt = conv_gemm(dproj, out_wd, None, B, S, x_planes=dprojP, lens=lens)   # dproj == 0 beyond len: exact
         d_out_w, d_out_b = conv_wgrad(att, dproj, B, S, D, D, 1, out_shape, x_planes=attP, dy_planes=dprojP, dbias=dpb, lens=lens)
         dqkv = torch.empty(B, S, 3 * D, device=dy.device, dtype=torch.float32)
@@ -338,7 +377,7 @@ class ConvFFSubLayer(torch.autograd.Function):
         w1p, w1d = packed(w1)
         w2p, w2d = packed(w2)
         C = w1.shape[0]
-        xP = make_planes(x, B * S, D)
+        xP = planes_of(x, B * S, D)
         k2 = (w2.shape[2] - 1) // 2
         if plane_handover(D, C) and xP is not None:
             # the hidden activation (8x wider than the model) only ever feeds GEMMs: it exists as operand planes only,
@@ -352,7 +391,7 @@ class ConvFFSubLayer(torch.autograd.Function):
         if film is not None:
             film = _check_input(film)
             assert film.shape[1] == 2 * D   # reference model.py:232
-        y, xhat, rstd = ln_fwd(o, x, ln_w, ln_b, film, 2 * D, lens, B, S, D, p_in=p_drop, seed_in=seed)
+        y, xhat, rstd = ln_fwd(o, x, ln_w, ln_b, film, 2 * D, lens, B, S, D, p_in=p_drop, seed_in=seed, emit_planes=True)
         ctx.save_for_backward(x, lens, h, xhat, rstd, ln_w, ln_b, film, xP, hP)
         ctx.packed = (w1d, w2d)
         ctx.cfg = (B, S, D, C, float(p_drop), seed, w1.shape, w2.shape)
@@ -364,13 +403,12 @@ class ConvFFSubLayer(torch.autograd.Function):
         w1d, w2d = ctx.packed
         B, S, D, C, p, seed, w1_shape, w2_shape = ctx.cfg
         dy = _check_input(dy)
-        dv, do, dln_w, dln_b, dfilm = ln_bwd(dy, xhat, rstd, ln_w, ln_b, film, 2 * D, lens, B, S, D, p_in=p, seed_in=seed,
-                                             want_film=film is not None)
-        doP, dob = make_planes(do, B * S, D, want_colsum=True)
+        dv, do, dln_w, dln_b, dfilm, doP, dob = ln_bwd(dy, xhat, rstd, ln_w, ln_b, film, 2 * D, lens, B, S, D, p_in=p, seed_in=seed,
+                                                       want_film=film is not None, emit_planes=True)
         k2 = (w2_shape[2] - 1) // 2
         if h is None:   # plane hand-over: dh exists as planes only; its column sums (conv1 bias gradient) are taken from them
-            dh, dhP = conv_gemm(do, w2d, None, B, S, relu_src_hi=hP, x_planes=doP, lens=lens, halo=k2, emit_planes=True, want_y=False)
-            dhb = colsum_planes(dhP, B * S, C)
+            dh, dhP, dhb = conv_gemm(do, w2d, None, B, S, relu_src_hi=hP, x_planes=doP, lens=lens, halo=k2, emit_planes=True, want_y=False,
+                                     want_colsum=True)   # conv1's bias gradient = column sums of dh, taken by the epilogue
         else:
             dh = conv_gemm(do, w2d, None, B, S, relu_src=h, round_out=True, x_planes=doP, lens=lens, halo=k2)   # do == 0 beyond len: exact
             dhP, dhb = make_planes(dh, B * S, C, want_colsum=True)
@@ -398,11 +436,11 @@ class PreNet(torch.autograd.Function):
         halos = [sum(pads[i + 1:]) for i in range(3)]
         for i, (w, b, g, e) in enumerate(layers):
             wp, wd = packed(w)
-            curP = make_planes(cur, B * T, w.shape[1])
+            curP = planes_of(cur, B * T, w.shape[1])
             in_planes.append(curP)
             a = conv_gemm(cur, wp, b, B, T, relu=True, x_planes=curP, lens=lens, halo=halos[i])
             seed = next_seed() if p_drop > 0 else 0
-            y, xhat, rstd = ln_fwd(a, None, g, e, None, 0, None, B, T, w.shape[0], p_out=p_drop, seed_out=seed)
+            y, xhat, rstd = ln_fwd(a, None, g, e, None, 0, None, B, T, w.shape[0], p_out=p_drop, seed_out=seed, emit_planes=i < 2)
             saved += [a, xhat, rstd, g, e]
             seeds.append(seed)
             wds.append(wd)
@@ -430,8 +468,8 @@ class PreNet(torch.autograd.Function):
             wd = ctx.packed[i]
             cout, cin, kw = shapes[i]
             inp = x if i == 0 else layers[i - 1][5]
-            dpre, _, dg, de, _ = ln_bwd(d, xhat, rstd, g, e, None, 0, None, B, T, cout, relu_src=a, p_out=p, seed_out=seeds[i])
-            dpreP, dpreb = make_planes(dpre, B * T, cout, want_colsum=True)
+            dpre, _, dg, de, _, dpreP, dpreb = ln_bwd(d, xhat, rstd, g, e, None, 0, None, B, T, cout, relu_src=a, p_out=p,
+                                                      seed_out=seeds[i], emit_planes=True)
             # the gradient of the masked pre-net output is zero beyond len, so dpre of layer i is exactly zero beyond len + halos[i]
             dw, db = conv_wgrad(inp, dpre, B, T, cin, cout, kw, shapes[i], x_planes=ctx.in_planes[i], dy_planes=dpreP, dbias=dpreb,
                                 lens=lens, halo=halos[i])
