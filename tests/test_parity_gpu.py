@@ -451,6 +451,23 @@ def test_dropout_statistics_and_mask_consistency(dev):
     lhs = ((ctx2 - ctx) * dctx).sum().item()
     rhs = (dqkv * dV).sum().item()
     assert abs(lhs - rhs) < 2e-3 * max(abs(lhs), abs(rhs), 1.0)
+    # statistics of the attention-weight mask: with q = k = 0 (uniform weights) and V = 1, ctx[q, :] = kept(q) / (len * (1 - p)):
+    # the kept fraction matches 1 - p and its row-to-row variance is binomial (no correlation along the keys)
+    pd = 0.1
+    for H2, dh2 in ((2, 64), (8, 16)):
+        Bs, Ss = 2, 512
+        qkv2 = torch.zeros(Bs, Ss, 3 * H2 * dh2, device=dev)
+        qkv2[:, :, 2 * H2 * dh2:] = 1.0
+        lens2 = torch.tensor([Ss, Ss], device=dev)
+        c2 = torch.empty(Bs, Ss, H2 * dh2, device=dev); l2 = torch.empty(Bs, H2, Ss, device=dev)
+        pl2 = ops.attention_planes(Bs, Ss, H2, dh2, dev)
+        ops._call('dx_attention_fwd', qkv2.data_ptr(), lens2.data_ptr(), c2.data_ptr(), l2.data_ptr(), ops._p(pl2), None, Bs, Ss, H2, dh2, pd, 4242,
+                  ops._st())
+        frac = c2.view(Bs, Ss, H2, dh2)[..., 0] * (1 - pd)      # kept fraction per (utterance, query, head)
+        n = frac.numel()
+        assert abs(frac.mean().item() - (1 - pd)) < 4 * (pd * (1 - pd) / (n * Ss)) ** 0.5
+        var_ratio = frac.var().item() / (pd * (1 - pd) / Ss)
+        assert 0.85 < var_ratio < 1.15, var_ratio
 
 
 # ----------------------------------------------------------------------------------------------------------------------

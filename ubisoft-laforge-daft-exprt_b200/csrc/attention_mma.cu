@@ -556,6 +556,15 @@ int prep(const float* src, int ld, int B, int S, int Sp, int NH, int dh, int sca
 
 inline int pad64(int s) { return (s + 63) / 64 * 64; }
 
+bool attn_tc_enabled() {   // DX_ATTN_TC=0 keeps the mma.sync forward (A/B timing, bring-up)
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("DX_ATTN_TC");
+        on = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return on == 1;
+}
+
 void bind_planes(AttnArgs& a, void* planes) {
     uint8_t* base = (uint8_t*)(((uintptr_t)planes + 255) & ~(uintptr_t)255);
     a.Sp = pad64(a.S);
@@ -583,6 +592,7 @@ int attention_fwd_mma(const AttnArgs& a_in, void* planes, cudaStream_t st) {
     const int D = a.H * a.dh;
     int rc = prep(a.qkv, 3 * D, a.B, a.S, a.Sp, 3 * a.H, a.dh, D, rsqrtf((float)a.dh), (__nv_bfloat16*)a.R, (__nv_bfloat16*)a.Tr, st);
     if (rc) return rc;
+    if (attn_tc_enabled() && attention_fwd_tc_supported(a)) return attention_fwd_tc(a, st);   // tcgen05 / TMEM forward
     switch (a.dh) {
         case 16: return launch_fwd_mma<16>(a, st);
         case 32: return launch_fwd_mma<32>(a, st);

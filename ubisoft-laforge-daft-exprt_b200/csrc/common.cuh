@@ -93,14 +93,14 @@ __device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned 
 __device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned long long idx, float p, float inv_keep) {
     return hash_uniform(seed, idx) >= p ? inv_keep : 0.f;
 }
-// Two-level variant for the tensor-core attention kernels (one decision per score, the hot spot of the dh = 16 heads): a fully
-// mixed key per query row (hash_u32, once per row) xor a Weyl term of the key index, then two multiply-xorshift rounds.  The
-// last xorshift of the finaliser is dropped: the unsigned compare is decided by the high bits.  keep <=> x >= p * 2^32.
+// Two-level variant for the tensor-core attention kernels (one decision per score: the per-score ALU work is what bounds them):
+// a fully mixed key per query row (hash_u32, once per row) xor a Weyl term of the key index, then ONE xorshift-multiply round;
+// the unsigned compare is decided by the high bits of the product, which depend on every bit of the input.
+// keep <=> x >= p * 2^32.  (tests: kept fraction, per-row binomial variance, forward/backward mask agreement.)
 __device__ __forceinline__ uint32_t drop_col_term(uint32_t col) { return col * 0x9E3779B1u; }
 __device__ __forceinline__ bool drop_keep(uint32_t row_key, uint32_t col_term, uint32_t thresh) {
     uint32_t x = row_key ^ col_term;
     x ^= x >> 16; x *= 0x85EBCA6Bu;
-    x ^= x >> 13; x *= 0xC2B2AE35u;
     return x >= thresh;
 }
 __device__ __forceinline__ uint32_t drop_threshold(float p) { return __float2uint_rz(fminf(p, 0.99999994f) * 4294967296.f); }

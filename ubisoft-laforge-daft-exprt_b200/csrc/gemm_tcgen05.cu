@@ -759,7 +759,7 @@ EncodeTiledFn get_encode() {
 
 // 3-D tensor (d0 contiguous), box (b0, b1, b2), SWIZZLE_128B (or 64B), zero OOB fill.  esz = 4 (fp32) or 2 (bf16).
 int make_map_3d(CUtensorMap* map, const void* ptr, int esz, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
-                uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, bool swizzle64 = false) {
+                uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, bool swizzle64 = false, bool swizzle32 = false) {
     EncodeTiledFn enc = get_encode();
     DX_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[3] = {d0, d1, d2};
@@ -768,7 +768,8 @@ int make_map_3d(CUtensorMap* map, const void* ptr, int esz, uint64_t d0, uint64_
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                      const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : (swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) esz=%d dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u,%u)",
                (int)r, esz, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
@@ -826,8 +827,17 @@ inline int round8(int x) { return (x + 7) & ~7; }
 
 }  // namespace
 
+bool tma_available() { return get_encode() != nullptr; }
+int make_tma_map_3d(void* map, const void* ptr, int esz, unsigned long long d0, unsigned long long d1, unsigned long long d2,
+                    unsigned long long stride1_bytes, unsigned long long stride2_bytes, unsigned b0, unsigned b1, unsigned b2,
+                    int swizzle_bytes) {
+    return make_map_3d((CUtensorMap*)map, ptr, esz, d0, d1, d2, stride1_bytes, stride2_bytes, b0, b1, b2, swizzle_bytes == 64,
+                       swizzle_bytes == 32);
+}
+
 void set_tc_precision(int tf32) { g_prec = tf32 ? PREC_TF32 : PREC_BF16X3; }
 void set_tc_trace(long long* buf) { g_trace = buf; }
+long long* tc_trace_buffer() { return g_trace; }
 
 int split_activation_planes(const float* x, int ld, void* planes, float* colsum_out, int rows, int C, cudaStream_t st) {
     DX_REQUIRE(C % 8 == 0 && ld % 4 == 0, "split_activation_planes: C=%d ld=%d", C, ld);

@@ -99,6 +99,16 @@ int attention_fwd_mma(const AttnArgs& a, void* planes, cudaStream_t st);
 int attention_bwd_mma(const AttnArgs& a, void* planes, void* scratch, cudaStream_t st);
 size_t attention_planes_bytes(int B, int S, int H, int dh);
 size_t attention_bwd_scratch_bytes(int B, int S, int H, int dh);
+// tcgen05 / TMEM forward (attention_tc.cu): head_dim 64 / 16, operand planes a.R / a.Sp already bound and filled
+bool attention_fwd_tc_supported(const AttnArgs& a);
+int attention_fwd_tc(const AttnArgs& a, cudaStream_t st);
+// cuTensorMapEncodeTiled wrapper (gemm_tcgen05.cu): 3-D tensor, d0 contiguous, zero out-of-bounds fill; esz 2 (bf16) / 4 (fp32);
+// swizzle_bytes in {32, 64, 128}; map = CUtensorMap* (128 bytes, 64-byte aligned)
+bool tma_available();
+long long* tc_trace_buffer();   // dx_debug_set_trace buffer ([4][256] int64) or nullptr
+int make_tma_map_3d(void* map, const void* ptr, int esz, unsigned long long d0, unsigned long long d1, unsigned long long d2,
+                    unsigned long long stride1_bytes, unsigned long long stride2_bytes, unsigned b0, unsigned b1, unsigned b2,
+                    int swizzle_bytes);
 int attention_bwd_prepare(const AttnArgs& a, cudaStream_t st);   // delta + zero dqkv
 int attention_bwd(const AttnArgs& a, cudaStream_t st);
 
