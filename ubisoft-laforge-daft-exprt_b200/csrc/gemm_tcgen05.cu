@@ -96,6 +96,16 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// one lane of the (converged) warp; the same lane every time for the same membermask
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -321,47 +331,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
             }
         }
     } else if (MODE == MODE_HALO && warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(1, TM, TN, 0);
-            int bs = 0, bph = 0, as = 0, aph = 0, it = 0, gk = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const TileCoord t = tile_coord<MODE>(p, tile);
-                if (tile_dead<MODE>(p, t)) continue;
-                const int acc = it & 1, acc_phase = (it >> 1) & 1;
-                ++it;
-                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * TN;
-                uint32_t started = 0;
-                for (int kc = 0; kc < p.k_chunks; ++kc) {
-                    mbar_wait(afull0 + 8 * as, aph);
-                    const uint32_t sa = base + as * HALO_A_STAGE_BYTES;
-                    for (uint32_t tap = 0; tap < 3; ++tap) {
-                        mbar_wait(full0 + 8 * bs, bph);
+        // The whole warp runs the issue loop (warp-uniform control flow keeps descriptors in uniform registers; a divergent
+        // `if (lane == 0)` costs ~12 instructions and a broadcast loop per MMA); one elected lane issues MMAs and commits.
+        constexpr uint32_t idesc = umma_idesc(1, TM, TN, 0);
+        int bs = 0, bph = 0, as = 0, aph = 0, it = 0, gk = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const TileCoord t = tile_coord<MODE>(p, tile);
+            if (tile_dead<MODE>(p, t)) continue;
+            const int acc = it & 1, acc_phase = (it >> 1) & 1;
+            ++it;
+            mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * TN;
+            uint32_t started = 0;
+            for (int kc = 0; kc < p.k_chunks; ++kc) {
+                mbar_wait(afull0 + 8 * as, aph);
+                const uint32_t sa = base + as * HALO_A_STAGE_BYTES;
+                for (uint32_t tap = 0; tap < 3; ++tap) {
+                    mbar_wait(full0 + 8 * bs, bph);
+                    tc_fence_after();
+                    const uint32_t sb = baseB + bs * HALO_B_STAGE_BYTES;
+                    const uint64_t a_hi = umma_desc_k_sw128_rows(sa, tap);
+                    const uint64_t a_lo = umma_desc_k_sw128_rows(sa + A_HALO_BYTES, tap);
+                    const uint64_t b_hi = umma_desc_k_sw128(sb), b_lo = b_hi + (TILE_BYTES >> 4);
+                    if (elect_one()) {
                         if (p.trace && blockIdx.x == 0 && gk < 256) p.trace[1 * 256 + gk] = clock64();
-                        ++gk;
-                        tc_fence_after();
-                        const uint32_t sb = baseB + bs * HALO_B_STAGE_BYTES;
-                        const uint64_t a_hi = umma_desc_k_sw128_rows(sa, tap);
-                        const uint64_t a_lo = umma_desc_k_sw128_rows(sa + A_HALO_BYTES, tap);
-                        const uint64_t b_hi = umma_desc_k_sw128(sb), b_lo = b_hi + (TILE_BYTES >> 4);
 #pragma unroll
                         for (int kk = 0; kk < ((p.debug & 1) ? 0 : 4); ++kk) {
                             umma<PREC>(tmem_d, a_hi + 2 * kk, b_hi + 2 * kk, idesc, started | (uint32_t)kk);
                             umma<PREC>(tmem_d, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1u);
                             umma<PREC>(tmem_d, a_hi + 2 * kk, b_lo + 2 * kk, idesc, 1u);
                         }
-                        started = 1;
                         if (p.debug & 1) mbar_arrive(empty0 + 8 * bs);
                         else umma_commit(empty0 + 8 * bs);
-                        if (++bs == HALO_B_STAGES) { bs = 0; bph ^= 1; }
+                        if (tap == 2) {
+                            if (p.debug & 1) mbar_arrive(aempty0 + 8 * as);
+                            else umma_commit(aempty0 + 8 * as);      // the halo tile is free once all three taps have retired
+                            if (kc == p.k_chunks - 1) {
+                                if (p.debug & 1) mbar_arrive(tfull0 + 8 * acc);
+                                else umma_commit(tfull0 + 8 * acc);
+                            }
+                        }
                     }
-                    if (p.debug & 1) mbar_arrive(aempty0 + 8 * as);
-                    else umma_commit(aempty0 + 8 * as);          // the halo tile is free once all three taps have retired
-                    if (++as == HALO_A_STAGES) { as = 0; aph ^= 1; }
+                    __syncwarp();
+                    ++gk;
+                    started = 1;
+                    if (++bs == HALO_B_STAGES) { bs = 0; bph ^= 1; }
                 }
-                if (p.debug & 1) mbar_arrive(tfull0 + 8 * acc);
-                else umma_commit(tfull0 + 8 * acc);
+                if (++as == HALO_A_STAGES) { as = 0; aph ^= 1; }
             }
         }
     } else if (warp == 0) {
@@ -411,30 +428,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(PREC == PREC_TF32 ? 2 : 1, TM, TN, MODE == MODE_WGRAD ? 1 : 0);
-            // descriptor step per K=16 (bf16) / K=8 (tf32) instruction, in 16-byte units:
-            //   K-major: 32 bytes along the 128-byte row;  MN-major: 16 rows of 128 bytes
-            constexpr uint32_t kstep = MODE == MODE_WGRAD ? (16 * 128) >> 4 : 2;
-            int stage = 0, phase = 0, it = 0, gk = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const TileCoord t = tile_coord<MODE>(p, tile);
-                if (tile_dead<MODE>(p, t)) continue;             // (the accumulator sequence `it` only counts live tiles)
-                const int acc = it & 1, acc_phase = (it >> 1) & 1;
-                ++it;
-                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);     // epilogue has drained this accumulator
+        // whole warp in the loop, one elected lane issues (see MODE_HALO above)
+        constexpr uint32_t idesc = umma_idesc(PREC == PREC_TF32 ? 2 : 1, TM, TN, MODE == MODE_WGRAD ? 1 : 0);
+        // descriptor step per K=16 (bf16) / K=8 (tf32) instruction, in 16-byte units:
+        //   K-major: 32 bytes along the 128-byte row;  MN-major: 16 rows of 128 bytes
+        constexpr uint32_t kstep = MODE == MODE_WGRAD ? (16 * 128) >> 4 : 2;
+        int stage = 0, phase = 0, it = 0, gk = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const TileCoord t = tile_coord<MODE>(p, tile);
+            if (tile_dead<MODE>(p, t)) continue;             // (the accumulator sequence `it` only counts live tiles)
+            const int acc = it & 1, acc_phase = (it >> 1) & 1;
+            ++it;
+            mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);     // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * TN;
+            uint32_t started = 0;
+            for (int k = t.k_begin; k < t.k_end; ++k) {
+                if (k_dead<MODE>(p, k)) continue;
+                mbar_wait(full0 + 8 * stage, phase);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * TN;
-                uint32_t started = 0;
-                for (int k = t.k_begin; k < t.k_end; ++k) {
-                    if (k_dead<MODE>(p, k)) continue;
-                    mbar_wait(full0 + 8 * stage, phase);
+                const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + PLANES * TILE_BYTES;
+                const uint64_t a_hi = MODE == MODE_WGRAD ? umma_desc_mn_sw128(sa) : umma_desc_k_sw128(sa);
+                const uint64_t b_hi = MODE == MODE_WGRAD ? umma_desc_mn_sw128(sb) : umma_desc_k_sw128(sb);
+                if (elect_one()) {
                     if (p.trace && blockIdx.x == 0 && gk < 256) p.trace[1 * 256 + gk] = clock64();
-                    ++gk;
-                    tc_fence_after();
-                    const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + PLANES * TILE_BYTES;
-                    const uint64_t a_hi = MODE == MODE_WGRAD ? umma_desc_mn_sw128(sa) : umma_desc_k_sw128(sa);
-                    const uint64_t b_hi = MODE == MODE_WGRAD ? umma_desc_mn_sw128(sb) : umma_desc_k_sw128(sb);
 #pragma unroll
                     for (int kk = 0; kk < ((p.debug & 1) ? 0 : 4); ++kk) {
                         umma<PREC>(tmem_d, a_hi + kstep * kk, b_hi + kstep * kk, idesc, started | (uint32_t)kk);
@@ -444,14 +461,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
                             umma<PREC>(tmem_d, a_hi + kstep * kk, b_lo + kstep * kk, idesc, 1u);
                         }
                     }
-                    started = 1;
                     if (p.debug & 1) mbar_arrive(empty0 + 8 * stage);
                     else umma_commit(empty0 + 8 * stage);     // frees the smem stage when these MMAs retire
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                ++gk;
+                started = 1;
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one()) {
                 if (p.debug & 1) mbar_arrive(tfull0 + 8 * acc);
                 else umma_commit(tfull0 + 8 * acc);           // accumulator complete -> epilogue
             }
+            __syncwarp();
         }
     } else {
         // epilogue: NUM_EPI_WARPS = 8 warps, two per SM sub-partition so one warp's TMEM / shared-memory / TMA latencies are
