@@ -27,4 +27,20 @@ for (B, S, H, dh, p) in [(32, 1000, 2, 64, 0.1), (32, 1000, 8, 16, 0.1), (32, 10
     ms = sorted(a.elapsed_time(b) for a, b in evs)
     us = 1e3 * sum(ms[:5]) / 5
     fl = 4.0 * float((lens.double() ** 2).sum()) * D   # valid-only algorithmic flops
+    dctx = torch.randn(B, S, D, device=dev)
+    dqkv = torch.empty(B, S, 3 * D, device=dev)
+    scratch = torch.empty(ops.lib().dx_attention_bwd_scratch_bytes(B, S, H, dh), device=dev, dtype=torch.uint8)
+    runb = lambda: ops._call('dx_attention_bwd', qkv.data_ptr(), ops._p(planes), lens.data_ptr(), ctx.data_ptr(), lse.data_ptr(), dctx.data_ptr(),
+                             dqkv.data_ptr(), scratch.data_ptr(), B, S, H, dh, p, 1234, ops._st())
+    for _ in range(3): runb()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); runb(); e1.record(); evs.append((e0, e1))
+    torch.cuda.synchronize()
+    msb = sorted(a.elapsed_time(b) for a, b in evs)
+    usb = 1e3 * sum(msb[:5]) / 5
+    print(f'attention bwd (delta + memset + prep + core) B={B} S={S} H={H} dh={dh} p={p}: {usb:7.1f} us  {2.5 * fl / usb / 1e6:6.1f} TFLOP/s alg  bwd_tc={os.environ.get("DX_ATTN_BWD_TC", "0")}')
     print(f'attention fwd (prep + core) B={B} S={S} H={H} dh={dh} p={p}: {us:7.1f} us  {fl / us / 1e6:6.1f} TFLOP/s alg (valid keys/queries)  tc={os.environ.get("DX_ATTN_TC", "1")}')

@@ -554,6 +554,17 @@ int prep(const float* src, int ld, int B, int S, int Sp, int NH, int dh, int sca
     return check_launch("attn_prep");
 }
 
+// tcgen05 backward: default for head_dim 64 (1.5x the mma.sync kernel at T = 1000); for head_dim 16 the per-score ALU work
+// bounds both and the mma.sync kernel's higher occupancy still wins.  DX_ATTN_BWD_TC=0 / 1 forces mma.sync / tcgen05 for all.
+bool attn_bwd_tc_enabled(int dh) {
+    static int mode = -2;
+    if (mode == -2) {
+        const char* e = getenv("DX_ATTN_BWD_TC");
+        mode = e ? (atoi(e) != 0 ? 1 : 0) : -1;
+    }
+    return mode == 1 || (mode == -1 && dh == 64);
+}
+
 inline int pad64(int s) { return (s + 63) / 64 * 64; }
 
 bool attn_tc_enabled() {   // DX_ATTN_TC=0 keeps the mma.sync forward (A/B timing, bring-up)
@@ -616,6 +627,7 @@ int attention_bwd_mma(const AttnArgs& a_in, void* planes, void* scratch, cudaStr
     if (rc) return rc;
     rc = prep(a.dctx, D, a.B, a.S, a.Sp, a.H, a.dh, 0, 1.f, (__nv_bfloat16*)a.GR, (__nv_bfloat16*)a.GTr, st);
     if (rc) return rc;
+    if (attn_bwd_tc_enabled(a.dh) && attention_bwd_tc_supported(a)) return attention_bwd_tc(a, st);   // tcgen05 / TMEM backward
     switch (a.dh) {
         case 16: return launch_bwd_mma<16>(a, st);
         case 32: return launch_bwd_mma<32>(a, st);

@@ -102,6 +102,9 @@ size_t attention_bwd_scratch_bytes(int B, int S, int H, int dh);
 // tcgen05 / TMEM forward (attention_tc.cu): head_dim 64 / 16, operand planes a.R / a.Sp already bound and filled
 bool attention_fwd_tc_supported(const AttnArgs& a);
 int attention_fwd_tc(const AttnArgs& a, cudaStream_t st);
+// tcgen05 / TMEM backward (attention_bwd_tc.cu): a.R, a.GR (dO planes), a.delta bound and filled, a.dqkv zeroed
+bool attention_bwd_tc_supported(const AttnArgs& a);
+int attention_bwd_tc(const AttnArgs& a, cudaStream_t st);
 // cuTensorMapEncodeTiled wrapper (gemm_tcgen05.cu): 3-D tensor, d0 contiguous, zero out-of-bounds fill; esz 2 (bf16) / 4 (fp32);
 // swizzle_bytes in {32, 64, 128}; map = CUtensorMap* (128 bytes, 64-byte aligned)
 bool tma_available();
