@@ -356,6 +356,305 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_kernel(const __gri
     }
 }
 
+// =====================================================================================================================
+// Pipelined variant (head_dim 16): the query tile is processed as two 64-query halves through TWO S^T / dP^T buffer pairs in
+// TMEM, so the five products of half g and the loads/handshakes around them run while the 16 element-wise warps work on half
+// g + 1 (the serial kernel above pays ~3 barrier round trips per tile, which for dh = 16 is as long as the arithmetic).
+// dQ is still one M = 128 product per query tile (its A operand = both staged halves), drained one half-step later.
+// TMEM columns: buffer u < 2: S^T / P^T [128u, 128u + 64), dP^T / dS^T [128u + 64, 128u + 128); dK 256.., dV 320.., dQ 384...
+// =====================================================================================================================
+template <int DH>
+__global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_r,
+                                                                          const __grid_constant__ CUtensorMap map_g, AbtParams p) {
+    using C = AbtCfg<DH>;
+    static_assert(DH == 16, "pipelined backward: shared-memory budget (two Q / dO stages + dS^T staging) is laid out for head_dim 16");
+    // (a third buffer pair at TMEM columns [256, 384) with the accumulators moved to 384 / 416 / 448 gave wrong products on B200 and
+    // only 6 % more speed: two buffers already cover the handshake latency)
+    constexpr int TB = C::TB, QST = 2, HQ = 64, NBUF = 2;
+    constexpr int COL_DK = C::COL_DK, COL_DV = C::COL_DV, COL_DQ = C::COL_DQ;
+    constexpr uint32_t HALF_BYTES = HQ * C::ROW_BYTES;           // 64 rows of a Q / dO tile
+    extern __shared__ uint8_t abt_smem_raw[];
+    const uint32_t base = (smem_u32(abt_smem_raw) + 1023u) & ~1023u;
+    const uint32_t sK = base, sV = base + 2 * TB;
+    const uint32_t sQG = base + 4 * TB;                           // [stage][Q hi, Q lo, dO hi, dO lo]
+    const uint32_t sDS = sQG + QST * 4 * TB;                      // [plane][64-query chunk][128 keys][128 B]
+    const uint32_t bars = sDS + C::DS_BYTES;
+    const uint32_t kv_full = bars, qg_full0 = bars + 8, qg_empty0 = bars + 32, s_full0 = bars + 56, pds_full0 = bars + 80;
+    const uint32_t dq_full = bars + 104, dq_free = bars + 112, dkv_full = bars + 120;
+    const uint32_t aux0 = bars + 256;
+    const uint32_t tmem_slot = aux0 + C::AUX_BYTES;
+    uint8_t* smem_gen = abt_smem_raw + (base - smem_u32(abt_smem_raw));
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(abt_smem_raw + (tmem_slot - smem_u32(abt_smem_raw)));
+    float* aux = reinterpret_cast<float*>(abt_smem_raw + (aux0 - smem_u32(abt_smem_raw)));
+    uint8_t* ds_gen = smem_gen + (sDS - base);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = blockIdx.x * BT, h = blockIdx.y, b = blockIdx.z;
+    const int D = p.H * DH, ld = 3 * D, NH = 3 * p.H;
+    const int len = min((int)p.lens[b], p.S);
+    if (k0 >= len) return;
+
+    if (threadIdx.x == 0) {
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < QST; ++i) { mbar_init(qg_full0 + 8 * i, 1); mbar_init(qg_empty0 + 8 * i, 1); }
+        for (int i = 0; i < NBUF; ++i) { mbar_init(s_full0 + 8 * i, 1); mbar_init(pds_full0 + 8 * i, ABT_SOFTMAX_WARPS); }
+        mbar_init(dq_full, 1); mbar_init(dq_free, ABT_SOFTMAX_WARPS); mbar_init(dkv_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(ABT_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const int n_q = (len + BT - 1) / BT, n_g = 2 * n_q;
+    const int sl_q = b * NH + h, sl_k = b * NH + p.H + h, sl_v = b * NH + 2 * p.H + h, sl_lo = p.B * NH;
+    const int sl_g = b * p.H + h, sl_glo = p.B * p.H;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(kv_full, 4 * TB);
+            tma_load_3d(sK, &map_r, kv_full, 0, k0, sl_k);
+            tma_load_3d(sK + TB, &map_r, kv_full, 0, k0, sl_lo + sl_k);
+            tma_load_3d(sV, &map_r, kv_full, 0, k0, sl_v);
+            tma_load_3d(sV + TB, &map_r, kv_full, 0, k0, sl_lo + sl_v);
+            int st = 0, ph = 0;
+            for (int i = 0; i < n_q; ++i) {
+                mbar_wait(qg_empty0 + 8 * st, ph ^ 1);
+                const uint32_t s0 = sQG + st * 4 * TB, bar = qg_full0 + 8 * st;
+                mbar_expect_tx(bar, 4 * TB);
+                tma_load_3d(s0, &map_r, bar, 0, i * BT, sl_q);
+                tma_load_3d(s0 + TB, &map_r, bar, 0, i * BT, sl_lo + sl_q);
+                tma_load_3d(s0 + 2 * TB, &map_g, bar, 0, i * BT, sl_g);
+                tma_load_3d(s0 + 3 * TB, &map_g, bar, 0, i * BT, sl_glo + sl_g);
+                if (++st == QST) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc_s = idesc_bf16(BT, HQ, 0, 0);     // S^T, dP^T halves: N = 64 queries
+        constexpr uint32_t idesc_g = idesc_bf16(BT, DH, 0, 1);     // dV, dK: A in TMEM, B MN-major
+        constexpr uint32_t idesc_q = idesc_bf16(BT, DH, 1, 1);     // dQ: A (staging) MN-major, B MN-major
+        const uint64_t kh = bdesc_k<DH>(sK), kl = bdesc_k<DH>(sK + TB), vh = bdesc_k<DH>(sV), vl = bdesc_k<DH>(sV + TB);
+        const uint64_t kmh = bdesc_mn<DH>(sK), kml = bdesc_mn<DH>(sK + TB);
+        const uint64_t dsh = bdesc_ds(sDS), dsl = bdesc_ds(sDS + 2 * 128 * 128);
+        const uint32_t t_dk = tmem_base + COL_DK, t_dv = tmem_base + COL_DV, t_dq = tmem_base + COL_DQ;
+        mbar_wait(kv_full, 0);
+        // S^T_g = K Q_h^T, dP^T_g = V dO_h^T into buffer g & 1 (rows [64 hh, 64 hh + 64) of query tile g >> 1)
+        auto issue_sdp = [&](int g) {
+            const int i = g >> 1, hh = g & 1, stg = i % QST, u = g % NBUF;
+            if (hh == 0) mbar_wait(qg_full0 + 8 * stg, (i / QST) & 1);
+            tc_fence_after();
+            const uint32_t s0 = sQG + stg * 4 * TB + hh * HALF_BYTES;
+            const uint64_t qh = bdesc_k<DH>(s0), ql = bdesc_k<DH>(s0 + TB), gh = bdesc_k<DH>(s0 + 2 * TB), gl = bdesc_k<DH>(s0 + 3 * TB);
+            const uint32_t t_st = tmem_base + u * 128, t_dpt = t_st + 64;
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < C::KS; ++kk) {
+                    umma_ss(t_st, kh + 2 * kk, qh + 2 * kk, idesc_s, kk > 0 ? 1u : 0u);
+                    umma_ss(t_st, kl + 2 * kk, qh + 2 * kk, idesc_s, 1u);
+                    umma_ss(t_st, kh + 2 * kk, ql + 2 * kk, idesc_s, 1u);
+                }
+#pragma unroll
+                for (int kk = 0; kk < C::KS; ++kk) {
+                    umma_ss(t_dpt, vh + 2 * kk, gh + 2 * kk, idesc_s, kk > 0 ? 1u : 0u);
+                    umma_ss(t_dpt, vl + 2 * kk, gh + 2 * kk, idesc_s, 1u);
+                    umma_ss(t_dpt, vh + 2 * kk, gl + 2 * kk, idesc_s, 1u);
+                }
+                umma_commit(s_full0 + 8 * u);
+            }
+            __syncwarp();
+        };
+        issue_sdp(0);
+        issue_sdp(1);
+        if (NBUF > 2 && n_g > 2) issue_sdp(2);
+        for (int g = 0; g < n_g; ++g) {
+            const int i = g >> 1, hh = g & 1, stg = i % QST, u = g % NBUF;
+            mbar_wait(pds_full0 + 8 * u, (g / NBUF) & 1);           // P^T_g, dS^T_g in TMEM (+ dS^T_g staged)
+            if (hh == 1 && i > 0) mbar_wait(dq_free, (i - 1) & 1);  // the previous tile's dQ has been drained
+            tc_fence_after();
+            const uint32_t s0 = sQG + stg * 4 * TB + hh * HALF_BYTES;
+            const uint64_t qmh = bdesc_mn<DH>(s0), qml = bdesc_mn<DH>(s0 + TB), gmh = bdesc_mn<DH>(s0 + 2 * TB), gml = bdesc_mn<DH>(s0 + 3 * TB);
+            const uint32_t t_st = tmem_base + u * 128, t_dpt = t_st + 64;
+            const uint32_t acc0 = g > 0 ? 1u : 0u;
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < HQ / 16; ++kk) {   // K-steps over the 64 queries of this half: pairs (hi | lo) of column group kk
+                    umma_ts(t_dv, t_st + 16 * kk, gmh + C::ROW_KSTEP * kk, idesc_g, kk > 0 ? 1u : acc0);
+                    umma_ts(t_dv, t_st + 16 * kk + 8, gmh + C::ROW_KSTEP * kk, idesc_g, 1u);
+                    umma_ts(t_dv, t_st + 16 * kk, gml + C::ROW_KSTEP * kk, idesc_g, 1u);
+                }
+#pragma unroll
+                for (int kk = 0; kk < HQ / 16; ++kk) {
+                    umma_ts(t_dk, t_dpt + 16 * kk, qmh + C::ROW_KSTEP * kk, idesc_g, kk > 0 ? 1u : acc0);
+                    umma_ts(t_dk, t_dpt + 16 * kk + 8, qmh + C::ROW_KSTEP * kk, idesc_g, 1u);
+                    umma_ts(t_dk, t_dpt + 16 * kk, qml + C::ROW_KSTEP * kk, idesc_g, 1u);
+                }
+                if (hh == 1) {
+                    umma_commit(qg_empty0 + 8 * stg);   // Q / dO of this tile are free once dV and dK retire
+#pragma unroll
+                    for (int kk = 0; kk < BT / 16; ++kk) {   // dQ = dS K over the 128 keys, both staged halves as M = 128
+                        umma_ss(t_dq, dsh + 128 * kk, kmh + C::ROW_KSTEP * kk, idesc_q, kk > 0 ? 1u : 0u);
+                        umma_ss(t_dq, dsl + 128 * kk, kmh + C::ROW_KSTEP * kk, idesc_q, 1u);
+                        umma_ss(t_dq, dsh + 128 * kk, kml + C::ROW_KSTEP * kk, idesc_q, 1u);
+                    }
+                    umma_commit(dq_full);
+                    if (g == n_g - 1) umma_commit(dkv_full);
+                }
+            }
+            __syncwarp();
+            if (g + NBUF < n_g) issue_sdp(g + NBUF);   // into the buffer this half just released (the tensor pipe is in order)
+        }
+    } else {
+        const int quad = warp & 3, cq = (warp - 2) >> 2;
+        const int rl = quad * 32 + lane;
+        const int key = k0 + rl;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const int st_tid = threadIdx.x - 64;
+        const float* lse = p.lse + ((size_t)b * p.H + h) * p.S;
+        const float* delta = p.delta + ((size_t)b * p.H + h) * p.S;
+        float* dbase = p.dqkv + (size_t)b * p.S * ld + h * DH;
+        const unsigned long long seed = dyn_seed(p.seed, p.dyn);
+        const bool drop = p.dropout_p > 0.f;
+        const float inv_keep = drop ? 1.f / (1.f - p.dropout_p) : 1.f;
+        const float keep_prob = drop ? 1.f - p.dropout_p : 1.f;
+        const uint32_t thresh = drop_threshold(p.dropout_p);
+        const unsigned long long bh = ((unsigned long long)b * p.H + h) * (unsigned long long)p.S;
+        const uint32_t kc = drop_col_term((uint32_t)key);
+        const float scale = rsqrtf((float)DH);
+        const bool key_ok = key < len;
+        auto load_aux = [&](int i) {
+            if (st_tid < BT) {
+                float* ax = aux + (i & 1) * 3 * BT;
+                const int q = i * BT + st_tid;
+                ax[st_tid] = q < len ? lse[q] * kLog2eB : 0.f;
+                ax[BT + st_tid] = q < len ? delta[q] * keep_prob : 0.f;
+                reinterpret_cast<uint32_t*>(ax)[2 * BT + st_tid] = drop ? hash_u32(seed, bh + q) : 0u;
+            }
+        };
+        // dQ of query tile i: TMEM lane = query row; vector fp32 reductions (q carries 1/sqrt(dh)); hands the accumulator back first
+        auto drain_dq = [&](int i, bool release) {
+            mbar_wait(dq_full, i & 1);   // (already observed by the staging guard except for the last tile)
+            tc_fence_after();
+            if (DH == 64 || cq == 0) {
+                const int c0 = DH == 64 ? cq * 16 : 0;
+                uint32_t v[16];
+                tmem_ld16(t_lane + COL_DQ + c0, v);
+                tmem_ld_wait16(v);
+                tc_fence_before();
+                __syncwarp();
+                if (release && lane == 0) mbar_arrive(dq_free);
+                const int q = i * BT + rl;
+                if (q < len) {
+                    float* dq = dbase + (size_t)q * ld + c0;
+                    const float sc = scale * inv_keep;
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dq + e), "f"(sc * __uint_as_float(v[e])),
+                                     "f"(sc * __uint_as_float(v[e + 1])), "f"(sc * __uint_as_float(v[e + 2])), "f"(sc * __uint_as_float(v[e + 3]))
+                                     : "memory");
+                }
+            } else {
+                tc_fence_before();
+                __syncwarp();
+                if (release && lane == 0) mbar_arrive(dq_free);
+            }
+        };
+        load_aux(0);
+        for (int g = 0; g < n_g; ++g) {
+            const int i = g >> 1, hh = g & 1, q0 = i * BT;
+            const float* ax = aux + (i & 1) * 3 * BT;
+            if (hh == 0) {
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                if (i + 1 < n_q) load_aux(i + 1);
+            }
+            const int u = g % NBUF;
+            mbar_wait(s_full0 + 8 * u, (g / NBUF) & 1);
+            tc_fence_after();
+            const uint32_t t_st = t_lane + u * 128 + 16 * cq, t_dpt = t_st + 64;
+            uint32_t s[16], gq[16];
+            tmem_ld16(t_st, s);
+            tmem_ld16(t_dpt, gq);
+            tmem_ld_wait16(s);
+            tmem_ld_wait16(gq);
+            const int cbase = 64 * hh + 16 * cq;                   // first query column of this thread within the tile
+            if ((q0 + BT > len) || !key_ok) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    if (!key_ok || q0 + cbase + c >= len) { s[c] = 0xff800000u; gq[c] = 0u; }
+                }
+            }
+            uint32_t pt[16], dst[16];                              // 8 hi pairs | 8 lo pairs
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = cbase + 2 * j;
+                const float2 ls = *reinterpret_cast<const float2*>(ax + c);
+                const float2 dl = *reinterpret_cast<const float2*>(ax + BT + c);
+                const float p0 = ex2(fmaf(__uint_as_float(s[2 * j]), kLog2eB, -ls.x));
+                const float p1 = ex2(fmaf(__uint_as_float(s[2 * j + 1]), kLog2eB, -ls.y));
+                float d0 = __uint_as_float(gq[2 * j]), d1 = __uint_as_float(gq[2 * j + 1]);
+                float pd0 = p0, pd1 = p1;
+                if (drop) {
+                    const uint2 rk = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint32_t*>(ax) + 2 * BT + c);
+                    const bool k0_ = drop_keep(rk.x, kc, thresh), k1_ = drop_keep(rk.y, kc, thresh);
+                    pd0 = k0_ ? p0 : 0.f; pd1 = k1_ ? p1 : 0.f;
+                    d0 = k0_ ? d0 : 0.f; d1 = k1_ ? d1 : 0.f;
+                }
+                split_pair(pd0, pd1, pt[j], pt[8 + j]);
+                split_pair(p0 * (d0 - dl.x), p1 * (d1 - dl.y), dst[j], dst[8 + j]);
+            }
+            tmem_st16(t_st, pt);
+            tmem_st16(t_dpt, dst);
+            if (hh == 0 && i > 0) mbar_wait(dq_full, (i - 1) & 1);   // dQ(i-1) has consumed the staging tile before it is overwritten
+            {   // dS^T staging: row = key, chunk hh (64 queries = 128 B), this thread's 16 queries = units 2 cq, 2 cq + 1
+                uint8_t* rowp = ds_gen + (size_t)hh * 16384 + (size_t)rl * 128;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int unit = (2 * cq + u) ^ (rl & 7);
+                    *reinterpret_cast<uint4*>(rowp + unit * 16) = make_uint4(dst[4 * u], dst[4 * u + 1], dst[4 * u + 2], dst[4 * u + 3]);
+                    *reinterpret_cast<uint4*>(rowp + 32768 + unit * 16) = make_uint4(dst[8 + 4 * u], dst[8 + 4 * u + 1], dst[8 + 4 * u + 2], dst[8 + 4 * u + 3]);
+                }
+            }
+            tmem_st_wait();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pds_full0 + 8 * u);
+            if (hh == 0 && i > 0) drain_dq(i - 1, true);           // one half-step late: its latency hides behind this half's arithmetic
+        }
+        drain_dq(n_q - 1, false);
+        // ---- dK, dV of this key tile ----
+        mbar_wait(dkv_full, 0);
+        tc_fence_after();
+        if (DH == 64 || cq == 0) {
+            const int c0 = DH == 64 ? cq * 16 : 0;
+            uint32_t vk[16], vv[16];
+            tmem_ld16(t_lane + COL_DK + c0, vk);
+            tmem_ld16(t_lane + COL_DV + c0, vv);
+            tmem_ld_wait16(vk);
+            tmem_ld_wait16(vv);
+            if (key_ok) {
+                float* dk = dbase + (size_t)key * ld + D + c0;
+                float* dv = dbase + (size_t)key * ld + 2 * D + c0;
+#pragma unroll
+                for (int e = 0; e < 16; e += 4) {
+                    *reinterpret_cast<float4*>(dk + e) = make_float4(__uint_as_float(vk[e]) * inv_keep, __uint_as_float(vk[e + 1]) * inv_keep,
+                                                                    __uint_as_float(vk[e + 2]) * inv_keep, __uint_as_float(vk[e + 3]) * inv_keep);
+                    *reinterpret_cast<float4*>(dv + e) = make_float4(__uint_as_float(vv[e]) * inv_keep, __uint_as_float(vv[e + 1]) * inv_keep,
+                                                                    __uint_as_float(vv[e + 2]) * inv_keep, __uint_as_float(vv[e + 3]) * inv_keep);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(ABT_TMEM_COLS) : "memory");
+    }
+}
+
 template <int DH>
 int launch_bwd_tc(const AttnArgs& a, cudaStream_t st) {
     using C = AbtCfg<DH>;
@@ -378,6 +677,15 @@ int launch_bwd_tc(const AttnArgs& a, cudaStream_t st) {
     p.B = a.B; p.S = a.S; p.H = a.H; p.Sp = a.Sp; p.dropout_p = a.dropout_p; p.seed = a.seed; p.dyn = a.dyn;
     p.trace = tc_trace_buffer();
     dim3 grid(ceil_div(a.S, BT), a.H, a.B);
+    if constexpr (DH == 16) {
+        static bool configured_pipe = false;
+        if (!configured_pipe) {
+            DX_CUDA(cudaFuncSetAttribute(attn_bwd_tc_pipe_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            configured_pipe = true;
+        }
+        attn_bwd_tc_pipe_kernel<DH><<<grid, ABT_THREADS, smem, st>>>(map_r, map_g, p);
+        return check_launch("attn_bwd_tc_pipe");
+    }
     attn_bwd_tc_kernel<DH><<<grid, ABT_THREADS, smem, st>>>(map_r, map_g, p);
     return check_launch("attn_bwd_tc");
 }

@@ -554,15 +554,16 @@ int prep(const float* src, int ld, int B, int S, int Sp, int NH, int dh, int sca
     return check_launch("attn_prep");
 }
 
-// tcgen05 backward: default for head_dim 64 (1.5x the mma.sync kernel at T = 1000); for head_dim 16 the per-score ALU work
-// bounds both and the mma.sync kernel's higher occupancy still wins.  DX_ATTN_BWD_TC=0 / 1 forces mma.sync / tcgen05 for all.
+// tcgen05 backward: default (head_dim 64: serial kernel, 1.5x the mma.sync one at T = 1000; head_dim 16: pipelined half-tile
+// kernel, 1.1x).  DX_ATTN_BWD_TC=0 forces the mma.sync kernel.
 bool attn_bwd_tc_enabled(int dh) {
     static int mode = -2;
     if (mode == -2) {
         const char* e = getenv("DX_ATTN_BWD_TC");
         mode = e ? (atoi(e) != 0 ? 1 : 0) : -1;
     }
-    return mode == 1 || (mode == -1 && dh == 64);
+    (void)dh;
+    return mode != 0;
 }
 
 inline int pad64(int s) { return (s + 63) / 64 * 64; }
