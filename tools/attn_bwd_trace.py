@@ -29,6 +29,14 @@ for (H, dh, p) in [(2, 64, 0.1), (8, 16, 0.1)]:
     t0 = int(t[t > 0].min())
     rows = [[int(a) - t0 for a in t[r] if a > 0] for r in range(4)]
     n = len(rows[0])
+    if dh == 16:   # pipelined kernel: per half-step {begin, scores available, arithmetic done, published}
+        print(f'H={H} dh={dh}: {n} half-steps (pipelined kernel)')
+        print('  half-step period     ', [rows[0][i + 1] - rows[0][i] for i in range(n - 1)])
+        print('  bar.sync + wait S^T  ', [rows[1][i] - rows[0][i] for i in range(n)])
+        print('  ld + arithmetic + st ', [rows[2][i] - rows[1][i] for i in range(n)])
+        print('  guard + staging + pub', [rows[3][i] - rows[2][i] for i in range(n)])
+        print('  drain (after publish)', [rows[0][i + 1] - rows[3][i] for i in range(n - 1)])
+        continue
     print(f'H={H} dh={dh}: {n} query tiles')
     print('  s_full seen          ', rows[0])
     print('  wait for S^T/dP^T    ', [rows[0][i] - rows[3][i - 1] for i in range(1, n)])

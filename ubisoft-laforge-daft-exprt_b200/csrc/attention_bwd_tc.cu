@@ -20,6 +20,8 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_ptx.cuh"
@@ -47,8 +49,9 @@ struct AbtCfg {
     static constexpr uint32_t ROW_KSTEP = (16 * ROW_BYTES) >> 4;        // 16 rows per K-step of an MN-major (dh-contiguous) tile
     static constexpr int QSTAGES = DH == 64 ? 1 : 2;                    // Q / dO ring
     static constexpr int DS_BYTES = 2 * 2 * 128 * 128;                  // dS^T staging: [plane][query chunk of 64][128 keys][128 B]
+    static constexpr int DS_BUFS = DH == 64 ? 1 : 2;                    // the pipelined dh = 16 kernel double-buffers it (no wait on dQ before refilling)
     static constexpr int AUX_BYTES = 2 * 3 * BT * 4;                    // lse*log2e, delta, dropout row keys; double buffered
-    static constexpr int SMEM_BYTES = (4 + 4 * QSTAGES) * TB + DS_BYTES + 256 + AUX_BYTES + 64 + 1024;
+    static constexpr int SMEM_BYTES = (4 + 4 * QSTAGES) * TB + DS_BUFS * DS_BYTES + 256 + AUX_BYTES + 64 + 1024;
     static constexpr int COL_DK = 256, COL_DV = 320, COL_DQ = 384;
 };
 template <int DH>
@@ -229,21 +232,31 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_kernel(const __gri
 
         const float keep_prob = drop ? 1.f - p.dropout_p : 1.f;
         // per-query vectors of a tile (lse * log2e, delta * keep_prob, dropout row key): written one tile ahead into the other buffer
-        auto load_aux = [&](int i) {
+        // the global loads are issued one tile ahead into registers (fetch) and only written to shared memory after this tile's
+        // arithmetic (store): their latency never sits in front of the score loads
+        float n_lse = 0.f, n_delta = 0.f;
+        auto fetch_aux = [&](int i) {
             if (st_tid < BT) {
-                float* ax = aux + (i & 1) * 3 * BT;
                 const int q = i * BT + st_tid;
-                ax[st_tid] = q < len ? lse[q] * kLog2eB : 0.f;
-                ax[BT + st_tid] = q < len ? delta[q] * keep_prob : 0.f;
-                reinterpret_cast<uint32_t*>(ax)[2 * BT + st_tid] = drop ? hash_u32(seed, bh + q) : 0u;
+                n_lse = q < len ? lse[q] : 0.f;
+                n_delta = q < len ? delta[q] : 0.f;
             }
         };
-        load_aux(0);
+        auto store_aux = [&](int i) {
+            if (st_tid < BT) {
+                float* ax = aux + (i & 1) * 3 * BT;
+                ax[st_tid] = n_lse * kLog2eB;
+                ax[BT + st_tid] = n_delta * keep_prob;
+                reinterpret_cast<uint32_t*>(ax)[2 * BT + st_tid] = drop ? hash_u32(seed, bh + i * BT + st_tid) : 0u;
+            }
+        };
+        fetch_aux(0);
+        store_aux(0);
         for (int i = 0; i < n_q; ++i) {
             const int q0 = i * BT;
             const float* ax = aux + (i & 1) * 3 * BT;             // [lse*log2e | delta*keep | row key]
             asm volatile("bar.sync 1, 512;" ::: "memory");        // this tile's vectors are visible; the other buffer is free
-            if (i + 1 < n_q) load_aux(i + 1);
+            if (i + 1 < n_q) fetch_aux(i + 1);
             mbar_wait(s_full, i & 1);
             if (tr && i < 256) p.trace[i] = clock64();
             tc_fence_after();
@@ -295,6 +308,7 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_kernel(const __gri
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(pds_full);
+            if (i + 1 < n_q) store_aux(i + 1);
             if (tr && i < 256) p.trace[256 + i] = clock64();
             // ---- drain dQ of this query tile: TMEM lane = query row, vector fp32 reductions (q carries 1/sqrt(dh)) ----
             mbar_wait(dq_full, i & 1);
@@ -378,7 +392,7 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_pipe_kernel(const 
     const uint32_t sK = base, sV = base + 2 * TB;
     const uint32_t sQG = base + 4 * TB;                           // [stage][Q hi, Q lo, dO hi, dO lo]
     const uint32_t sDS = sQG + QST * 4 * TB;                      // [plane][64-query chunk][128 keys][128 B]
-    const uint32_t bars = sDS + C::DS_BYTES;
+    const uint32_t bars = sDS + C::DS_BUFS * C::DS_BYTES;     // dS^T staging is double buffered by query tile parity
     const uint32_t kv_full = bars, qg_full0 = bars + 8, qg_empty0 = bars + 32, s_full0 = bars + 56, pds_full0 = bars + 80;
     const uint32_t dq_full = bars + 104, dq_free = bars + 112, dkv_full = bars + 120;
     const uint32_t aux0 = bars + 256;
@@ -438,7 +452,6 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_pipe_kernel(const 
         constexpr uint32_t idesc_q = idesc_bf16(BT, DH, 1, 1);     // dQ: A (staging) MN-major, B MN-major
         const uint64_t kh = bdesc_k<DH>(sK), kl = bdesc_k<DH>(sK + TB), vh = bdesc_k<DH>(sV), vl = bdesc_k<DH>(sV + TB);
         const uint64_t kmh = bdesc_mn<DH>(sK), kml = bdesc_mn<DH>(sK + TB);
-        const uint64_t dsh = bdesc_ds(sDS), dsl = bdesc_ds(sDS + 2 * 128 * 128);
         const uint32_t t_dk = tmem_base + COL_DK, t_dv = tmem_base + COL_DV, t_dq = tmem_base + COL_DQ;
         mbar_wait(kv_full, 0);
         // S^T_g = K Q_h^T, dP^T_g = V dO_h^T into buffer g & 1 (rows [64 hh, 64 hh + 64) of query tile g >> 1)
@@ -493,6 +506,7 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_pipe_kernel(const 
                 }
                 if (hh == 1) {
                     umma_commit(qg_empty0 + 8 * stg);   // Q / dO of this tile are free once dV and dK retire
+                    const uint64_t dsh = bdesc_ds(sDS + (i & 1) * C::DS_BYTES), dsl = bdesc_ds(sDS + (i & 1) * C::DS_BYTES + 2 * 128 * 128);
 #pragma unroll
                     for (int kk = 0; kk < BT / 16; ++kk) {   // dQ = dS K over the 128 keys, both staged halves as M = 128
                         umma_ss(t_dq, dsh + 128 * kk, kmh + C::ROW_KSTEP * kk, idesc_q, kk > 0 ? 1u : 0u);
@@ -524,13 +538,20 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_pipe_kernel(const 
         const uint32_t kc = drop_col_term((uint32_t)key);
         const float scale = rsqrtf((float)DH);
         const bool key_ok = key < len;
-        auto load_aux = [&](int i) {
+        float n_lse = 0.f, n_delta = 0.f;   // next tile's per-query values: fetched at half 0, stored to smem after half 1
+        auto fetch_aux = [&](int i) {
+            if (st_tid < BT) {
+                const int q = i * BT + st_tid;
+                n_lse = q < len ? lse[q] : 0.f;
+                n_delta = q < len ? delta[q] : 0.f;
+            }
+        };
+        auto store_aux = [&](int i) {
             if (st_tid < BT) {
                 float* ax = aux + (i & 1) * 3 * BT;
-                const int q = i * BT + st_tid;
-                ax[st_tid] = q < len ? lse[q] * kLog2eB : 0.f;
-                ax[BT + st_tid] = q < len ? delta[q] * keep_prob : 0.f;
-                reinterpret_cast<uint32_t*>(ax)[2 * BT + st_tid] = drop ? hash_u32(seed, bh + q) : 0u;
+                ax[st_tid] = n_lse * kLog2eB;
+                ax[BT + st_tid] = n_delta * keep_prob;
+                reinterpret_cast<uint32_t*>(ax)[2 * BT + st_tid] = drop ? hash_u32(seed, bh + i * BT + st_tid) : 0u;
             }
         };
         // dQ of query tile i: TMEM lane = query row; vector fp32 reductions (q carries 1/sqrt(dh)); hands the accumulator back first
@@ -561,16 +582,20 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_pipe_kernel(const 
                 if (release && lane == 0) mbar_arrive(dq_free);
             }
         };
-        load_aux(0);
+        const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
+        fetch_aux(0);
+        store_aux(0);
         for (int g = 0; g < n_g; ++g) {
             const int i = g >> 1, hh = g & 1, q0 = i * BT;
+            if (tr && g < 256) p.trace[g] = clock64();                       // half-step begins
             const float* ax = aux + (i & 1) * 3 * BT;
             if (hh == 0) {
                 asm volatile("bar.sync 1, 512;" ::: "memory");
-                if (i + 1 < n_q) load_aux(i + 1);
+                if (i + 1 < n_q) fetch_aux(i + 1);
             }
             const int u = g % NBUF;
             mbar_wait(s_full0 + 8 * u, (g / NBUF) & 1);
+            if (tr && g < 256) p.trace[256 + g] = clock64();                 // S^T / dP^T of this half available
             tc_fence_after();
             const uint32_t t_st = t_lane + u * 128 + 16 * cq, t_dpt = t_st + 64;
             uint32_t s[16], gq[16];
@@ -606,9 +631,10 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_pipe_kernel(const 
             }
             tmem_st16(t_st, pt);
             tmem_st16(t_dpt, dst);
-            if (hh == 0 && i > 0) mbar_wait(dq_full, (i - 1) & 1);   // dQ(i-1) has consumed the staging tile before it is overwritten
-            {   // dS^T staging: row = key, chunk hh (64 queries = 128 B), this thread's 16 queries = units 2 cq, 2 cq + 1
-                uint8_t* rowp = ds_gen + (size_t)hh * 16384 + (size_t)rl * 128;
+            if (tr && g < 256) p.trace[512 + g] = clock64();                 // arithmetic done
+            {   // dS^T staging (buffer i & 1: its previous reader dQ(i-2) retired before dQ(i-1), whose completion this thread saw
+                // when it drained it): row = key, chunk hh (64 queries = 128 B), this thread's 16 queries = units 2 cq, 2 cq + 1
+                uint8_t* rowp = ds_gen + (size_t)(i & 1) * C::DS_BYTES + (size_t)hh * 16384 + (size_t)rl * 128;
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int unit = (2 * cq + u) ^ (rl & 7);
@@ -621,7 +647,9 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_pipe_kernel(const 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(pds_full0 + 8 * u);
-            if (hh == 0 && i > 0) drain_dq(i - 1, true);           // one half-step late: its latency hides behind this half's arithmetic
+            if (tr && g < 256) p.trace[768 + g] = clock64();                 // published
+            if (hh == 1 && i + 1 < n_q) store_aux(i + 1);
+            if (hh == 1 && i > 0) drain_dq(i - 1, true);           // a whole tile late: dQ(i-1) retired long ago, nothing to wait for
         }
         drain_dq(n_q - 1, false);
         // ---- dK, dV of this key tile ----
