@@ -39,6 +39,12 @@ uint64_t dx_launch_count(void);
 int dx_device_check(void);
 int dx_set_gemm_backend(int backend);
 int dx_get_gemm_backend(void);
+/* Attention kernels used with the tensor-core GEMM backends: DX_ATTENTION_TCGEN05 (default: tcgen05/TMEM/TMA forward and
+ * backward for head_dim 64 and 16) or DX_ATTENTION_MMA_SYNC (the mma.sync flash kernels; always used for head_dim 32).
+ * Initial value from the environment (DX_ATTN_TC=0 / DX_ATTN_BWD_TC=0 select mma.sync for forward / backward). */
+#define DX_ATTENTION_MMA_SYNC 0
+#define DX_ATTENTION_TCGEN05 1
+int dx_set_attention_backend(int forward_backend, int backward_backend);
 /* bring-up aid: device buffer of 4*256 int64 receiving clock64() traces of CTA 0 of the tensor-core GEMM (NULL = off) */
 int dx_debug_set_trace(void* buf);
 

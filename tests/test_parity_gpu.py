@@ -572,3 +572,49 @@ def test_gemm_plane_handover(dev):
     assert torch.equal(a, a2)
     cs = ops.colsum_planes(aP, B * S, cout)
     np.testing.assert_allclose(cs.cpu().numpy(), a.view(-1, cout).sum(0).cpu().numpy(), rtol=1e-4, atol=1e-3)
+    # column sums taken by the GEMM epilogue itself (warp transpose-reduce + atomics) == column sums of the stored output,
+    # for both output forms (fp32 + planes, planes only) and with the padding skip active
+    a3, aP3, cs3 = ops.conv_gemm(None, wqp, None, B, S, relu_src_hi=yP, x_planes=dyP, emit_planes=True, want_colsum=True)
+    np.testing.assert_allclose(cs3.cpu().numpy(), a3.view(-1, cout).double().sum(0).cpu().numpy(), rtol=1e-4, atol=1e-3)
+    _, hP, cs4 = ops.conv_gemm(None, wp, b, B, S, relu=True, x_planes=xP, lens=lens, halo=1, emit_planes=True, want_y=False, want_colsum=True)
+    np.testing.assert_allclose(cs4.cpu().numpy(), y.view(-1, cout).double().sum(0).cpu().numpy(), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('cfg', [(2, 300, 2, 64, 0.0), (2, 300, 8, 16, 0.0), (3, 129, 2, 64, 0.2), (3, 129, 8, 16, 0.2), (1, 1000, 8, 16, 0.1),
+                                 (2, 64, 2, 64, 0.1)])
+def test_attention_tcgen05_matches_mma_sync(dev, cfg):
+    """The tcgen05/TMEM attention kernels (default) against the mma.sync flash kernels on the same inputs, same dropout seed (one
+    shared mask hash): forward context / log-sum-exp and all three gradients, incl. utterances of length 1 and ragged lengths that
+    end inside a 128-row tile."""
+    from daft_exprt_b200 import cabi, ops
+    set_backend('bf16x3')
+    B, S, H, dh, p = cfg
+    D = H * dh
+    g = torch.Generator().manual_seed(S + H)
+    qkv = torch.randn(B, S, 3 * D, generator=g).to(dev)
+    lens = torch.randint(1, S + 1, (B,), generator=g)
+    lens[0], lens[-1] = S, (1 if B > 1 else S)
+    lens = lens.to(dev)
+    dctx = (torch.randn(B, S, D, generator=g) * (torch.arange(S)[None, :] < lens.cpu()[:, None])[:, :, None]).to(dev)
+    res = []
+    for backend in (cabi.DX_ATTENTION_TCGEN05, cabi.DX_ATTENTION_MMA_SYNC):
+        ops._call('dx_set_attention_backend', backend, backend)
+        ctx = torch.empty(B, S, D, device=dev); lse = torch.empty(B, H, S, device=dev)
+        planes = ops.attention_planes(B, S, H, dh, dev)
+        ctxP = torch.empty(2, B * S, D, device=dev, dtype=torch.bfloat16)
+        ops._call('dx_attention_fwd', qkv.data_ptr(), lens.data_ptr(), ctx.data_ptr(), lse.data_ptr(), ops._p(planes), ops._p(ctxP), B, S, H, dh,
+                  p, 99, ops._st())
+        dqkv = torch.empty(B, S, 3 * D, device=dev)
+        scratch = torch.empty(ops.lib().dx_attention_bwd_scratch_bytes(B, S, H, dh), device=dev, dtype=torch.uint8)
+        ops._call('dx_attention_bwd', qkv.data_ptr(), ops._p(planes), lens.data_ptr(), ctx.data_ptr(), lse.data_ptr(), dctx.data_ptr(),
+                  dqkv.data_ptr(), scratch.data_ptr(), B, S, H, dh, p, 99, ops._st())
+        res.append((ctx.clone(), lse.clone(), dqkv.clone(), ctxP.float().sum(0).view(B, S, D)))
+    ops._call('dx_set_attention_backend', cabi.DX_ATTENTION_TCGEN05, cabi.DX_ATTENTION_TCGEN05)
+    (c1, l1, g1, p1), (c0, l0, g0, p0) = res
+    assert torch.isfinite(c1).all() and torch.isfinite(g1).all()
+    assert scale_rel_err(c1, c0) < 2e-5 and scale_rel_err(l1, l0) < 2e-5 and scale_rel_err(p1, c1) < 2e-5
+    for i, name in enumerate(('dq', 'dk', 'dv')):
+        assert scale_rel_err(g1[..., i * D:(i + 1) * D], g0[..., i * D:(i + 1) * D]) < 1e-4, name
+    valid = (torch.arange(S, device=dev)[None, :] < lens[:, None])
+    assert float(c1[~valid].abs().max() if (~valid).any() else 0.0) == 0.0 and float(g1[~valid].abs().max() if (~valid).any() else 0.0) == 0.0

@@ -15,6 +15,8 @@ LIB_PATH = os.path.join(_HERE, 'libdaftexprt_b200.so')
 DX_GEMM_FP32_CUDA_CORES = 0
 DX_GEMM_TCGEN05_TF32 = 1
 DX_GEMM_TCGEN05_BF16X3 = 2
+DX_ATTENTION_MMA_SYNC = 0
+DX_ATTENTION_TCGEN05 = 1
 
 _lib = None
 _protos = None

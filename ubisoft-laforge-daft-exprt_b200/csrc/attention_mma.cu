@@ -554,27 +554,23 @@ int prep(const float* src, int ld, int B, int S, int Sp, int NH, int dh, int sca
     return check_launch("attn_prep");
 }
 
-// tcgen05 backward: default (head_dim 64: serial kernel, 1.5x the mma.sync one at T = 1000; head_dim 16: pipelined half-tile
-// kernel, 1.1x).  DX_ATTN_BWD_TC=0 forces the mma.sync kernel.
+// attention backend selection (dx_set_attention_backend; initial values from DX_ATTN_TC / DX_ATTN_BWD_TC, default tcgen05)
+int g_attn_fwd_tc = -1, g_attn_bwd_tc = -1;
+int env_flag(const char* name) {
+    const char* e = getenv(name);
+    return (e && atoi(e) == 0) ? 0 : 1;
+}
 bool attn_bwd_tc_enabled(int dh) {
-    static int mode = -2;
-    if (mode == -2) {
-        const char* e = getenv("DX_ATTN_BWD_TC");
-        mode = e ? (atoi(e) != 0 ? 1 : 0) : -1;
-    }
     (void)dh;
-    return mode != 0;
+    if (g_attn_bwd_tc < 0) g_attn_bwd_tc = env_flag("DX_ATTN_BWD_TC");
+    return g_attn_bwd_tc == 1;
 }
 
 inline int pad64(int s) { return (s + 63) / 64 * 64; }
 
-bool attn_tc_enabled() {   // DX_ATTN_TC=0 keeps the mma.sync forward (A/B timing, bring-up)
-    static int on = -1;
-    if (on < 0) {
-        const char* e = getenv("DX_ATTN_TC");
-        on = (e && atoi(e) == 0) ? 0 : 1;
-    }
-    return on == 1;
+bool attn_tc_enabled() {
+    if (g_attn_fwd_tc < 0) g_attn_fwd_tc = env_flag("DX_ATTN_TC");
+    return g_attn_fwd_tc == 1;
 }
 
 void bind_planes(AttnArgs& a, void* planes) {
@@ -585,6 +581,11 @@ void bind_planes(AttnArgs& a, void* planes) {
 }
 
 }  // namespace
+
+void set_attention_backend(int fwd_tc, int bwd_tc) {
+    g_attn_fwd_tc = fwd_tc;
+    g_attn_bwd_tc = bwd_tc;
+}
 
 bool attention_mma_supported(const AttnArgs& a) {
     return (a.dh == 16 || a.dh == 32 || a.dh == 64) && ((a.H * a.dh) % 64 == 0);

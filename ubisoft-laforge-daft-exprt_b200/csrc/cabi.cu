@@ -68,6 +68,12 @@ int dx_set_gemm_backend(int backend) {
 }
 int dx_get_gemm_backend(void) { return g_backend; }
 int dx_debug_set_trace(void* buf) { set_tc_trace((long long*)buf); return DX_OK; }
+int dx_set_attention_backend(int forward_backend, int backward_backend) {
+    DX_REQUIRE((forward_backend == 0 || forward_backend == 1) && (backward_backend == 0 || backward_backend == 1),
+               "dx_set_attention_backend: backends must be DX_ATTENTION_MMA_SYNC (0) or DX_ATTENTION_TCGEN05 (1)");
+    set_attention_backend(forward_backend, backward_backend);
+    return DX_OK;
+}
 
 int dx_pack_conv_weight(const float* w, float* fwd, float* dgrad, void* fwd_planes, void* dgrad_planes, int Cout, int Cin, int KW,
                         int round_tf32, void* stream) {

@@ -102,6 +102,7 @@ size_t attention_bwd_scratch_bytes(int B, int S, int H, int dh);
 // tcgen05 / TMEM forward (attention_tc.cu): head_dim 64 / 16, operand planes a.R / a.Sp already bound and filled
 bool attention_fwd_tc_supported(const AttnArgs& a);
 int attention_fwd_tc(const AttnArgs& a, cudaStream_t st);
+void set_attention_backend(int fwd_tc, int bwd_tc);   // 1 = tcgen05, 0 = mma.sync (attention_mma.cu)
 // tcgen05 / TMEM backward (attention_bwd_tc.cu): a.R, a.GR (dO planes), a.delta bound and filled, a.dqkv zeroed
 bool attention_bwd_tc_supported(const AttnArgs& a);
 int attention_bwd_tc(const AttnArgs& a, cudaStream_t st);
