@@ -202,6 +202,7 @@ def main():
     if rank != 0:
         entry.build()
     from daft_exprt_b200 import cabi, ops, synthetic
+    from daft_exprt_b200.data import BatchPrefetcher
     from daft_exprt_b200.ddp import FlatAdam, FlatGradSync, broadcast_parameters
     from daft_exprt_b200.graph import GraphedTrainStep
     from daft_exprt_b200.hparams import default_hparams
@@ -241,10 +242,19 @@ def main():
         opt.step()
         return out
 
+    prefetch = BatchPrefetcher(model, local_rank)   # the package's loader-side helper: parse_batch one step ahead on a side stream
+
     def step_e2e(it):
-        inp, tgt, _ = model.parse_batch(local_rank, host_batch)       # 11 H2D copies from pinned memory
+        # every step copies ITS inputs from pinned host memory (11 H2D copies = model.parse_batch) and reads its loss back; the
+        # copies of step i+1 are issued while step i computes, exactly as a training loop over a DataLoader would use the helper
+        if prefetch.pending is None:
+            prefetch.submit(host_batch)
+        inp, tgt, _ = prefetch.get()
         if graphed is not None:
-            return graphed.step(inp, tgt, it).tolist()                # ONE D2H read of the 8 loss floats
+            out = graphed.step(inp, tgt, it)                          # replay enqueued first ...
+            prefetch.submit(host_batch)                               # ... then the next step's copies, while the GPU is busy
+            return out.tolist()                                       # ONE D2H read of the 8 loss floats
+        prefetch.submit(host_batch)
         opt.zero_grad()
         loss, terms = crit(model(inp), tgt, it)                        # ONE D2H read of the 8 loss floats
         loss.backward()
@@ -255,6 +265,7 @@ def main():
     def timed(fn, steps, warmup):
         for i in range(warmup):
             fn(i)
+        prefetch.drop()   # nothing copied before the timed region is consumed inside it
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

@@ -618,3 +618,20 @@ def test_attention_tcgen05_matches_mma_sync(dev, cfg):
         assert scale_rel_err(g1[..., i * D:(i + 1) * D], g0[..., i * D:(i + 1) * D]) < 1e-4, name
     valid = (torch.arange(S, device=dev)[None, :] < lens[:, None])
     assert float(c1[~valid].abs().max() if (~valid).any() else 0.0) == 0.0 and float(g1[~valid].abs().max() if (~valid).any() else 0.0) == 0.0
+
+
+def test_batch_prefetcher_matches_parse_batch(dev):
+    """data.BatchPrefetcher (parse_batch one step ahead on a side stream) hands over exactly what parse_batch returns."""
+    from daft_exprt_b200.data import BatchPrefetcher
+    from daft_exprt_b200.hparams import default_hparams
+    from daft_exprt_b200.model import DaftExprt
+    model = DaftExprt(default_hparams(n_speakers=12)).to(dev)
+    host = tuple(t.pin_memory() for t in synthetic.make_batch(4, 30, 120, 11, seed=9)) + (['d'] * 4, ['f'] * 4)
+    ref_in, ref_tg, ref_ids = model.parse_batch(0, host)
+    pre = BatchPrefetcher(model, 0)
+    for _ in range(3):
+        pre.submit(host)
+        inp, tgt, ids = pre.get()
+        assert ids == ref_ids
+        for a, b in zip(tuple(inp) + tuple(tgt), tuple(ref_in) + tuple(ref_tg)):
+            assert a.dtype == b.dtype and torch.equal(a, b)
