@@ -114,7 +114,9 @@ class GraphedTrainStep:
     def _capture(self, inputs, targets):
         c = _Captured()
         c.inputs = tuple(t.clone() for t in inputs)
-        c.targets = tuple(t.clone() for t in targets)
+        # targets that ARE input tensors (parse_batch returns the same objects, model.py:750) share the static buffer: one copy per step
+        alias = self._alias(inputs, targets)
+        c.targets = tuple(c.inputs[a] if a >= 0 else t.clone() for a, t in zip(alias, targets))
         lib = cabi.load()
         # warm-up on a side stream (lazy kernel attributes, allocator pools, weight packs), parameters restored afterwards
         backup = (self.opt.flat_p.clone(), self.opt.m.clone(), self.opt.v.clone(), self.opt.step_count)
@@ -149,8 +151,13 @@ class GraphedTrainStep:
         return c
 
     # ------------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _alias(inputs, targets):
+        ptrs = {t.data_ptr(): i for i, t in enumerate(inputs)}
+        return tuple(ptrs.get(t.data_ptr(), -1) if t.numel() else -1 for t in targets)
+
     def step(self, inputs, targets, iteration):
-        key = tuple(tuple(t.shape) for t in tuple(inputs) + tuple(targets))
+        key = tuple(tuple(t.shape) for t in tuple(inputs) + tuple(targets)) + self._alias(inputs, targets)
         self.state.register(True)
         try:
             c = self.cache.get(key)
@@ -161,9 +168,14 @@ class GraphedTrainStep:
                     self.cache.popitem(last=False)
             else:
                 self.cache.move_to_end(key)
+            dsts, srcs, seen = [], [], set()
             for dst, src in zip(c.inputs + c.targets, tuple(inputs) + tuple(targets)):
-                if dst.data_ptr() != src.data_ptr():
-                    dst.copy_(src, non_blocking=True)
+                if dst.data_ptr() != src.data_ptr() and dst.data_ptr() not in seen:
+                    seen.add(dst.data_ptr())
+                    dsts.append(dst)
+                    srcs.append(src)
+            if dsts:
+                torch._foreach_copy_(dsts, srcs)   # a few multi-tensor launches instead of one per tensor
             self._push_state(iteration)
             c.graph_a.replay()
             if c.graph_b is not None:
@@ -177,5 +189,5 @@ class GraphedTrainStep:
 
     def static_batch(self, inputs, targets):
         """The graph's own input buffers for this shape (None before the first step): fill them directly to skip the copy."""
-        c = self.cache.get(tuple(tuple(t.shape) for t in tuple(inputs) + tuple(targets)))
+        c = self.cache.get(tuple(tuple(t.shape) for t in tuple(inputs) + tuple(targets)) + self._alias(inputs, targets))
         return (c.inputs, c.targets) if c is not None else None
