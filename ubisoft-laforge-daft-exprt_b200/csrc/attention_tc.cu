@@ -34,9 +34,13 @@ namespace {
 using namespace tcptx;
 
 constexpr int TQ = 128, TKEY = 128;
-constexpr int ATC_SOFTMAX_WARPS = 16;                  // 4 TMEM lane quarters x 4 column quarters
-constexpr int ATC_THREADS = 64 + 32 * ATC_SOFTMAX_WARPS;   // + TMA warp, MMA warp
-constexpr int ATC_TMEM_COLS = 512;
+// Two shapes of the same kernel:
+//   NBUF = 2 score buffers, NSW = 16 softmax warps (thread = row x 32-key quarter), all 512 TMEM columns, one CTA per SM  (dh = 64)
+//   NBUF = 1 score buffer,  NSW = 8 softmax warps (thread = row x 64-key half), 256 TMEM columns, TWO CTAs per SM       (dh = 16):
+//            the small K/V tiles leave room for a second CTA, whose softmax arithmetic fills this one's max pass, prologue,
+//            epilogue and the gaps between consecutive CTAs (the per-score ALU work is the bound for dh = 16)
+template <int NSW> constexpr int atc_threads() { return 64 + 32 * NSW; }   // + TMA warp, MMA warp
+template <int NBUF> constexpr int atc_tmem_cols() { return NBUF == 2 ? 512 : 256; }
 constexpr float kLog2e = 1.4426950408889634f;
 
 template <int DH>
@@ -51,7 +55,6 @@ struct AtcCfg {
     static constexpr int K_STAGES = DH == 64 ? 3 : 6, V_STAGES = DH == 64 ? 2 : 4;
     static constexpr int SMEM_TILES = 2 + 2 * K_STAGES + 2 * V_STAGES;   // Q, K ring, V ring; hi|lo planes each
     static constexpr int SMEM_BYTES = SMEM_TILES * TILE_BYTES + 256 + 4 * TQ * 4 + 64 + 1024;   // + barriers + max/sum exchange
-    static constexpr int O_COL0 = 256;
 };
 // K-major tile (rows x dh): 8-row groups SBO apart
 template <int DH>
@@ -83,9 +86,16 @@ struct AtcParams {
     long long* trace;        // optional [4][256] clock64 trace of block (0,0,0): softmax warp 2 lane 0 (rows 0-2), MMA thread (row 3)
 };
 
-template <int DH>
-__global__ void __launch_bounds__(ATC_THREADS, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_r, AtcParams p) {
+template <int DH, int NBUF, int NSW>
+__global__ void __launch_bounds__(atc_threads<NSW>(), NBUF == 1 ? 2 : 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_r, AtcParams p) {
     using C = AtcCfg<DH>;
+    constexpr int NCG = NSW / 4;             // column groups of a 128-key tile
+    constexpr int CPT = 4 / NCG;             // 32-column chunks per thread
+    constexpr int O_COL0 = NBUF * TKEY;      // O accumulator behind the score buffer(s)
+    constexpr int ATC_TMEM_COLS = atc_tmem_cols<NBUF>();
+    constexpr int ATC_SOFTMAX_WARPS = NSW;
+    static_assert(NBUF == 2 || DH == 16, "the single-buffer / two-CTA shape is sized for head_dim 16");
     constexpr int TB = C::TILE_BYTES, KST = C::K_STAGES, VST = C::V_STAGES;
     extern __shared__ uint8_t atc_smem_raw[];
     const uint32_t base = (smem_u32(atc_smem_raw) + 1023u) & ~1023u;
@@ -199,7 +209,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attn_fwd_tc_kernel(const __gri
         auto issue_s = [&](int t) {
             mbar_wait(k_full0 + 8 * ks, kph);
             tc_fence_after();
-            const uint32_t tmem_s = tmem_base + (t & 1) * TKEY;
+            const uint32_t tmem_s = tmem_base + (t % NBUF) * TKEY;
             const uint64_t kh = desc_k<DH>(sK + (ks * 2 + 0) * TB), kl = desc_k<DH>(sK + (ks * 2 + 1) * TB);
             if (elect_one()) {
 #pragma unroll
@@ -208,7 +218,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attn_fwd_tc_kernel(const __gri
                     umma_ss(tmem_s, ql + 2 * kk, kh + 2 * kk, idesc_s, 1u);
                     umma_ss(tmem_s, qh + 2 * kk, kl + 2 * kk, idesc_s, 1u);
                 }
-                umma_commit(s_full0 + 8 * (t & 1));
+                umma_commit(s_full0 + 8 * (t % NBUF));
                 umma_commit(k_empty0 + 8 * ks);
                 if (tr && t < 256) p.trace[3 * 256 + t] = clock64();
             }
@@ -217,10 +227,10 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attn_fwd_tc_kernel(const __gri
         };
         mbar_wait(q_full, 0);
         issue_s(0);
-        if (n_steps > 1) issue_s(1);
+        if (NBUF > 1 && n_steps > 1) issue_s(1);
         uint32_t sfree_cnt0 = 0, sfree_cnt1 = 0, pfull_cnt0 = 0, pfull_cnt1 = 0;
         for (int t = 0; t < n_steps; ++t) {
-            const int buf = t & 1;
+            const int buf = t % NBUF;
             if (t < n_tiles) {   // pass A: the softmax warps have read S(t): its buffer may take S(t + 2)
                 const uint32_t par = (buf ? sfree_cnt1 : sfree_cnt0) & 1;
                 if (buf) ++sfree_cnt1; else ++sfree_cnt0;
@@ -233,7 +243,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attn_fwd_tc_kernel(const __gri
                 mbar_wait(v_full0 + 8 * vs, vph);
                 tc_fence_after();
                 const uint64_t vh = desc_mn<DH>(sV + (vs * 2 + 0) * TB), vl = desc_mn<DH>(sV + (vs * 2 + 1) * TB);
-                const uint32_t tmem_o = tmem_base + C::O_COL0, tmem_p = tmem_base + buf * TKEY;
+                const uint32_t tmem_o = tmem_base + O_COL0, tmem_p = tmem_base + buf * TKEY;
                 const uint32_t acc0 = t > n_tiles ? 1u : 0u;
                 if (elect_one()) {
 #pragma unroll
@@ -248,7 +258,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attn_fwd_tc_kernel(const __gri
                 __syncwarp();
                 if (++vs == VST) { vs = 0; vph ^= 1; }
             }
-            if (t + 2 < n_steps) issue_s(t + 2);   // (the tensor pipe is in order: it runs after the P V that read this buffer)
+            if (t + NBUF < n_steps) issue_s(t + NBUF);   // (the tensor pipe is in order: it runs after the P V that read this buffer)
         }
         if (elect_one()) umma_commit(o_full);
         __syncwarp();
@@ -263,32 +273,35 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attn_fwd_tc_kernel(const __gri
         const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         for (int t = 0; t < n_tiles; ++t) {
-            const int buf = t & 1;
-            mbar_wait(s_full0 + 8 * buf, (t >> 1) & 1);
+            const int buf = t % NBUF;
+            mbar_wait(s_full0 + 8 * buf, (t / NBUF) & 1);
             if (tr) p.trace[t] = clock64();
             tc_fence_after();
-            uint32_t v[32];
-            tmem_ld32(t_lane + buf * TKEY + 32 * cq, v);
-            tmem_ld_wait32(v);
+            uint32_t v[32 * CPT];
+#pragma unroll
+            for (int cc = 0; cc < CPT; ++cc) tmem_ld32(t_lane + buf * TKEY + 32 * (cq * CPT + cc), v + 32 * cc);
+#pragma unroll
+            for (int cc = 0; cc < CPT; ++cc) tmem_ld_wait32(v + 32 * cc);
             if (tr) p.trace[256 + t] = clock64();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_free0 + 8 * buf);
             if ((t + 1) * TKEY > len) {
-                const int key0 = t * TKEY + 32 * cq;
+                const int key0 = t * TKEY + 32 * cq * CPT;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], key0 + i < len ? __uint_as_float(v[i]) : -INFINITY);
+                for (int i = 0; i < 32 * CPT; ++i) m4[i & 3] = fmaxf(m4[i & 3], key0 + i < len ? __uint_as_float(v[i]) : -INFINITY);
             } else {
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) m4[(i >> 1) & 3] = fmaxf(m4[(i >> 1) & 3], fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+                for (int i = 0; i < 32 * CPT; i += 2) m4[(i >> 1) & 3] = fmaxf(m4[(i >> 1) & 3], fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
             }
             if (tr) p.trace[512 + t] = clock64();
         }
         float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         xch[cq * TQ + rl] = m;
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        m = fmaxf(fmaxf(xch[rl], xch[TQ + rl]), fmaxf(xch[2 * TQ + rl], xch[3 * TQ + rl]));   // finite: key 0 is always valid
-        asm volatile("bar.sync 1, 512;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * NSW) : "memory");
+#pragma unroll
+        for (int c = 0; c < NCG; ++c) m = fmaxf(m, xch[c * TQ + rl]);   // finite: key 0 is always valid
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * NSW) : "memory");
         // ---- pass B: P = exp(S - m) in place, row sums ----
         const unsigned long long seed = dyn_seed(p.seed, p.dyn);
         const bool drop = p.dropout_p > 0.f;
@@ -297,16 +310,18 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attn_fwd_tc_kernel(const __gri
         const float m2 = m * kLog2e;
         float l0 = 0.f, l1 = 0.f;
         for (int t = n_tiles; t < n_steps; ++t) {
-            const int buf = t & 1, j = t - n_tiles;
-            mbar_wait(s_full0 + 8 * buf, (t >> 1) & 1);
+            const int buf = t % NBUF, j = t - n_tiles;
+            mbar_wait(s_full0 + 8 * buf, (t / NBUF) & 1);
             if (tr) p.trace[t] = clock64();
             tc_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < CPT; ++cc) {
             uint32_t v[32], o[32];
-            const uint32_t taddr = t_lane + buf * TKEY + 32 * cq;
+            const uint32_t taddr = t_lane + buf * TKEY + 32 * (cq * CPT + cc);
             tmem_ld32(taddr, v);
             tmem_ld_wait32(v);
             if (tr) p.trace[256 + t] = clock64();
-            const int key0 = j * TKEY + 32 * cq;
+            const int key0 = j * TKEY + 32 * (cq * CPT + cc);
             if ((j + 1) * TKEY > len) {   // last tile: keys >= len score -inf (a separate, rarely taken pre-pass keeps the hot loop unpredicated)
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
@@ -324,6 +339,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attn_fwd_tc_kernel(const __gri
                 split_pair(p0, p1, o[i], o[16 + i]);
             }
             tmem_st32(taddr, o);
+            }   // cc
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -331,8 +347,10 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attn_fwd_tc_kernel(const __gri
             if (tr) p.trace[512 + t] = clock64();
         }
         xch[cq * TQ + rl] = l0 + l1;
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        const float l = (xch[rl] + xch[TQ + rl]) + (xch[2 * TQ + rl] + xch[3 * TQ + rl]);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * NSW) : "memory");
+        float l = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCG; ++c) l += xch[c * TQ + rl];
         // ---- epilogue: O / l -> ctx (+ operand planes), lse; the column quarters split the head dimension ----
         mbar_wait(o_full, 0);
         tc_fence_after();
@@ -342,7 +360,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attn_fwd_tc_kernel(const __gri
         if (DH == 64 || cq == 0) {
             const int c0 = DH == 64 ? cq * 16 : 0;
             uint32_t v[16];
-            tmem_ld16(t_lane + C::O_COL0 + c0, v);
+            tmem_ld16(t_lane + O_COL0 + c0, v);
             tmem_ld_wait16(v);
             if (r < p.S) {
                 float f[16];
@@ -382,14 +400,16 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attn_fwd_tc_kernel(const __gri
     }
 }
 
-template <int DH>
+template <int DH, int NBUF, int NSW>
 int launch_fwd_tc(const AttnArgs& a, cudaStream_t st) {
     using C = AtcCfg<DH>;
-    // one CTA per SM (the kernel owns all 512 TMEM columns): request more than half of the shared memory
-    const int smem = C::SMEM_BYTES > 120 * 1024 ? C::SMEM_BYTES : 120 * 1024;
+    // NBUF = 2: one CTA per SM (the kernel owns all 512 TMEM columns): request more than half of the shared memory.
+    // NBUF = 1: two CTAs per SM (256 TMEM columns each): request what is needed (< half).
+    const int smem = NBUF == 2 ? (C::SMEM_BYTES > 120 * 1024 ? C::SMEM_BYTES : 120 * 1024) : C::SMEM_BYTES;
+    static_assert(NBUF == 2 || C::SMEM_BYTES <= 110 * 1024, "two CTAs per SM need at most half of the shared memory each");
     static bool configured = false;
     if (!configured) {
-        DX_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DX_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, NBUF, NSW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     CUtensorMap map;
@@ -403,7 +423,7 @@ int launch_fwd_tc(const AttnArgs& a, cudaStream_t st) {
     p.trace = tc_trace_buffer();
     p.cta_trace = getenv("DX_ATTN_CTA_TRACE") != nullptr;
     dim3 grid(ceil_div(a.S, TQ), a.H, a.B);
-    attn_fwd_tc_kernel<DH><<<grid, ATC_THREADS, smem, st>>>(map, p);
+    attn_fwd_tc_kernel<DH, NBUF, NSW><<<grid, atc_threads<NSW>(), smem, st>>>(map, p);
     return check_launch("attn_fwd_tc");
 }
 
@@ -415,8 +435,12 @@ bool attention_fwd_tc_supported(const AttnArgs& a) {
 
 // a.R / a.Sp must be bound (attention_mma.cu: bind_planes + prep)
 int attention_fwd_tc(const AttnArgs& a, cudaStream_t st) {
-    if (a.dh == 64) return launch_fwd_tc<64>(a, st);
-    if (a.dh == 16) return launch_fwd_tc<16>(a, st);
+    if (a.dh == 64) return launch_fwd_tc<64, 2, 16>(a, st);
+    if (a.dh == 16) {
+        static int two = -1;   // DX_ATTN_FWD_2CTA=0: the one-CTA-per-SM shape for head_dim 16 as well (A/B timing)
+        if (two < 0) { const char* e = getenv("DX_ATTN_FWD_2CTA"); two = (e && atoi(e) == 0) ? 0 : 1; }
+        return two ? launch_fwd_tc<16, 1, 8>(a, st) : launch_fwd_tc<16, 2, 16>(a, st);
+    }
     set_last_error("attention_fwd_tc: unsupported head_dim %d", a.dh);
     return DX_ERR_UNSUPPORTED;
 }
