@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_kernel(const __gri
     const uint32_t sDS = sQG + QST * 4 * TB;                      // [plane][chunk][128 keys][128 B]
     const uint32_t bars = sDS + C::DS_BYTES;
     const uint32_t kv_full = bars, qg_full0 = bars + 8, qg_empty0 = bars + 24, s_full = bars + 40, pds_full = bars + 48;
-    const uint32_t dq_full = bars + 56, dq_free = bars + 64, dkv_full = bars + 72;
+    const uint32_t dq_full = bars + 56, dq_free = bars + 64, dkv_full = bars + 72, k_ready = bars + 80;
     const uint32_t aux0 = bars + 256;                             // float/u32 [2 buffers][3][128]
     const uint32_t tmem_slot = aux0 + C::AUX_BYTES;
     uint8_t* smem_gen = abt_smem_raw + (base - smem_u32(abt_smem_raw));
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_kernel(const __gri
         mbar_init(kv_full, 1);
         for (int i = 0; i < QST; ++i) { mbar_init(qg_full0 + 8 * i, 1); mbar_init(qg_empty0 + 8 * i, 1); }
         mbar_init(s_full, 1); mbar_init(pds_full, ABT_SOFTMAX_WARPS);
-        mbar_init(dq_full, 1); mbar_init(dq_free, ABT_SOFTMAX_WARPS); mbar_init(dkv_full, 1);
+        mbar_init(dq_full, 1); mbar_init(dq_free, ABT_SOFTMAX_WARPS); mbar_init(dkv_full, 1); mbar_init(k_ready, ABT_SOFTMAX_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_kernel(const __gri
         const uint64_t dsh = bdesc_ds(sDS), dsl = bdesc_ds(sDS + 2 * 128 * 128);
         const uint32_t t_st = tmem_base, t_dpt = tmem_base + BT, t_dk = tmem_base + C::COL_DK, t_dv = tmem_base + C::COL_DV,
                        t_dq = tmem_base + C::COL_DQ;
-        mbar_wait(kv_full, 0);
+        mbar_wait(k_ready, 0);   // K, V landed and the K rows of padded keys are zeroed
         int st = 0, ph = 0;
         for (int i = 0; i < n_q; ++i) {
             mbar_wait(qg_full0 + 8 * st, ph);
@@ -230,6 +230,20 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_kernel(const __gri
         const bool key_ok = key < len;
         const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
 
+        // padded keys (rows >= len of this utterance, only in its last key tile): zero their K rows (both planes) once, so that
+        // whatever their dS^T rows hold adds nothing to dQ = dS K; generic-proxy writes -> proxy fence -> the MMA warp's k_ready
+        mbar_wait(kv_full, 0);
+        if (!key_ok && cq == 0) {
+#pragma unroll
+            for (int c = 0; c < C::ROW_BYTES; c += 16) {
+                *reinterpret_cast<uint4*>(smem_gen + (sK - base) + (size_t)rl * C::ROW_BYTES + c) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(smem_gen + (sK - base) + C::TB + (size_t)rl * C::ROW_BYTES + c) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(k_ready);
+
         const float keep_prob = drop ? 1.f - p.dropout_p : 1.f;
         // per-query vectors of a tile (lse * log2e, delta * keep_prob, dropout row key): written one tile ahead into the other buffer
         // the global loads are issued one tile ahead into registers (fetch) and only written to shared memory after this tile's
@@ -245,7 +259,8 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_kernel(const __gri
         auto store_aux = [&](int i) {
             if (st_tid < BT) {
                 float* ax = aux + (i & 1) * 3 * BT;
-                ax[st_tid] = n_lse * kLog2eB;
+                // padded queries: lse = +inf makes P = exp2(S - inf) = 0 (and with it dS) without any per-score select
+                ax[st_tid] = i * BT + st_tid < len ? n_lse * kLog2eB : INFINITY;
                 ax[BT + st_tid] = n_delta * keep_prob;
                 reinterpret_cast<uint32_t*>(ax)[2 * BT + st_tid] = drop ? hash_u32(seed, bh + i * BT + st_tid) : 0u;
             }
@@ -265,13 +280,9 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_kernel(const __gri
             tmem_ld32(t_lane + BT + 32 * cq, g);
             tmem_ld_wait32(s);
             tmem_ld_wait32(g);
-            if ((q0 + BT > len) || !key_ok) {   // edge tiles only: padded keys / queries get P = 0 (score -inf) and dP = 0
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    if (!key_ok || q0 + 32 * cq + c >= len) { s[c] = 0xff800000u; g[c] = 0u; }
-                }
-            }
             // in place: s <- P^T pairs (hi | lo), g <- dS^T pairs (hi | lo); both WITHOUT the 1/keep factor (dK, dV, dQ are scaled once)
+            // no per-score masking: padded queries carry lse = +inf (P = 0), padded keys have their K rows zeroed in shared memory
+            // (their dS^T rows then add nothing to dQ, and their dK / dV rows are never stored)
             uint32_t pt[32], dst[32];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -394,7 +405,7 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_pipe_kernel(const 
     const uint32_t sDS = sQG + QST * 4 * TB;                      // [plane][64-query chunk][128 keys][128 B]
     const uint32_t bars = sDS + C::DS_BUFS * C::DS_BYTES;     // dS^T staging is double buffered by query tile parity
     const uint32_t kv_full = bars, qg_full0 = bars + 8, qg_empty0 = bars + 32, s_full0 = bars + 56, pds_full0 = bars + 80;
-    const uint32_t dq_full = bars + 104, dq_free = bars + 112, dkv_full = bars + 120;
+    const uint32_t dq_full = bars + 104, dq_free = bars + 112, dkv_full = bars + 120, k_ready = bars + 128;
     const uint32_t aux0 = bars + 256;
     const uint32_t tmem_slot = aux0 + C::AUX_BYTES;
     uint8_t* smem_gen = abt_smem_raw + (base - smem_u32(abt_smem_raw));
@@ -412,7 +423,7 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_pipe_kernel(const 
         mbar_init(kv_full, 1);
         for (int i = 0; i < QST; ++i) { mbar_init(qg_full0 + 8 * i, 1); mbar_init(qg_empty0 + 8 * i, 1); }
         for (int i = 0; i < NBUF; ++i) { mbar_init(s_full0 + 8 * i, 1); mbar_init(pds_full0 + 8 * i, ABT_SOFTMAX_WARPS); }
-        mbar_init(dq_full, 1); mbar_init(dq_free, ABT_SOFTMAX_WARPS); mbar_init(dkv_full, 1);
+        mbar_init(dq_full, 1); mbar_init(dq_free, ABT_SOFTMAX_WARPS); mbar_init(dkv_full, 1); mbar_init(k_ready, ABT_SOFTMAX_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -453,7 +464,7 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_pipe_kernel(const 
         const uint64_t kh = bdesc_k<DH>(sK), kl = bdesc_k<DH>(sK + TB), vh = bdesc_k<DH>(sV), vl = bdesc_k<DH>(sV + TB);
         const uint64_t kmh = bdesc_mn<DH>(sK), kml = bdesc_mn<DH>(sK + TB);
         const uint32_t t_dk = tmem_base + COL_DK, t_dv = tmem_base + COL_DV, t_dq = tmem_base + COL_DQ;
-        mbar_wait(kv_full, 0);
+        mbar_wait(k_ready, 0);   // K, V landed and the K rows of padded keys are zeroed
         // S^T_g = K Q_h^T, dP^T_g = V dO_h^T into buffer g & 1 (rows [64 hh, 64 hh + 64) of query tile g >> 1)
         auto issue_sdp = [&](int g) {
             const int i = g >> 1, hh = g & 1, stg = i % QST, u = g % NBUF;
@@ -538,6 +549,20 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_pipe_kernel(const 
         const uint32_t kc = drop_col_term((uint32_t)key);
         const float scale = rsqrtf((float)DH);
         const bool key_ok = key < len;
+
+        // padded keys (rows >= len of this utterance, only in its last key tile): zero their K rows (both planes) once, so that
+        // whatever their dS^T rows hold adds nothing to dQ = dS K; generic-proxy writes -> proxy fence -> the MMA warp's k_ready
+        mbar_wait(kv_full, 0);
+        if (!key_ok && cq == 0) {
+#pragma unroll
+            for (int c = 0; c < C::ROW_BYTES; c += 16) {
+                *reinterpret_cast<uint4*>(smem_gen + (sK - base) + (size_t)rl * C::ROW_BYTES + c) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(smem_gen + (sK - base) + C::TB + (size_t)rl * C::ROW_BYTES + c) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(k_ready);
         float n_lse = 0.f, n_delta = 0.f;   // next tile's per-query values: fetched at half 0, stored to smem after half 1
         auto fetch_aux = [&](int i) {
             if (st_tid < BT) {
@@ -549,7 +574,8 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_pipe_kernel(const 
         auto store_aux = [&](int i) {
             if (st_tid < BT) {
                 float* ax = aux + (i & 1) * 3 * BT;
-                ax[st_tid] = n_lse * kLog2eB;
+                // padded queries: lse = +inf makes P = exp2(S - inf) = 0 (and with it dS) without any per-score select
+                ax[st_tid] = i * BT + st_tid < len ? n_lse * kLog2eB : INFINITY;
                 ax[BT + st_tid] = n_delta * keep_prob;
                 reinterpret_cast<uint32_t*>(ax)[2 * BT + st_tid] = drop ? hash_u32(seed, bh + i * BT + st_tid) : 0u;
             }
@@ -604,13 +630,8 @@ __global__ void __launch_bounds__(ABT_THREADS, 1) attn_bwd_tc_pipe_kernel(const 
             tmem_ld_wait16(s);
             tmem_ld_wait16(gq);
             const int cbase = 64 * hh + 16 * cq;                   // first query column of this thread within the tile
-            if ((q0 + BT > len) || !key_ok) {
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    if (!key_ok || q0 + cbase + c >= len) { s[c] = 0xff800000u; gq[c] = 0u; }
-                }
-            }
             uint32_t pt[16], dst[16];                              // 8 hi pairs | 8 lo pairs
+            // no per-score masking: padded queries carry lse = +inf (P = 0), padded keys have their K rows zeroed in shared memory
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int c = cbase + 2 * j;
