@@ -131,7 +131,7 @@ int dx_ln_fwd(const float* a, const float* res, const float* ln_w, const float* 
               uint64_t seed_in, float p_out, uint64_t seed_out, void* stream);
 /* relu_src (nullable, [B,S,D]): dv/da are multiplied by (relu_src > 0) — the ReLU that feeds the LN in the pre-net/predictor.
  * dv = grad wrt v (== grad wrt res); da (nullable) = grad wrt a when p_in > 0; dln_w/dln_b [D]; dfilm [B,2D] nullable.
- * g_planes / g_colsum (nullable, D in {128, 256} only): the gradient that leaves through `a` (da when p_in > 0, else dv) as
+ * g_planes / g_colsum (nullable): the gradient that leaves through `a` (da when p_in > 0, else dv) as
  * bf16 hi|lo operand planes [2][B*S][D] and its column sums [D] (= bias gradient of the GEMM that produced a). */
 int dx_ln_bwd(const float* dy, const float* xhat, const float* rstd, const float* ln_w, const float* ln_b, const float* film,
               int film_stride, const int64_t* lens, const float* relu_src, float* dv, float* da, float* dln_w, float* dln_b, float* dfilm,

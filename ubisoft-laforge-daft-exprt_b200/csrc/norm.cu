@@ -8,6 +8,7 @@
 //   * pre-net / predictor        dropout(LN(relu(conv)))  (ReLU is done in the GEMM epilogue)  model.py:341-363, :528-543
 // HBM-bound: algorithmic bytes per row = (2 reads + 2 writes) * D * 4.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -111,80 +112,11 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(LnArgs p) {
     }
 }
 
-// grad wrt v:  g = dy * mask * drop_out * film_gamma * w ;  dv = rstd * (g - mean(g) - xhat * mean(g * xhat))
-template <int VPT>
-__global__ void __launch_bounds__(256) ln_bwd_dx_kernel(LnArgs p) {
-    const unsigned long long seed_in = dyn_seed(p.seed_in, p.dyn), seed_out = dyn_seed(p.seed_out, p.dyn);
-    (void)seed_in; (void)seed_out;
-    constexpr int D = 32 * VPT, NV = VPT / 4;
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int R = p.B * p.S;
-    if (row >= R) return;
-    const int b = row / p.S, s = row - b * p.S;
-    const bool masked = p.lens && s >= (int)p.lens[b];
-    float* dvrow = p.dv + (size_t)row * D;
-    float* darow = p.da ? p.da + (size_t)row * D : nullptr;
-    if (masked) {
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const int c = (j * 32 + lane) * 4;
-            *reinterpret_cast<float4*>(dvrow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (darow) *reinterpret_cast<float4*>(darow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        return;
-    }
-    const float inv_keep_out = p.p_out > 0.f ? 1.f / (1.f - p.p_out) : 1.f;
-    const float inv_keep_in = p.p_in > 0.f ? 1.f / (1.f - p.p_in) : 1.f;
-    float g[VPT], h[VPT];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        const int c = (j * 32 + lane) * 4;
-        const float4 d = *reinterpret_cast<const float4*>(p.dy + (size_t)row * D + c);
-        const float4 hh = *reinterpret_cast<const float4*>(p.xhat + (size_t)row * D + c);
-        const float4 w = *reinterpret_cast<const float4*>(p.ln_w + c);
-        float dv[4] = {d.x, d.y, d.z, d.w};
-        const float wv[4] = {w.x, w.y, w.z, w.w};
-        h[j * 4 + 0] = hh.x; h[j * 4 + 1] = hh.y; h[j * 4 + 2] = hh.z; h[j * 4 + 3] = hh.w;
-        if (p.p_out > 0.f) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) dv[e] *= dropout_scale(seed_out, (unsigned long long)row * D + c + e, p.p_out, inv_keep_out);
-        }
-        if (p.film) {
-            const float4 fg = *reinterpret_cast<const float4*>(p.film + (size_t)b * p.film_stride + c);
-            dv[0] *= fg.x; dv[1] *= fg.y; dv[2] *= fg.z; dv[3] *= fg.w;
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            g[j * 4 + e] = dv[e] * wv[e];
-            s1 += g[j * 4 + e];
-            s2 += g[j * 4 + e] * h[j * 4 + e];
-        }
-    }
-    const float c1 = warp_sum(s1) * (1.f / D), c2 = warp_sum(s2) * (1.f / D);
-    const float rstd = p.rstd[row];
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        const int c = (j * 32 + lane) * 4;
-        float o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = rstd * (g[j * 4 + e] - c1 - h[j * 4 + e] * c2);
-        if (p.relu_src) {
-            const float4 rs = *reinterpret_cast<const float4*>(p.relu_src + (size_t)row * D + c);
-            o[0] = rs.x > 0.f ? o[0] : 0.f; o[1] = rs.y > 0.f ? o[1] : 0.f; o[2] = rs.z > 0.f ? o[2] : 0.f; o[3] = rs.w > 0.f ? o[3] : 0.f;
-        }
-        *reinterpret_cast<float4*>(dvrow + c) = make_float4(o[0], o[1], o[2], o[3]);
-        if (darow) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] *= dropout_scale(seed_in, (unsigned long long)row * D + c + e, p.p_in, inv_keep_in);
-            *reinterpret_cast<float4*>(darow + c) = make_float4(o[0], o[1], o[2], o[3]);
-        }
-    }
-}
+// Backward.  grad wrt v:  g = dy * mask * drop_out * film_gamma * w ;  dv = rstd * (g - mean(g) - xhat * mean(g * xhat));
+// column reductions: dln_w[c] = sum_r q * xhat, dln_b[c] = sum_r q with q = dy * mask * drop_out * film_gamma;
+// dfilm_gamma[b][c] = sum_s e * drop_out(xhat * w + b), dfilm_beta[b][c] = sum_s e with e = dy * mask.
 
-
-// Fused backward for D <= 256: grad wrt v / a (as above) AND the column reductions of ln_bwd_param_kernel AND (optionally) the
+// Fused backward for D <= 256: grad wrt v / a AND the column reductions (parameters, FiLM) AND (optionally) the
 // bf16 hi|lo operand planes + column sums (= bias gradient of the producing GEMM) of the gradient that leaves through `a`.
 // Block = 8 warps over `rpb` consecutive rows of ONE utterance (grid (ceil(S/rpb), B)); a warp walks rows w, w+8, ...; each
 // lane keeps its columns' partial sums in registers; one shared-memory pass + fp32 atomics per block at the end.
@@ -310,44 +242,120 @@ __global__ void __launch_bounds__(256) ln_bwd_fused_kernel(LnArgs p, int rpb) {
     flush(ac, p.g_colsum);
 }
 
-// Column reductions: dln_w[c] += sum_r q*xhat, dln_b[c] += sum_r q  with q = dy*mask*drop_out*film_gamma;
-// dfilm_gamma[b][c] += sum_s e*drop_out(xhat*w+b), dfilm_beta[b][c] += sum_s e  with e = dy*mask.
-// Block = 32 columns x 8 row lanes over a row chunk inside one utterance; cross-block accumulation with fp32 atomics.
-__global__ void __launch_bounds__(256) ln_bwd_param_kernel(LnArgs p, int rows_per_chunk) {
+// Fused backward for D = 1024 (pre-net): same outputs as ln_bwd_fused_kernel, organised the other way round because a lane
+// cannot keep 32 columns x 3 running sums in registers.  Block = 8 warps over `rpb` rows of ONE utterance; WARP w owns the
+// column slice [128 w, 128 w + 128) of every row (a lane 4 consecutive columns, so its column sums stay in registers), rows are
+// processed eight at a time: slice partial sums of the two LayerNorm statistics -> shared memory -> row totals -> outputs.
+constexpr int LNW_ROWS = 8;
+__global__ void __launch_bounds__(256) ln_bwd_fused_wide_kernel(LnArgs p, int rpb) {
     const unsigned long long seed_in = dyn_seed(p.seed_in, p.dyn), seed_out = dyn_seed(p.seed_out, p.dyn);
     (void)seed_in; (void)seed_out;
-    __shared__ float sm[4][8][33];
-    const int D = p.D;
-    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cl, b = blockIdx.z;
+    constexpr int D = 1024;
+    __shared__ float part[2][LNW_ROWS][8];    // [statistic][row][warp slice]
+    __shared__ float tot[2][LNW_ROWS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int R = p.B * p.S;
     const int len = p.lens ? min((int)p.lens[b], p.S) : p.S;
-    const int s0 = blockIdx.y * rows_per_chunk, s1 = min(len, s0 + rows_per_chunk);
+    const int s_begin = blockIdx.x * rpb, s_end = min(p.S, s_begin + rpb);
+    const int c = warp * 128 + lane * 4;      // this lane's 4 columns
     const float inv_keep_out = p.p_out > 0.f ? 1.f / (1.f - p.p_out) : 1.f;
-    float aw = 0.f, ab = 0.f, ag = 0.f, abe = 0.f;
-    if (c < D) {
-        const float w = p.ln_w[c], bb = p.ln_b[c];
-        const float fg = p.film ? p.film[(size_t)b * p.film_stride + c] : 1.f;
-        for (int s = s0 + rl; s < s1; s += 8) {
-            const size_t i = ((size_t)b * p.S + s) * D + c;
-            const float e = p.dy[i];
-            const float dm = p.p_out > 0.f ? dropout_scale(seed_out, i, p.p_out, inv_keep_out) : 1.f;
-            const float h = p.xhat[i];
-            ag += e * dm * (h * w + bb);
-            abe += e;
-            const float q = e * fg * dm;
-            aw += q * h;
-            ab += q;
-        }
+    const float inv_keep_in = p.p_in > 0.f ? 1.f / (1.f - p.p_in) : 1.f;
+    const float4 w4 = *reinterpret_cast<const float4*>(p.ln_w + c);
+    const float4 b4 = *reinterpret_cast<const float4*>(p.ln_b + c);
+    const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+    float fg[4] = {1.f, 1.f, 1.f, 1.f};
+    if (p.film) {
+        const float4 f4 = *reinterpret_cast<const float4*>(p.film + (size_t)b * p.film_stride + c);
+        fg[0] = f4.x; fg[1] = f4.y; fg[2] = f4.z; fg[3] = f4.w;
     }
-    sm[0][rl][cl] = aw; sm[1][rl][cl] = ab; sm[2][rl][cl] = ag; sm[3][rl][cl] = abe;
-    __syncthreads();
-    if (rl < 4 && c < D) {
-        float tot = 0.f;
+    float aw[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f}, ag[4] = {0.f, 0.f, 0.f, 0.f}, abe[4] = {0.f, 0.f, 0.f, 0.f},
+          ac[4] = {0.f, 0.f, 0.f, 0.f};
+
+    for (int s0 = s_begin; s0 < s_end; s0 += LNW_ROWS) {
+        float q[LNW_ROWS][4], h[LNW_ROWS][4];   // q = dy * mask * drop_out * film_gamma (gradient wrt the normalised, scaled value)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) tot += sm[rl][k][cl];
-        if (rl == 0) atomicAdd(p.dln_w + c, tot);
-        else if (rl == 1) atomicAdd(p.dln_b + c, tot);
-        else if (p.dfilm) atomicAdd(p.dfilm + (size_t)b * 2 * D + (rl == 2 ? 0 : D) + c, tot);
+        for (int r = 0; r < LNW_ROWS; ++r) {
+            const int s = s0 + r;
+            float s1 = 0.f, s2 = 0.f;
+            if (s < s_end && s < len) {
+                const size_t row = (size_t)b * p.S + s;
+                const float4 d = *reinterpret_cast<const float4*>(p.dy + row * D + c);
+                const float4 hh = *reinterpret_cast<const float4*>(p.xhat + row * D + c);
+                float dv[4] = {d.x, d.y, d.z, d.w};
+                h[r][0] = hh.x; h[r][1] = hh.y; h[r][2] = hh.z; h[r][3] = hh.w;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    abe[e] += dv[e];
+                    if (p.p_out > 0.f) dv[e] *= dropout_scale(seed_out, row * D + c + e, p.p_out, inv_keep_out);
+                    ag[e] += dv[e] * (h[r][e] * wv[e] + bv[e]);
+                    dv[e] *= fg[e];
+                    aw[e] += dv[e] * h[r][e];
+                    ab[e] += dv[e];
+                    q[r][e] = dv[e];
+                    const float g = dv[e] * wv[e];
+                    s1 += g;
+                    s2 += g * h[r][e];
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { q[r][e] = 0.f; h[r][e] = 0.f; }
+            }
+            s1 = warp_sum(s1);
+            s2 = warp_sum(s2);
+            if (lane == 0) { part[0][r][warp] = s1; part[1][r][warp] = s2; }
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * LNW_ROWS) {
+            const int st = threadIdx.x / LNW_ROWS, r = threadIdx.x % LNW_ROWS;
+            float t = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += part[st][r][k];
+            tot[st][r] = t * (1.f / D);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < LNW_ROWS; ++r) {
+            const int s = s0 + r;
+            if (s >= s_end) break;
+            const size_t row = (size_t)b * p.S + s;
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+            if (s < len) {
+                const float c1 = tot[0][r], c2 = tot[1][r], rstd = p.rstd[row];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = rstd * (q[r][e] * wv[e] - c1 - h[r][e] * c2);
+                if (p.relu_src) {
+                    const float4 rs = *reinterpret_cast<const float4*>(p.relu_src + row * D + c);
+                    o[0] = rs.x > 0.f ? o[0] : 0.f; o[1] = rs.y > 0.f ? o[1] : 0.f; o[2] = rs.z > 0.f ? o[2] : 0.f; o[3] = rs.w > 0.f ? o[3] : 0.f;
+                }
+            }
+            *reinterpret_cast<float4*>(p.dv + row * D + c) = make_float4(o[0], o[1], o[2], o[3]);
+            if (p.da) {
+                if (s < len) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] *= dropout_scale(seed_in, row * D + c + e, p.p_in, inv_keep_in);
+                }
+                *reinterpret_cast<float4*>(p.da + row * D + c) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+            if (p.g_planes) {
+                __nv_bfloat16* phi = (__nv_bfloat16*)p.g_planes + row * D + c;
+                store_planes4(phi, phi + (size_t)R * D, o);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ac[e] += o[e];
+        }
+        __syncthreads();   // tot[] has been read by everyone before the next eight rows overwrite part[] / tot[]
+    }
+    atomicAdd(p.dln_w + c + 0, aw[0]); atomicAdd(p.dln_w + c + 1, aw[1]); atomicAdd(p.dln_w + c + 2, aw[2]); atomicAdd(p.dln_w + c + 3, aw[3]);
+    atomicAdd(p.dln_b + c + 0, ab[0]); atomicAdd(p.dln_b + c + 1, ab[1]); atomicAdd(p.dln_b + c + 2, ab[2]); atomicAdd(p.dln_b + c + 3, ab[3]);
+    if (p.dfilm) {
+        float* df = p.dfilm + (size_t)b * 2 * D;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { atomicAdd(df + c + e, ag[e]); atomicAdd(df + D + c + e, abe[e]); }
+    }
+    if (p.g_colsum) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) atomicAdd(p.g_colsum + c + e, ac[e]);
     }
 }
 
@@ -364,40 +372,26 @@ int ln_fwd(const LnArgs& a, cudaStream_t st) {
 }
 
 int ln_bwd(const LnArgs& a, cudaStream_t st) {
-    if (a.D == 128 || a.D == 256) {   // one fused launch: dv/da + parameter / FiLM / bias-gradient column sums + planes
-        DX_CUDA(cudaMemsetAsync(a.dln_w, 0, (size_t)a.D * sizeof(float), st));
-        DX_CUDA(cudaMemsetAsync(a.dln_b, 0, (size_t)a.D * sizeof(float), st));
-        if (a.dfilm) DX_CUDA(cudaMemsetAsync(a.dfilm, 0, (size_t)a.B * 2 * a.D * sizeof(float), st));
-        if (a.g_colsum) DX_CUDA(cudaMemsetAsync(a.g_colsum, 0, (size_t)a.D * sizeof(float), st));
-        const int rpb = a.S >= 512 ? 64 : (a.S >= 128 ? 32 : 16);
-        dim3 grid(ceil_div(a.S, rpb), a.B);
-        if (a.D == 128) ln_bwd_fused_kernel<4><<<grid, 256, 0, st>>>(a, rpb);
-        else ln_bwd_fused_kernel<8><<<grid, 256, 0, st>>>(a, rpb);
-        return check_launch("ln_bwd_fused");
-    }
-    if (a.g_planes || a.g_colsum) {
-        set_last_error("ln_bwd: gradient planes / column sums are fused for D in {128, 256} only (D=%d)", a.D);
+    // one fused launch per call: dv / da + parameter / FiLM / bias-gradient column sums + operand planes
+    if (a.D != 128 && a.D != 256 && a.D != 1024) {
+        set_last_error("ln_bwd: unsupported width D=%d (128, 256, 1024)", a.D);
         return DX_ERR_UNSUPPORTED;
     }
-    const int R = a.B * a.S;
-    const int blocks = ceil_div(R, 8);
-    switch (a.D) {
-        case 128: ln_bwd_dx_kernel<4><<<blocks, 256, 0, st>>>(a); break;
-        case 256: ln_bwd_dx_kernel<8><<<blocks, 256, 0, st>>>(a); break;
-        case 1024: ln_bwd_dx_kernel<32><<<blocks, 256, 0, st>>>(a); break;
-        default: set_last_error("ln_bwd: unsupported width D=%d (128, 256, 1024)", a.D); return DX_ERR_UNSUPPORTED;
-    }
-    int rc = check_launch("ln_bwd_dx");
-    if (rc) return rc;
     DX_CUDA(cudaMemsetAsync(a.dln_w, 0, (size_t)a.D * sizeof(float), st));
     DX_CUDA(cudaMemsetAsync(a.dln_b, 0, (size_t)a.D * sizeof(float), st));
     if (a.dfilm) DX_CUDA(cudaMemsetAsync(a.dfilm, 0, (size_t)a.B * 2 * a.D * sizeof(float), st));
-    const int col_blocks = ceil_div(a.D, 32);
-    int chunks = max(1, min(ceil_div(a.S, 64), ceil_div(148 * 4, col_blocks * a.B)));
-    const int rpc = ceil_div(a.S, chunks);
-    dim3 grid(col_blocks, ceil_div(a.S, rpc), a.B);
-    ln_bwd_param_kernel<<<grid, 256, 0, st>>>(a, rpc);
-    return check_launch("ln_bwd_param");
+    if (a.g_colsum) DX_CUDA(cudaMemsetAsync(a.g_colsum, 0, (size_t)a.D * sizeof(float), st));
+    if (a.D == 1024) {   // pre-net width: warp-per-column-slice organisation
+        const int rpb = a.S >= 512 ? 64 : (a.S >= 64 ? 32 : 8);
+        dim3 grid(ceil_div(a.S, rpb), a.B);
+        ln_bwd_fused_wide_kernel<<<grid, 256, 0, st>>>(a, rpb);
+        return check_launch("ln_bwd_fused_wide");
+    }
+    const int rpb = a.S >= 512 ? 64 : (a.S >= 128 ? 32 : 16);
+    dim3 grid(ceil_div(a.S, rpb), a.B);
+    if (a.D == 128) ln_bwd_fused_kernel<4><<<grid, 256, 0, st>>>(a, rpb);
+    else ln_bwd_fused_kernel<8><<<grid, 256, 0, st>>>(a, rpb);
+    return check_launch("ln_bwd_fused");
 }
 
 }  // namespace dx

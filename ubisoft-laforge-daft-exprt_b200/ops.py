@@ -307,7 +307,7 @@ def ln_bwd(dy, xhat, rstd, ln_w, ln_b, film, film_stride, lens, B, S, D, relu_sr
     dw = torch.empty(D, device=dy.device, dtype=torch.float32)
     db = torch.empty(D, device=dy.device, dtype=torch.float32)
     dfilm = torch.empty(B, 2 * D, device=dy.device, dtype=torch.float32) if want_film else None
-    fuse = emit_planes and _uses_planes(D) and D in (128, 256)
+    fuse = emit_planes and _uses_planes(D) and D in (128, 256, 1024)
     gP = torch.empty(2, B * S, D, device=dy.device, dtype=torch.bfloat16) if fuse else None
     gcs = torch.empty(D, device=dy.device, dtype=torch.float32) if fuse else None
     _call('dx_ln_bwd', _p(dy), _p(xhat), _p(rstd), _p(ln_w), _p(ln_b), _p(film), film_stride, _p(lens), _p(relu_src),
