@@ -274,17 +274,29 @@ __global__ void film_assemble_bwd_kernel(const float* __restrict__ dfilm, const 
                                          float* __restrict__ dbraw, float* __restrict__ dpost, int B, int NF, int NB,
                                          FilmLayout lay) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * NF) return;
-    const int b = i / NF, j = i % NF;
-    int blk, dst, ch;
-    film_locate(lay, j, blk, dst, ch);
-    const float pg = post ? post[blk] : 1.f, pb = post ? post[NB + blk] : 1.f;
-    const float dg = dfilm[(size_t)b * 2 * NF + dst], db = dfilm[(size_t)b * 2 * NF + dst + ch];
-    dgraw[i] = pg * dg;
-    dbraw[i] = pb * db;
+    const bool live = i < B * NF;
+    int blk = -1, dst = 0, ch = 0;
+    float vg = 0.f, vb = 0.f;
+    if (live) {
+        const int b = i / NF, j = i % NF;
+        film_locate(lay, j, blk, dst, ch);
+        const float pg = post ? post[blk] : 1.f, pb = post ? post[NB + blk] : 1.f;
+        const float dg = dfilm[(size_t)b * 2 * NF + dst], db = dfilm[(size_t)b * 2 * NF + dst + ch];
+        dgraw[i] = pg * dg;
+        dbraw[i] = pb * db;
+        if (dpost) { vg = dg * graw[i]; vb = db * braw[i]; }
+    }
     if (dpost) {
-        atomicAdd(dpost + blk, dg * graw[i]);
-        atomicAdd(dpost + NB + blk, db * braw[i]);
+        // only 2 * NB (= 18) accumulators: a warp's 32 consecutive channels almost always belong to one block -> one atomic per warp
+        const int blk0 = __shfl_sync(0xffffffffu, blk, 0);
+        if (__all_sync(0xffffffffu, blk == blk0)) {
+            vg = warp_sum(vg);
+            vb = warp_sum(vb);
+            if ((threadIdx.x & 31) == 0 && blk0 >= 0) { atomicAdd(dpost + blk0, vg); atomicAdd(dpost + NB + blk0, vb); }
+        } else if (live) {
+            atomicAdd(dpost + blk, vg);
+            atomicAdd(dpost + NB + blk, vb);
+        }
     }
 }
 
