@@ -245,8 +245,8 @@ __global__ void __launch_bounds__(256) ln_bwd_fused_kernel(LnArgs p, int rpb) {
 // Fused backward for D = 1024 (pre-net): same outputs as ln_bwd_fused_kernel, organised the other way round because a lane
 // cannot keep 32 columns x 3 running sums in registers.  Block = 8 warps over `rpb` rows of ONE utterance; WARP w owns the
 // column slice [128 w, 128 w + 128) of every row (a lane 4 consecutive columns, so its column sums stay in registers), rows are
-// processed eight at a time: slice partial sums of the two LayerNorm statistics -> shared memory -> row totals -> outputs.
-constexpr int LNW_ROWS = 8;
+// processed four at a time: slice partial sums of the two LayerNorm statistics -> shared memory -> row totals -> outputs.
+constexpr int LNW_ROWS = 4;   // rows in flight per warp (sixteen 16-byte loads per lane and phase)
 __global__ void __launch_bounds__(256) ln_bwd_fused_wide_kernel(LnArgs p, int rpb) {
     const unsigned long long seed_in = dyn_seed(p.seed_in, p.dyn), seed_out = dyn_seed(p.seed_out, p.dyn);
     (void)seed_in; (void)seed_out;
@@ -274,14 +274,24 @@ __global__ void __launch_bounds__(256) ln_bwd_fused_wide_kernel(LnArgs p, int rp
 
     for (int s0 = s_begin; s0 < s_end; s0 += LNW_ROWS) {
         float q[LNW_ROWS][4], h[LNW_ROWS][4];   // q = dy * mask * drop_out * film_gamma (gradient wrt the normalised, scaled value)
+        // all sixteen loads of the eight rows are issued before the first use (a load inside the per-row branch / shuffle sequence
+        // is not hoisted by the compiler and costs one exposed DRAM latency per row); invalid rows read row s0 and are discarded
+        float4 dld[LNW_ROWS], hld[LNW_ROWS];
+#pragma unroll
+        for (int r = 0; r < LNW_ROWS; ++r) {
+            const int s = (s0 + r < s_end && s0 + r < len) ? s0 + r : s0;
+            const size_t row = (size_t)b * p.S + s;
+            dld[r] = __ldg(reinterpret_cast<const float4*>(p.dy + row * D + c));
+            hld[r] = __ldg(reinterpret_cast<const float4*>(p.xhat + row * D + c));
+        }
 #pragma unroll
         for (int r = 0; r < LNW_ROWS; ++r) {
             const int s = s0 + r;
             float s1 = 0.f, s2 = 0.f;
             if (s < s_end && s < len) {
                 const size_t row = (size_t)b * p.S + s;
-                const float4 d = *reinterpret_cast<const float4*>(p.dy + row * D + c);
-                const float4 hh = *reinterpret_cast<const float4*>(p.xhat + row * D + c);
+                const float4 d = dld[r];
+                const float4 hh = hld[r];
                 float dv[4] = {d.x, d.y, d.z, d.w};
                 h[r][0] = hh.x; h[r][1] = hh.y; h[r][2] = hh.z; h[r][3] = hh.w;
 #pragma unroll
@@ -314,6 +324,15 @@ __global__ void __launch_bounds__(256) ln_bwd_fused_wide_kernel(LnArgs p, int rp
             tot[st][r] = t * (1.f / D);
         }
         __syncthreads();
+        float4 rld[LNW_ROWS];
+        float rstd_ld[LNW_ROWS];
+#pragma unroll
+        for (int r = 0; r < LNW_ROWS; ++r) {   // same for the ReLU sources and the row scales of the second phase
+            const int s = (s0 + r < s_end && s0 + r < len) ? s0 + r : s0;
+            const size_t row = (size_t)b * p.S + s;
+            rld[r] = p.relu_src ? __ldg(reinterpret_cast<const float4*>(p.relu_src + row * D + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+            rstd_ld[r] = __ldg(p.rstd + row);
+        }
 #pragma unroll
         for (int r = 0; r < LNW_ROWS; ++r) {
             const int s = s0 + r;
@@ -321,11 +340,11 @@ __global__ void __launch_bounds__(256) ln_bwd_fused_wide_kernel(LnArgs p, int rp
             const size_t row = (size_t)b * p.S + s;
             float o[4] = {0.f, 0.f, 0.f, 0.f};
             if (s < len) {
-                const float c1 = tot[0][r], c2 = tot[1][r], rstd = p.rstd[row];
+                const float c1 = tot[0][r], c2 = tot[1][r], rstd = rstd_ld[r];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) o[e] = rstd * (q[r][e] * wv[e] - c1 - h[r][e] * c2);
                 if (p.relu_src) {
-                    const float4 rs = *reinterpret_cast<const float4*>(p.relu_src + row * D + c);
+                    const float4 rs = rld[r];
                     o[0] = rs.x > 0.f ? o[0] : 0.f; o[1] = rs.y > 0.f ? o[1] : 0.f; o[2] = rs.z > 0.f ? o[2] : 0.f; o[3] = rs.w > 0.f ? o[3] : 0.f;
                 }
             }
