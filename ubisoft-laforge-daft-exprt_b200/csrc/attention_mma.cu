@@ -112,7 +112,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) attn_prep_kernel(const float* __restrict__ src, int ld, int B, int S, int Sp, int NH, int dh,
                                                         int scale_cols, float scale, __nv_bfloat16* __restrict__ R,
-                                                        __nv_bfloat16* __restrict__ Tr) {
+                                                        __nv_bfloat16* __restrict__ Tr, const float* __restrict__ dot_with = nullptr,
+                                                        float* __restrict__ dot_out = nullptr) {
     __shared__ __align__(16) unsigned short th[64][72], tl[64][72];   // [c][s] bf16 bit patterns
     const int b = blockIdx.z, s0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
     const int t = threadIdx.x;
@@ -124,6 +125,17 @@ __global__ void __launch_bounds__(256) attn_prep_kernel(const float* __restrict_
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (s < S) v = *reinterpret_cast<const float4*>(src + ((size_t)b * S + s) * ld + c);
         if (c < scale_cols) { v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale; }
+        if (dot_out) {
+            // backward: delta[b, head, s] = sum_d dctx * ctx, fused into the pass that already reads dctx (src): the dh / 4 lanes
+            // that hold one (row, head) reduce with shuffles, the first of them writes (64-column blocks are head aligned)
+            float part = 0.f;
+            if (s < S) {
+                const float4 o = *reinterpret_cast<const float4*>(dot_with + ((size_t)b * S + s) * ld + c);
+                part = v.x * o.x + v.y * o.y + v.z * o.z + v.w * o.w;
+            }
+            for (int off = dh / 8; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+            if (s < S && (cq % dh) == 0) dot_out[((size_t)b * NH + c / dh) * S + s] = part;
+        }
         uint32_t h0, l0, h1, l1;
         split_pair(v.x, v.y, h0, l0);
         split_pair(v.z, v.w, h1, l1);
@@ -548,9 +560,9 @@ int launch_bwd_mma(const AttnArgs& a, cudaStream_t st) {
 }
 
 int prep(const float* src, int ld, int B, int S, int Sp, int NH, int dh, int scale_cols, float scale, __nv_bfloat16* R,
-         __nv_bfloat16* Tr, cudaStream_t st) {
+         __nv_bfloat16* Tr, cudaStream_t st, const float* dot_with = nullptr, float* dot_out = nullptr) {
     dim3 grid(Sp / 64, (NH * dh) / 64, B);
-    attn_prep_kernel<<<grid, 256, 0, st>>>(src, ld, B, S, Sp, NH, dh, scale_cols, scale, R, Tr);
+    attn_prep_kernel<<<grid, 256, 0, st>>>(src, ld, B, S, Sp, NH, dh, scale_cols, scale, R, Tr, dot_with, dot_out);
     return check_launch("attn_prep");
 }
 
@@ -625,9 +637,9 @@ int attention_bwd_mma(const AttnArgs& a_in, void* planes, void* scratch, cudaStr
     a.GTr = nullptr;
     a.delta = (float*)(sb + ghalf);
     const int D = a.H * a.dh;
-    int rc = attention_bwd_prepare(a, st);   // delta + zero dqkv
-    if (rc) return rc;
-    rc = prep(a.dctx, D, a.B, a.S, a.Sp, a.H, a.dh, 0, 1.f, (__nv_bfloat16*)a.GR, (__nv_bfloat16*)a.GTr, st);
+    DX_CUDA(cudaMemsetAsync(a.dqkv, 0, (size_t)a.B * a.S * 3 * D * sizeof(float), st));   // dq is accumulated with atomics
+    // dO planes and delta = rowsum(dO * O) per head in ONE pass over dctx
+    int rc = prep(a.dctx, D, a.B, a.S, a.Sp, a.H, a.dh, 0, 1.f, (__nv_bfloat16*)a.GR, (__nv_bfloat16*)a.GTr, st, a.ctx, a.delta);
     if (rc) return rc;
     if (attn_bwd_tc_enabled(a.dh) && attention_bwd_tc_supported(a)) return attention_bwd_tc(a, st);   // tcgen05 / TMEM backward
     switch (a.dh) {
