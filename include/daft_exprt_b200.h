@@ -35,6 +35,9 @@ const char* dx_last_error(void);
 int dx_abi_version(void);
 /* number of CUDA kernels this library has launched so far in this process */
 uint64_t dx_launch_count(void);
+/* number of tcgen05 tensor-core GEMM kernels (gemm_tc_kernel) among them: lets a caller assert that the tensor-core path,
+ * not the exact-fp32 CUDA-core path, is the one running */
+uint64_t dx_tc_gemm_launch_count(void);
 /* 0 when the current device is sm_100 (B200); negative otherwise */
 int dx_device_check(void);
 int dx_set_gemm_backend(int backend);
@@ -109,6 +112,9 @@ int dx_scale_copy(const float* x, float* y, float alpha, size_t n, void* stream)
 /* planes: workspace of dx_attention_planes_bytes() written by the forward (per-head bf16 hi|lo operand planes of q|k|v used by
  * the tensor-core kernels) and handed back to the backward; may be NULL with the fp32 backend. */
 size_t dx_attention_planes_bytes(int B, int S, int H, int dh);
+/* 1 when dx_attention_fwd/bwd will run the tensor-core kernels for this head layout under the current GEMM backend (and
+ * therefore WRITE `planes` / `ctx_planes`), 0 when they fall back to the exact-fp32 kernels (which never touch them). */
+int dx_attention_uses_planes(int H, int dh);
 size_t dx_attention_bwd_scratch_bytes(int B, int S, int H, int dh);
 /* ctx_planes (nullable, tensor-core backends): ctx additionally as bf16 hi|lo operand planes [2][B*S][H*dh] for the
  * out-projection GEMM (no split pass over ctx). */
@@ -232,8 +238,13 @@ int dx_set_step_state(const void* device_state);
 size_t dx_step_state_bytes(void);
 
 /* ---- optimiser: fused Adam over a flat buffer (train.py:299-301,401) ---------------------------------------------------*/
+/* clip (nullable): the device buffer dx_grad_norm_clip filled; its coefficient out[1] multiplies grad_scale (train.py:399). */
 int dx_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
-                 float weight_decay, int step, float grad_scale, void* stream);
+                 float weight_decay, int step, float grad_scale, const float* clip, void* stream);
+/* torch.nn.utils.clip_grad_norm_(parameters, max_norm) (train.py:399) over the flat gradient buffer, without a host sync:
+ * out[0] = || grad_scale * g ||_2 (what the reference logs as grad_norm), out[1] = min(1, max_norm / (out[0] + 1e-6)),
+ * out[2] = scratch.  max_norm = INFINITY only measures the norm.  out: 3 floats of device memory. */
+int dx_grad_norm_clip(const float* g, size_t n, float grad_scale, float max_norm, float* out, void* stream);
 
 #ifdef __cplusplus
 }

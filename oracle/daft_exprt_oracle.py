@@ -14,7 +14,11 @@ and commits its outputs under `tests/golden/`; `tests/test_oracle_vs_golden.py` 
 (the reference itself ships no tests or golden vectors).
 
 Every function cites the reference lines it restates (paths relative to `/root/reference/src/daft_exprt/`).
-Eval-mode semantics only (all dropouts are identity), which is what parity is defined on.
+Eval-mode semantics by default (all dropouts are identity), which is what the golden fixtures pin.  Train-mode
+parity: `forward(..., dropout=hook)` applies a caller-supplied mask at every `nn.Dropout` / attention-dropout site of the
+reference, in call order (`hook.rows(x, p)` for element-wise sites, `hook.attn(probs, p)` for the attention weights); the tests
+replay the CUDA path's own counter-based masks through it (tests/helpers.py: DropoutReplay), so one train-mode step can be
+compared numerically instead of statistically.
 """
 import math
 
@@ -37,11 +41,14 @@ class OracleHParams:
         self.warmup_steps = 10000
         self.dur_weight = self.energy_weight = self.pitch_weight = self.mel_spec_weight = 1.
         self.filter_length, self.hop_length, self.sampling_rate, self.centered = 1024, 256, 22050, True
-        self.prosody_encoder = dict(nb_blocks=4, hidden_embed_dim=128, attn_nb_heads=8, conv_kernel=3, conv_channels=1024)
-        self.phoneme_encoder = dict(nb_blocks=4, hidden_embed_dim=128, attn_nb_heads=2, conv_kernel=3, conv_channels=1024)
-        self.local_prosody_predictor = dict(nb_blocks=1, conv_kernel=3, conv_channels=256)
+        # dropout rates: hparams.py:90-128 (only used when a dropout hook is passed to forward)
+        self.prosody_encoder = dict(nb_blocks=4, hidden_embed_dim=128, attn_nb_heads=8, conv_kernel=3, conv_channels=1024,
+                                    attn_dropout=0.1, conv_dropout=0.1)
+        self.phoneme_encoder = dict(nb_blocks=4, hidden_embed_dim=128, attn_nb_heads=2, conv_kernel=3, conv_channels=1024,
+                                    attn_dropout=0.1, conv_dropout=0.1)
+        self.local_prosody_predictor = dict(nb_blocks=1, conv_kernel=3, conv_channels=256, conv_dropout=0.1)
         self.gaussian_upsampling_module = dict(conv_kernel=3)
-        self.frame_decoder = dict(nb_blocks=4, attn_nb_heads=2, conv_kernel=3, conv_channels=1024)
+        self.frame_decoder = dict(nb_blocks=4, attn_nb_heads=2, conv_kernel=3, conv_channels=1024, attn_dropout=0.1, conv_dropout=0.1)
         self.stats = stats or {}
         for k, v in kw.items():
             setattr(self, k, v)
@@ -80,10 +87,10 @@ def conv1d_cl(x, w, b, relu=False):
     return F.relu(y) if relu else y
 
 
-def self_attention(x, lengths, sd, prefix, nb_heads):
+def self_attention(x, lengths, sd, prefix, nb_heads, dropout=None, p=0.):
     """MultiHeadAttention, model.py:171-193 around nn.MultiheadAttention (model.py:165, math path):
     q,k,v = split(x W_in^T + b_in); scores = (q/sqrt(dh)) k^T with key padding -> -inf; softmax; PV; out-proj;
-    then LN(attn + x) (dropout = identity in eval)."""
+    then LN(dropout(attn) + x) (model.py:189-191); nn.MultiheadAttention drops the softmax weights with the same p (model.py:165)."""
     B, S, D = x.shape
     dh = D // nb_heads
     w_in, b_in = sd[prefix + 'multi_head_attention.in_proj_weight'], sd[prefix + 'multi_head_attention.in_proj_bias']
@@ -97,16 +104,22 @@ def self_attention(x, lengths, sd, prefix, nb_heads):
     key_ok = valid_mask(lengths, S)[:, None, None, :]
     scores = scores.masked_fill(~key_ok, float('-inf'))
     probs = torch.softmax(scores, dim=-1)
+    if dropout is not None:
+        probs = dropout.attn(probs, p)
     ctx = (probs @ v).permute(0, 2, 1, 3).reshape(B, S, D)
     out = F.linear(ctx, sd[prefix + 'multi_head_attention.out_proj.weight'], sd[prefix + 'multi_head_attention.out_proj.bias'])
+    if dropout is not None:
+        out = dropout.rows(out, p)
     return F.layer_norm(out + x, (D,), sd[prefix + 'layer_norm.weight'], sd[prefix + 'layer_norm.bias'])
 
 
-def conv_feed_forward(x, film, sd, prefix):
+def conv_feed_forward(x, film, sd, prefix, dropout=None, p=0.):
     """PositionWiseConvFF, model.py:220-237 — gamma * LN(conv2(relu(conv1(x))) + x) + beta."""
     D = x.shape[2]
     h = conv1d_cl(x, sd[prefix + 'convs.0.conv.weight'], sd[prefix + 'convs.0.conv.bias'], relu=True)
     y = conv1d_cl(h, sd[prefix + 'convs.2.conv.weight'], sd[prefix + 'convs.2.conv.bias'])
+    if dropout is not None:   # model.py:213-217: the Sequential ends with nn.Dropout
+        y = dropout.rows(y, p)
     y = F.layer_norm(y + x, (D,), sd[prefix + 'layer_norm.weight'], sd[prefix + 'layer_norm.bias'])
     if film is not None:
         assert film.shape[1] == 2 * D
@@ -114,17 +127,18 @@ def conv_feed_forward(x, film, sd, prefix):
     return y
 
 
-def fft_block(x, film, lengths, sd, prefix, nb_heads):
+def fft_block(x, film, lengths, sd, prefix, nb_heads, dropout=None, cfg=None):
     """FFTBlock, model.py:251-264 — attention, zero padded rows, conv-FF (+FiLM), zero padded rows."""
     keep = valid_mask(lengths, x.shape[1])[:, :, None].to(x.dtype)
-    a = self_attention(x, lengths, sd, prefix + 'attention.', nb_heads) * keep
-    return conv_feed_forward(a, film, sd, prefix + 'feed_forward.') * keep
+    pa, pc = (cfg['attn_dropout'], cfg['conv_dropout']) if dropout is not None else (0., 0.)
+    a = self_attention(x, lengths, sd, prefix + 'attention.', nb_heads, dropout, pa) * keep
+    return conv_feed_forward(a, film, sd, prefix + 'feed_forward.', dropout, pc) * keep
 
 
 # ----------------------------------------------------------------------------------------------------------------------
 # sub-modules
 # ----------------------------------------------------------------------------------------------------------------------
-def prosody_encoder(sd, hp, frames_energy, frames_pitch, mel_specs, speaker_ids, output_lengths):
+def prosody_encoder(sd, hp, frames_energy, frames_pitch, mel_specs, speaker_ids, output_lengths, dropout=None):
     """ProsodyEncoder.forward, model.py:391-464."""
     p = 'prosody_encoder.'
     cfg = hp.prosody_encoder
@@ -138,10 +152,12 @@ def prosody_encoder(sd, hp, frames_energy, frames_pitch, mel_specs, speaker_ids,
     for conv_i, ln_i in ((0, 2), (4, 6), (8, 10)):  # model.py:341-363: conv -> ReLU -> LayerNorm (-> dropout)
         x = conv1d_cl(x, sd[f'{p}convs.{conv_i}.conv.weight'], sd[f'{p}convs.{conv_i}.conv.bias'], relu=True)
         x = F.layer_norm(x, (x.shape[2],), sd[f'{p}convs.{ln_i}.weight'], sd[f'{p}convs.{ln_i}.bias'])
+        if dropout is not None:
+            x = dropout.rows(x, cfg['conv_dropout'])
     keep = valid_mask(output_lengths, T)[:, :, None].to(dt)
     x = (x + energy + pitch + pos) * keep
     for i in range(cfg['nb_blocks']):
-        x = fft_block(x, None, output_lengths, sd, f'{p}blocks.{i}.', cfg['attn_nb_heads'])
+        x = fft_block(x, None, output_lengths, sd, f'{p}blocks.{i}.', cfg['attn_nb_heads'], dropout, cfg)
     pooled = x.sum(dim=1) / output_lengths[:, None]  # model.py:419
     h = pooled + sd[p + 'spk_embedding.weight'][speaker_ids]
     gammas = F.linear(h, sd[p + 'gammas_predictor.linear_layer.weight'], sd[p + 'gammas_predictor.linear_layer.bias'])
@@ -175,7 +191,7 @@ def speaker_classifier(sd, x):
     return F.linear(x, sd[p + '5.linear_layer.weight'], sd[p + '5.linear_layer.bias'])
 
 
-def phoneme_encoder(sd, hp, symbols, film, input_lengths):
+def phoneme_encoder(sd, hp, symbols, film, input_lengths, dropout=None):
     """PhonemeEncoder.forward, model.py:490-509."""
     p = 'phoneme_encoder.'
     cfg = hp.phoneme_encoder
@@ -184,17 +200,19 @@ def phoneme_encoder(sd, hp, symbols, film, input_lengths):
     x = emb[symbols] + positional_encoding(input_lengths, L, cfg['hidden_embed_dim'], emb.dtype)
     x = x * valid_mask(input_lengths, L)[:, :, None].to(emb.dtype)
     for i in range(cfg['nb_blocks']):
-        x = fft_block(x, film[:, i, :], input_lengths, sd, f'{p}blocks.{i}.', cfg['attn_nb_heads'])
+        x = fft_block(x, film[:, i, :], input_lengths, sd, f'{p}blocks.{i}.', cfg['attn_nb_heads'], dropout, cfg)
     return x
 
 
-def local_prosody_predictor(sd, hp, x, film, input_lengths):
+def local_prosody_predictor(sd, hp, x, film, input_lengths, dropout=None):
     """LocalProsodyPredictor.forward, model.py:549-575."""
     p = 'prosody_predictor.'
     for i in range(hp.local_prosody_predictor['nb_blocks']):
         for conv_i, ln_i in ((0, 2), (4, 6)):
             x = conv1d_cl(x, sd[f'{p}blocks.{i}.{conv_i}.conv.weight'], sd[f'{p}blocks.{i}.{conv_i}.conv.bias'], relu=True)
             x = F.layer_norm(x, (x.shape[2],), sd[f'{p}blocks.{i}.{ln_i}.weight'], sd[f'{p}blocks.{i}.{ln_i}.bias'])
+            if dropout is not None:
+                x = dropout.rows(x, hp.local_prosody_predictor['conv_dropout'])
         C = x.shape[2]
         assert film.shape[2] == 2 * C
         x = film[:, i, None, :C] * x + film[:, i, None, C:]
@@ -229,7 +247,7 @@ def gaussian_upsampling(sd, x, durations_float, durations_int, energies, pitch, 
     return x_up, weights
 
 
-def frame_decoder(sd, hp, x, film, output_lengths):
+def frame_decoder(sd, hp, x, film, output_lengths, dropout=None):
     """FrameDecoder.forward, model.py:689-710."""
     p = 'frame_decoder.'
     cfg = hp.frame_decoder
@@ -237,7 +255,7 @@ def frame_decoder(sd, hp, x, film, output_lengths):
     keep = valid_mask(output_lengths, T)[:, :, None].to(x.dtype)
     x = (x + positional_encoding(output_lengths, T, D, x.dtype)) * keep
     for i in range(cfg['nb_blocks']):
-        x = fft_block(x, film[:, i, :], output_lengths, sd, f'{p}blocks.{i}.', cfg['attn_nb_heads'])
+        x = fft_block(x, film[:, i, :], output_lengths, sd, f'{p}blocks.{i}.', cfg['attn_nb_heads'], dropout, cfg)
     mel = F.linear(x, sd[p + 'projection.linear_layer.weight'], sd[p + 'projection.linear_layer.bias']) * keep
     return mel.transpose(1, 2)
 
@@ -245,16 +263,17 @@ def frame_decoder(sd, hp, x, film, output_lengths):
 # ----------------------------------------------------------------------------------------------------------------------
 # top level: forward / loss / inference
 # ----------------------------------------------------------------------------------------------------------------------
-def forward(sd, hp, inputs, return_intermediates=False):
-    """DaftExprt.forward, model.py:755-787 — same 5-tuple."""
+def forward(sd, hp, inputs, return_intermediates=False, dropout=None):
+    """DaftExprt.forward, model.py:755-787 — same 5-tuple.  dropout: None (eval) or a hook with .rows(x, p) / .attn(probs, p)."""
     (symbols, durations_float, durations_int, symbols_energy, symbols_pitch, input_lengths,
      frames_energy, frames_pitch, mel_specs, output_lengths, speaker_ids) = inputs
-    prosody_embed, enc_film, pp_film, dec_film = prosody_encoder(sd, hp, frames_energy, frames_pitch, mel_specs, speaker_ids, output_lengths)
+    prosody_embed, enc_film, pp_film, dec_film = prosody_encoder(sd, hp, frames_energy, frames_pitch, mel_specs, speaker_ids,
+                                                                 output_lengths, dropout)
     spk_preds = speaker_classifier(sd, prosody_embed)
-    enc = phoneme_encoder(sd, hp, symbols, enc_film, input_lengths)
-    dur, energy, pitch = local_prosody_predictor(sd, hp, enc, pp_film, input_lengths)
+    enc = phoneme_encoder(sd, hp, symbols, enc_film, input_lengths, dropout)
+    dur, energy, pitch = local_prosody_predictor(sd, hp, enc, pp_film, input_lengths, dropout)
     up, weights = gaussian_upsampling(sd, enc, durations_float, durations_int, symbols_energy, symbols_pitch, input_lengths)
-    mel = frame_decoder(sd, hp, up, dec_film, output_lengths)
+    mel = frame_decoder(sd, hp, up, dec_film, output_lengths, dropout)
     post = sd.get('prosody_encoder.post_multipliers', 1.)
     out = (spk_preds, [post, enc_film, pp_film, dec_film], [dur, energy, pitch, input_lengths], [mel, output_lengths], weights)
     if return_intermediates:

@@ -15,8 +15,8 @@ import torch
 
 import daft_exprt_oracle as oracle
 from daft_exprt_b200 import synthetic
-from helpers import (GOLDEN_CASES, GOLDEN_DIR, case_inference_inputs, case_inputs, fake_stats, grad_projection, l2_rel_err,
-                     load_golden, scale_rel_err, targets_of)
+from helpers import (GOLDEN_CASES, GOLDEN_DIR, DropoutReplay, case_inference_inputs, case_inputs, fake_stats, grad_projection,
+                     l2_rel_err, load_golden, record_seeds, rows_dropout_scale, scale_rel_err, targets_of)
 
 pytestmark = pytest.mark.gpu
 
@@ -331,19 +331,28 @@ def test_all_gradients_match_oracle_autograd(dev, backend):
     assert not bad, bad[:10]
 
 
+@pytest.mark.parametrize('backend', ['fp32', 'bf16x3'])
 @pytest.mark.parametrize('case', GOLDEN_CASES)
 @pytest.mark.parametrize('transform', ['add', 'multiply'])
-def test_inference_matches_reference_golden(dev, case, transform):
-    set_backend('fp32')
+def test_inference_matches_reference_golden(dev, case, transform, backend):
+    """`inference()` on BOTH parity backends: the integer durations (discontinuous in the predicted float durations) must be
+    bit-exact on the default tcgen05 bf16x3 backend too, not only on the exact-fp32 one."""
+    set_backend(backend)
     fx = load_golden(case)
     n_ids = int(fx['meta_n_speaker_ids'])
     model, hp, _ = build_model(n_ids, dev, nudge=True)
     with torch.no_grad():
         enc, dec, w = model.inference(to_dev(case_inference_inputs(fx, transform), dev), transform, hp)
-    assert torch.equal(enc[1].cpu(), torch.from_numpy(fx[f'inf_{transform}_durations_int']))      # bit-exact
+    ref_int = torch.from_numpy(fx[f'inf_{transform}_durations_int'])
+    flips = (enc[1].cpu() != ref_int)
+    if flips.any():   # report how many frames moved and how close to a frame boundary the float durations were
+        d = (enc[0].cpu() - torch.from_numpy(fx[f'inf_{transform}_duration_preds'])).abs()
+        print(f'[{backend}/{case}/{transform}] {int(flips.sum())} integer durations differ; max |d float duration| = {float(d.max()):.3e} s')
+    assert torch.equal(enc[1].cpu(), ref_int)                                                      # bit-exact
     assert torch.equal(dec[1].cpu(), torch.from_numpy(fx[f'inf_{transform}_output_lengths']))
+    tol = 2e-4 if backend == 'fp32' else 1e-3
     for name, got in (('duration_preds', enc[0]), ('energy_preds', enc[2]), ('pitch_preds', enc[3]), ('mel_spec_preds', dec[0])):
-        assert scale_rel_err(got, fx[f'inf_{transform}_{name}']) < 2e-4, name
+        assert scale_rel_err(got, fx[f'inf_{transform}_{name}']) < tol, name
 
 
 def test_state_dict_roundtrip_and_unknown_transform(dev):
@@ -635,3 +644,330 @@ def test_batch_prefetcher_matches_parse_batch(dev):
         assert ids == ref_ids
         for a, b in zip(tuple(inp) + tuple(tgt), tuple(ref_in) + tuple(ref_tg)):
             assert a.dtype == b.dtype and torch.equal(a, b)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# round 2: parity on the path that is benchmarked (default backend, full length, train mode)
+# ----------------------------------------------------------------------------------------------------------------------
+def test_default_backend_is_tcgen05_bf16x3():
+    """A fresh process that never calls set_backend must run the tcgen05 GEMMs (the documented default), not the fp32 SIMT path."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import torch\n"
+        "from daft_exprt_b200 import cabi, ops, synthetic\n"
+        "from daft_exprt_b200.hparams import default_hparams\n"
+        "from daft_exprt_b200.model import DaftExprt\n"
+        "lib = cabi.load()\n"
+        "assert ops.get_backend() == 'bf16x3' and lib.dx_get_gemm_backend() == cabi.DX_GEMM_TCGEN05_BF16X3\n"
+        "m = DaftExprt(default_hparams(n_speakers=12)).cuda().eval()\n"
+        "n0 = lib.dx_tc_gemm_launch_count()\n"
+        "out = m(tuple(t.cuda() for t in synthetic.make_batch(2, 20, 80, 11, seed=1)))\n"
+        "torch.cuda.synchronize()\n"
+        "n = lib.dx_tc_gemm_launch_count() - n0\n"
+        "assert n >= 50, n\n"
+        "print('tc_gemm_launches', n)\n") % root
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert 'tc_gemm_launches' in r.stdout
+
+
+def test_full_length_parity_vs_oracle(dev):
+    """B=8 utterances at the FULL benchmark lengths (L<=200, T<=1000, the first 8 of the bench batch) on the default bf16x3 backend
+    against the oracle run here on the host CPU: every forward output, the 7 loss terms and all 193 gradients (fp64 oracle as the
+    arbiter).  T=1000 exercises the 8-tile attention rings, partial last tiles and the K=3072 pre-net GEMM at their real sizes."""
+    from daft_exprt_b200.loss import DaftExprtLoss
+    set_backend('bf16x3')
+    t_dense, t_l2, t_loss, t_grad = TOL['bf16x3']
+    n_ids = 11
+    full = synthetic.make_batch(32, 200, 1000, n_ids, seed=0)
+    inputs = tuple(t[:8].clone() for t in full)
+    assert int(inputs[9].max()) == 1000 and int(inputs[5].max()) == 200
+    model, hp, sd = build_model(n_ids, dev)
+    crit = DaftExprtLoss(0, hp)
+    din = to_dev(inputs, dev)
+    out = model(din)
+    total, terms = crit(out, targets_of(din), 3000)
+    total.backward()
+    ohp = oracle.OracleHParams(n_speakers=n_ids + 1)
+    sd_o = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    in64 = tuple(t.double() if t.is_floating_point() else t for t in inputs)
+    ref = oracle.forward(sd_o, ohp, in64)
+    total_o, terms_o = oracle.loss(ohp, ref, targets_of(in64), 3000)
+    total_o.backward()
+    spk, film, enc, dec, align = out
+    rspk, rfilm, renc, rdec, ralign = ref
+    assert torch.equal(dec[1].cpu(), rdec[1])
+    report = {}
+    for name, got, want in (('speaker_preds', spk, rspk), ('encoder_film', film[1], rfilm[1]), ('prosody_pred_film', film[2], rfilm[2]),
+                            ('decoder_film', film[3], rfilm[3]), ('duration_preds', enc[0], renc[0]), ('energy_preds', enc[1], renc[1]),
+                            ('pitch_preds', enc[2], renc[2]), ('mel_spec_preds', dec[0], rdec[0]), ('alignments', align, ralign)):
+        report[name] = (scale_rel_err(got.detach(), want.detach()), l2_rel_err(got.detach(), want.detach()))
+    print('[full-length bf16x3] (scale-rel, l2-rel):', {k: (f'{a:.1e}', f'{b:.1e}') for k, (a, b) in report.items()})
+    for name, (a, b) in report.items():
+        assert a < t_dense and b < t_l2, (name, a, b)
+    assert abs(total.item() - total_o.item()) <= t_loss * abs(total_o.item())
+    for k, v in terms.items():
+        r = float(terms_o[k])
+        assert abs(v - r) <= t_loss * max(abs(r), 1e-6), (k, v, r)
+    worst = []
+    for n, p in model.named_parameters():
+        worst.append((l2_rel_err(p.grad, sd_o[n].grad), scale_rel_err(p.grad, sd_o[n].grad), n))
+    worst.sort(reverse=True)
+    print('[full-length bf16x3] worst gradient (l2-rel, scale-rel):', [(n, f'{a:.1e}', f'{b:.1e}') for a, b, n in worst[:6]])
+    for a, b, n in worst:
+        tg = t_grad if not n.startswith('gaussian_upsampling.') else 5e-2     # same ill-conditioned sums as in the golden test
+        assert a < tg and b < max(tg, 1e-2), (n, a, b)
+
+
+def test_dropout_hash_numpy_restatement_matches_kernel(dev):
+    """Pins tests/helpers.py's numpy hash to the kernels: the mask `dx_ln_fwd` applies == rows_dropout_scale for the same seed."""
+    from daft_exprt_b200 import ops
+    B, S, D, p = 3, 70, 128, 0.1
+    a = torch.randn(B, S, D, generator=torch.Generator().manual_seed(8)).to(dev)
+    w, b = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+    seed = 0x9E3779B97F4A7C15 ^ 0x1234
+    y0, _, _ = ops.ln_fwd(a, None, w, b, None, 0, None, B, S, D)
+    y1, _, _ = ops.ln_fwd(a, None, w, b, None, 0, None, B, S, D, p_out=p, seed_out=seed)
+    scale = torch.from_numpy(rows_dropout_scale(seed, B * S * D, p)).view(B, S, D).to(dev)
+    assert torch.equal(y1, y0 * scale)
+
+
+def test_train_mode_step_matches_oracle_with_replayed_masks(dev):
+    """ONE train-mode (dropout 0.1 everywhere) forward + loss + backward compared NUMERICALLY with the oracle: the counter-based masks
+    of the 41 dropout sites are regenerated in numpy from the seeds the CUDA path drew and applied at the same sites of the oracle."""
+    from daft_exprt_b200.loss import DaftExprtLoss
+    set_backend('bf16x3')
+    n_ids = 11
+    inputs = synthetic.make_batch(3, 37, 150, n_ids, seed=33)
+    model, hp, sd = build_model(n_ids, dev, train=True)
+    crit = DaftExprtLoss(0, hp)
+    din = to_dev(inputs, dev)
+    with record_seeds() as seeds:
+        out = model(din)
+    assert len(seeds) == 41
+    total, terms = crit(out, targets_of(din), 2500)
+    total.backward()
+    ohp = oracle.OracleHParams(n_speakers=n_ids + 1)
+    sd_o = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    in64 = tuple(t.double() if t.is_floating_point() else t for t in inputs)
+    hook = DropoutReplay(seeds)
+    ref = oracle.forward(sd_o, ohp, in64, dropout=hook)
+    assert hook.k == 41
+    total_o, terms_o = oracle.loss(ohp, ref, targets_of(in64), 2500)
+    total_o.backward()
+    with torch.no_grad():
+        ref_eval = oracle.forward(sd_o, ohp, in64)
+    mel, rmel = out[3][0].detach(), ref[3][0].detach()
+    assert scale_rel_err(rmel, ref_eval[3][0]) > 1e-2                      # the masks do matter ...
+    e_mel = (scale_rel_err(mel, rmel), l2_rel_err(mel, rmel))
+    print('[train-mode bf16x3] mel (scale-rel, l2-rel):', e_mel, 'loss rel:', abs(total.item() - total_o.item()) / abs(total_o.item()))
+    assert e_mel[0] < 1e-3 and e_mel[1] < 2e-4                             # ... and with the same masks the outputs agree
+    for name, got, want in (('duration', out[2][0], ref[2][0]), ('energy', out[2][1], ref[2][1]), ('pitch', out[2][2], ref[2][2]),
+                            ('speaker', out[0], ref[0])):
+        assert scale_rel_err(got.detach(), want.detach()) < 1e-3, name
+    assert abs(total.item() - total_o.item()) <= 1e-4 * abs(total_o.item())
+    bad = []
+    for n, p in model.named_parameters():
+        e = l2_rel_err(p.grad, sd_o[n].grad)
+        tg = 2e-3 if not n.startswith('gaussian_upsampling.') else 5e-2
+        if not e < tg:
+            bad.append((n, e))
+    assert not bad, bad[:10]
+
+
+def test_small_head_layout_falls_back_without_reading_uninitialised_planes(dev):
+    """hidden_embed_dim 32 with 2 heads (H*dh = 32 is not a multiple of 64): dx_attention_fwd runs the exact-fp32 attention, which
+    writes no operand planes; the sub-layer must then split the context itself (the out-projection used to read
+    uninitialised planes).  Checked against plain torch."""
+    from daft_exprt_b200 import ops
+    set_backend('bf16x3')
+    assert ops.lib().dx_attention_uses_planes(2, 16) == 0 and ops.lib().dx_attention_uses_planes(2, 64) == 1
+    B, S, D, H = 2, 50, 32, 2
+    g = torch.Generator().manual_seed(11)
+    mha = torch.nn.MultiheadAttention(D, H, 0.0)
+    ln = torch.nn.LayerNorm(D)
+    with torch.no_grad():
+        ln.weight.copy_(torch.rand(D, generator=g) + 0.5); ln.bias.copy_(torch.randn(D, generator=g) * 0.1)
+        mha.in_proj_bias.copy_(torch.randn(3 * D, generator=g) * 0.1); mha.out_proj.bias.copy_(torch.randn(D, generator=g) * 0.1)
+    x = torch.randn(B, S, D, generator=g)
+    lens = torch.tensor([50, 31])
+    xr = x.double().clone().requires_grad_(True)
+    mha64, ln64 = mha.double(), ln.double()
+    q = xr.transpose(0, 1)
+    a, _ = mha64(q, q, q, key_padding_mask=~oracle.valid_mask(lens, S))
+    ref = ln64(a.transpose(0, 1) + xr) * oracle.valid_mask(lens, S)[:, :, None]
+    dy = torch.randn(B, S, D, generator=g).double()
+    ref.backward(dy)
+    f = lambda t: t.detach().float().to(dev).requires_grad_(True)
+    xd = f(x)
+    params = [f(t) for t in (mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, ln.weight, ln.bias)]
+    y = ops.AttentionSubLayer.apply(xd, lens.to(dev), *params, H, 0.0)
+    y.backward(dy.float().to(dev))
+    assert scale_rel_err(y.detach(), ref.detach()) < 1e-4
+    assert scale_rel_err(xd.grad, xr.grad) < 1e-3
+    for got, want in zip(params, (mha64.in_proj_weight, mha64.in_proj_bias, mha64.out_proj.weight, mha64.out_proj.bias, ln64.weight, ln64.bias)):
+        assert scale_rel_err(got.grad, want.grad) < 1e-3
+
+
+def test_stale_pack_guard_raises(dev):
+    """forward(A), weights change + forward(B), backward(A): the dgrad packs held by A were refilled in place -> loud error."""
+    from daft_exprt_b200 import ops
+    set_backend('bf16x3')
+    w = torch.randn(64, 32, device=dev, requires_grad=True)
+    b = torch.zeros(64, device=dev, requires_grad=True)
+    x = torch.randn(40, 32, device=dev, requires_grad=True)
+    ya = ops.Linear.apply(x, w, b, False, 1.0)
+    with torch.no_grad():
+        w.add_(1.0)
+    yb = ops.Linear.apply(x, w, b, False, 1.0)
+    yb.sum().backward()                                    # fine: the pack is current
+    with pytest.raises(RuntimeError, match='packed weight was refilled'):
+        ya.sum().backward()
+
+
+def test_out_of_range_ids_raise_like_the_reference(dev):
+    model, hp, _ = build_model(3, dev)
+    batch = list(synthetic.make_batch(2, 10, 40, 3, seed=1)) + [[], []]
+    bad = list(batch)
+    bad[10] = torch.tensor([0, 3])                         # the speaker classifier has n_speakers - 1 = 3 classes: ids 0..2
+    with pytest.raises(IndexError):
+        model.parse_batch(0, tuple(bad))
+    bad = list(batch)
+    bad[0] = batch[0].clone()
+    bad[0][0, 0] = 76
+    with pytest.raises(IndexError):
+        model.parse_batch(0, tuple(bad))
+    model.parse_batch(0, tuple(batch))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# rows N1 / N2 / N4: the reference's loop shape (accumulation_steps = 3), bucketed flat batches, sharded validation
+# ----------------------------------------------------------------------------------------------------------------------
+def _loop_objects(dev, clip=float('inf')):
+    from daft_exprt_b200.ddp import FlatAdam, FlatGradSync
+    from daft_exprt_b200.loss import DaftExprtLoss
+    model, hp, _ = build_model(5, dev, train=False)
+    hp.accumulation_steps, hp.grad_clip_thresh = 3, clip
+    crit = DaftExprtLoss(0, hp)
+    params = list(model.parameters())
+    sync = FlatGradSync(params, mode='gather')
+    opt = FlatAdam(params, sync, lr=hp.initial_learning_rate, betas=hp.betas, eps=hp.epsilon, weight_decay=hp.weight_decay,
+                   grad_clip_thresh=clip, track_grad_norm=True)
+    return model, hp, crit, sync, opt
+
+
+def test_reference_loop_shape_accumulation_eager_graph_and_torch_adam(dev):
+    """train.py:368-401 with accumulation_steps = 3 over 6 micro-batches of two bucket shapes: (a) eager FlatAdam, (b) graph replay,
+    (c) stock torch.optim.Adam + clip_grad_norm_ on the same module -> same trajectories; a finite grad_clip_thresh is honoured."""
+    from daft_exprt_b200.data import BucketedCollate
+    from daft_exprt_b200.graph import GraphedTrainStep
+    from daft_exprt_b200.training import train_epoch
+    set_backend('bf16x3')
+    col = BucketedCollate(None, l_step=32, t_step=128)
+    raw = [tuple(synthetic.make_batch(4, L, T, 5, seed=40 + i)) + ([], []) for i, (L, T) in
+           enumerate([(30, 200), (40, 300), (25, 230), (60, 350), (28, 250), (33, 120)])]
+    batches = [col(b).pin_memory() for b in raw]
+    assert len({b.key() for b in batches}) == 2
+    clip = 0.05
+    logs = {}
+
+    def run(kind):
+        model, hp, crit, sync, opt = _loop_objects(dev, clip)
+        p0 = opt.flat_p.detach().clone()
+        log = []
+        on_step = lambda it, tot, indiv, gn, lr: log.append((it, tot, gn, lr))
+        if kind == 'graph':
+            g = GraphedTrainStep(model, crit, sync, opt, accumulation_steps=3)
+            it = train_epoch(0, model, crit, opt, batches, hp, 100, graphed=g, on_step=on_step)
+            assert g.misses == 2 and g.hits == 4 and opt.step_count == 2
+        elif kind == 'eager':
+            it = train_epoch(0, model, crit, opt, batches, hp, 100, sync=sync, on_step=on_step)
+        else:
+            # the reference's own optimiser on the module's (re-pointed) parameters
+            topt = torch.optim.Adam(model.parameters(), lr=hp.initial_learning_rate, betas=hp.betas, eps=hp.epsilon,
+                                    weight_decay=hp.weight_decay)
+            it = train_epoch(0, model, crit, topt, batches, hp, 100, on_step=on_step)
+        assert it == 102 and len(log) == 2
+        logs[kind] = log
+        return (opt.flat_p.detach() - p0).cpu().numpy(), opt
+    d_eager, opt_e = run('eager')
+    d_graph, _ = run('graph')
+    d_torch, _ = run('torch')
+    assert np.abs(d_eager).max() > 1e-5
+    assert l2_rel_err(d_graph, d_eager) < 5e-2 and l2_rel_err(d_torch, d_eager) < 5e-2
+    for kind in ('graph', 'torch'):
+        for (it_a, tot_a, gn_a, lr_a), (it_b, tot_b, gn_b, lr_b) in zip(logs['eager'], logs[kind]):
+            assert it_a == it_b and lr_a == lr_b
+            assert abs(tot_a - tot_b) < 2e-3 * abs(tot_a)
+            assert abs(float(gn_a) - float(gn_b)) < 5e-3 * float(gn_a), (kind, gn_a, gn_b)
+    assert logs['eager'][0][2] > clip                                # the threshold was active
+    # checkpoint format of torch.optim.Adam: FlatAdam -> torch Adam -> FlatAdam
+    sd = opt_e.state_dict()
+    tmodel_params = [torch.nn.Parameter(p.detach().clone()) for p in opt_e.params]
+    topt = torch.optim.Adam(tmodel_params, lr=1.0)
+    topt.load_state_dict(sd)
+    assert topt.param_groups[0]['lr'] == opt_e.lr and topt.param_groups[0]['betas'] == tuple(opt_e.betas)
+    assert torch.equal(topt.state[tmodel_params[3]]['exp_avg'], sd['state'][3]['exp_avg'])
+    model, hp, crit, sync, opt2 = _loop_objects(dev)
+    opt2.load_state_dict(topt.state_dict())
+    assert opt2.step_count == 2 and torch.equal(opt2.m, opt_e.m) and torch.equal(opt2.v, opt_e.v)
+
+
+def test_flat_batch_single_copy_matches_parse_batch(dev):
+    """data.FlatBatch: ONE pinned buffer, ONE H2D copy, device views == what the 11-copy parse_batch produces (then padded)."""
+    from daft_exprt_b200.data import BatchPrefetcher, BucketedCollate
+    model, hp, _ = build_model(11, dev)
+    raw = tuple(synthetic.make_batch(4, 30, 120, 11, seed=9)) + (['d'] * 4, ['f'] * 4)
+    fb = BucketedCollate(None, 64, 128)(raw).pin_memory()
+    assert fb.buf.is_pinned()
+    ref_in, ref_tg, ref_ids = model.parse_batch(0, raw)
+    pre = BatchPrefetcher(model, 0)
+    pre.submit(fb)
+    inp, tgt, ids = pre.get()
+    assert ids == ref_ids
+    base = inp[0].untyped_storage().data_ptr()
+    assert all(t.untyped_storage().data_ptr() == base for t in inp)                 # views of one device buffer
+    for a, b in zip(inp, ref_in):
+        assert a.dtype == b.dtype
+        assert torch.equal(a[tuple(slice(0, n) for n in b.shape)], b)
+    # padding to the bucket shape leaves every utterance that was already padded in the batch bit-for-bit on the same path; only
+    # utterances that defined L_max / T_max (no padding after them before) see the reference's own batch-composition effect
+    # (SURVEY.md section 0.6: convs run unmasked over the zero-padded layout)
+    set_backend('bf16x3')
+    mel_pad = model(inp)[3][0][:, :, :120]
+    mel_ref = model(ref_in)[3][0]
+    inner = [b for b in range(4) if int(ref_in[5][b]) <= 30 - 3 and int(ref_in[9][b]) <= 120 - 4]   # beyond the conv receptive fields
+    assert inner, 'test batch needs at least one utterance shorter than both maxima'
+    for b in inner:
+        assert scale_rel_err(mel_pad[b], mel_ref[b].detach()) < 1e-4, b
+    edge = [b for b in range(4) if b not in inner]
+    print('[bucket padding] scale-rel change of the utterances that defined the batch maxima:',
+          [f'{scale_rel_err(mel_pad[b], mel_ref[b].detach()):.1e}' for b in edge])
+    assert torch.isfinite(mel_pad).all()
+
+
+def test_validate_sharded_single_process_matches_manual_mean(dev):
+    from daft_exprt_b200.loss import DaftExprtLoss
+    from daft_exprt_b200.training import validate_sharded
+    set_backend('bf16x3')
+    model, hp, _ = build_model(5, dev, train=True)
+    crit = DaftExprtLoss(0, hp)
+    batches = [tuple(synthetic.make_batch(3, 20, 90, 5, seed=70 + i)) + ([], []) for i in range(3)]
+    loss, indiv, tg, outs = validate_sharded(0, model, crit, batches)
+    assert model.training and len(outs) == 3
+    model.eval()
+    tot, parts = 0.0, {k: 0.0 for k in indiv}
+    with torch.no_grad():
+        for b in batches:
+            i, t, _ = model.parse_batch(0, b)
+            l, d = crit(model(i), t, 0)
+            tot += l.item()
+            for k in parts:
+                parts[k] += d[k]
+    assert abs(loss - tot / 3) < 1e-5 * abs(tot / 3)
+    for k in parts:
+        assert abs(indiv[k] - parts[k] / 3) < 1e-5 * max(abs(parts[k] / 3), 1e-6)

@@ -9,7 +9,7 @@
 namespace dx {
 
 static thread_local char g_err[1024] = "";
-static int g_backend = DX_GEMM_FP32_CUDA_CORES;
+static int g_backend = DX_GEMM_TCGEN05_BF16X3;   // default: tcgen05 bf16 hi|lo split, fp32-grade (ops.py mirrors this)
 static const StepState* g_step_state = nullptr;   // graph mode: device block of per-step scalars (dx_set_step_state)
 static unsigned long long g_launches = 0;   // kernels launched by this library (every launch goes through check_launch)
 
@@ -41,6 +41,7 @@ extern "C" {
 const char* dx_last_error(void) { return g_err; }
 int dx_abi_version(void) { return DX_ABI_VERSION; }
 uint64_t dx_launch_count(void) { return g_launches; }
+uint64_t dx_tc_gemm_launch_count(void) { return tc_gemm_launches(); }
 int dx_set_step_state(const void* device_state) {
     g_step_state = static_cast<const StepState*>(device_state);
     return DX_OK;
@@ -168,6 +169,12 @@ int dx_relu_bwd(const float* dy, const float* y, float* dx_, size_t n, void* str
 int dx_scale_copy(const float* x, float* y, float alpha, size_t n, void* stream) { return scale_copy(x, y, alpha, n, ST(stream)); }
 
 size_t dx_attention_planes_bytes(int B, int S, int H, int dh) { return attention_planes_bytes(B, S, H, dh); }
+int dx_attention_uses_planes(int H, int dh) {
+    AttnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.H = H; a.dh = dh;
+    return (g_backend != DX_GEMM_FP32_CUDA_CORES && attention_mma_supported(a)) ? 1 : 0;
+}
 size_t dx_attention_bwd_scratch_bytes(int B, int S, int H, int dh) { return attention_bwd_scratch_bytes(B, S, H, dh); }
 
 int dx_attention_fwd(const float* qkv, const int64_t* lens, float* ctx, float* lse, void* planes, void* ctx_planes, int B, int S,
@@ -175,11 +182,11 @@ int dx_attention_fwd(const float* qkv, const int64_t* lens, float* ctx, float* l
     AttnArgs a;
     memset(&a, 0, sizeof(a));
     a.ctx_planes = ctx_planes;
-    DX_REQUIRE(!ctx_planes || (g_backend != DX_GEMM_FP32_CUDA_CORES && planes), "dx_attention_fwd: ctx_planes needs the tensor-core path");
     a.qkv = qkv; a.lens = (cll)lens; a.ctx = ctx; a.lse = lse; a.B = B; a.S = S; a.H = H; a.dh = dh;
     a.dropout_p = dropout_p; a.seed = seed;
     a.dyn = g_step_state;
     if (g_backend != DX_GEMM_FP32_CUDA_CORES && attention_mma_supported(a)) return attention_fwd_mma(a, planes, ST(stream));
+    DX_REQUIRE(!ctx_planes, "dx_attention_fwd: ctx_planes is only written by the tensor-core kernels (dx_attention_uses_planes(%d, %d) == 0)", H, dh);
     return attention_fwd(a, ST(stream));
 }
 
@@ -382,8 +389,11 @@ int dx_pitch_multiply(float* pitch, const float* factors, int B, int L, void* st
     return pitch_multiply(pitch, factors, B, L, ST(stream));
 }
 int dx_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
-                 float weight_decay, int step, float grad_scale, void* stream) {
-    return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, g_step_state, ST(stream));
+                 float weight_decay, int step, float grad_scale, const float* clip, void* stream) {
+    return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, g_step_state, clip, ST(stream));
+}
+int dx_grad_norm_clip(const float* g, size_t n, float grad_scale, float max_norm, float* out, void* stream) {
+    return grad_norm_clip(g, n, grad_scale, max_norm, out, ST(stream));
 }
 
 }  // extern "C"

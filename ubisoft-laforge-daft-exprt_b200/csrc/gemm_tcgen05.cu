@@ -801,6 +801,7 @@ int make_map_3d(CUtensorMap* map, const void* ptr, int esz, uint64_t d0, uint64_
 
 int g_num_sms = 0;
 int g_prec = PREC_BF16X3;
+unsigned long long g_tc_launches = 0;
 
 int num_sms() {
     if (g_num_sms == 0) {
@@ -821,6 +822,7 @@ int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, 
     }
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
     gemm_tc_kernel<PREC, MODE><<<grid, NTHREADS, smem_bytes<PREC, MODE>(), st>>>(ah, al, bh, bl, my, p);
+    ++g_tc_launches;
     return check_launch("gemm_tc");
 }
 
@@ -859,6 +861,7 @@ int make_tma_map_3d(void* map, const void* ptr, int esz, unsigned long long d0, 
 
 void set_tc_precision(int tf32) { g_prec = tf32 ? PREC_TF32 : PREC_BF16X3; }
 void set_tc_trace(long long* buf) { g_trace = buf; }
+unsigned long long tc_gemm_launches() { return g_tc_launches; }
 long long* tc_trace_buffer() { return g_trace; }
 
 int split_activation_planes(const float* x, int ld, void* planes, float* colsum_out, int rows, int C, cudaStream_t st) {

@@ -64,6 +64,7 @@ int pack_conv_weight(const float* w, float* fwd, float* dgrad, void* fwd_planes,
 // tcgen05 / TMEM / TMA path (gemm_tcgen05.cu)
 void set_tc_precision(int tf32);
 void set_tc_trace(long long* buf);
+unsigned long long tc_gemm_launches();   // gemm_tc_kernel launches so far
 int split_weight_planes(const float* w, void* planes, size_t n, cudaStream_t st);
 int split_activation_planes(const float* x, int ld, void* planes, float* colsum_out, int rows, int C, cudaStream_t st);
 size_t conv_gemm_tc_workspace(const ConvGemmArgs& a);
@@ -249,6 +250,8 @@ int pitch_multiply(float* pitch, const float* factors, int B, int L, cudaStream_
 
 // fused Adam step over a flat parameter buffer (optim.cu): torch.optim.Adam semantics (L2 weight decay added to grad)
 int adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
-              float weight_decay, int step, float grad_scale, const StepState* dyn, cudaStream_t st);
+              float weight_decay, int step, float grad_scale, const StepState* dyn, const float* clip, cudaStream_t st);
+// clip_grad_norm_ on the device: out[3] = {norm of grad_scale * g, clip coefficient, scratch}; `clip` above = this buffer
+int grad_norm_clip(const float* g, size_t n, float grad_scale, float max_norm, float* out, cudaStream_t st);
 
 }  // namespace dx

@@ -64,6 +64,21 @@ class FlatGradSync:
                 grads.append(p.grad)
         torch._foreach_copy_(views, grads)
 
+    def accumulate(self, alpha=1.0):
+        """mode='gather', gradient accumulation (reference train.py:379,391: loss / accumulation_steps, backward per micro-batch):
+        flat += alpha * grads with ONE multi-tensor add, then drop the per-parameter gradients so the next micro-batch's
+        backward starts clean.  The caller zeroes `flat` once per optimiser step."""
+        assert self.mode == 'gather'
+        views, grads = [], []
+        for p, v in zip(self.params, self.views):
+            if p.grad is not None:
+                views.append(v)
+                grads.append(p.grad)
+        if views:
+            torch._foreach_add_(views, grads, alpha=alpha)
+        for p in self.params:
+            p.grad = None
+
     def world_size(self):
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
@@ -91,17 +106,28 @@ def broadcast_parameters(module, src=0, process_group=None):
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src=src, group=process_group)
+    from . import ops
+    ops.invalidate_packed_weights()   # p.data writes do not bump tensor versions: cached weight packs are stale on non-src ranks
 
 
 class FlatAdam:
     """torch.optim.Adam semantics (reference train.py:299-301: betas (0.9, 0.98), eps 1e-9, weight_decay 1e-6) as ONE fused
-    kernel over flat parameter / gradient / moment buffers.  Parameters are re-pointed at views of the flat buffer."""
+    kernel over flat parameter / gradient / moment buffers.  Parameters are re-pointed at views of the flat buffer.
 
-    def __init__(self, params, sync: FlatGradSync, lr=1e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6):
+    The parts of the torch.optim interface the reference's loop touches are kept: `param_groups` (train.py:316,405-408 read and
+    write `param_group['lr']`), `state_dict()` / `load_state_dict()` in torch.optim.Adam's own format (save/load_checkpoint,
+    train.py:77,122-128 — a checkpoint written by the reference's Adam loads here and vice versa), `zero_grad()`, `step()`.
+    `grad_clip_thresh` reproduces `clip_grad_norm_` (train.py:399) on the device; `last_grad_norm()` reads the norm back."""
+
+    def __init__(self, params, sync: FlatGradSync, lr=1e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6,
+                 grad_clip_thresh=float('inf'), track_grad_norm=False):
         self.sync = sync
         self.params = sync.params
         assert [id(p) for p in self.params] == [id(p) for p in params if p.requires_grad]
-        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.param_groups = [dict(params=self.params, lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay,
+                                  amsgrad=False, maximize=False)]
+        self.grad_clip_thresh = float(grad_clip_thresh)
+        self.track_grad_norm = bool(track_grad_norm)
         self.flat_p = torch.zeros_like(sync.flat)
         with torch.no_grad():
             for p, off in zip(self.params, sync.offsets):
@@ -110,15 +136,75 @@ class FlatAdam:
                 p.data = self.flat_p[off:off + n].view_as(p)
         self.m = torch.zeros_like(self.flat_p)
         self.v = torch.zeros_like(self.flat_p)
+        self.grad_stats = torch.zeros(4, device=self.flat_p.device, dtype=torch.float32)   # {norm, clip coefficient, scratch}
         self.step_count = 0
+
+    # the scalar hyper-parameters live in param_groups[0] (what the reference's loop edits); these are views of it
+    lr = property(lambda self: self.param_groups[0]['lr'], lambda self, v: self.param_groups[0].__setitem__('lr', v))
+    betas = property(lambda self: self.param_groups[0]['betas'], lambda self, v: self.param_groups[0].__setitem__('betas', tuple(v)))
+    eps = property(lambda self: self.param_groups[0]['eps'], lambda self, v: self.param_groups[0].__setitem__('eps', v))
+    weight_decay = property(lambda self: self.param_groups[0]['weight_decay'],
+                            lambda self, v: self.param_groups[0].__setitem__('weight_decay', v))
+
+    def wants_clip(self):
+        return self.track_grad_norm or self.grad_clip_thresh != float('inf')
+
+    def launch(self, step, grad_scale, stream=None):
+        """Issue (clip +) Adam for optimiser step number `step` on the current stream; no host-side state changes."""
+        from . import ops
+        st = ops._st() if stream is None else stream
+        clip = None
+        if self.wants_clip():
+            ops._call('dx_grad_norm_clip', self.sync.flat.data_ptr(), self.sync.flat.numel(), float(grad_scale),
+                      float(self.grad_clip_thresh), self.grad_stats.data_ptr(), st)
+            clip = self.grad_stats.data_ptr()
+        ops._call('dx_adam_step', self.flat_p.data_ptr(), self.sync.flat.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                  self.flat_p.numel(), float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                  float(self.weight_decay), int(step), float(grad_scale), clip, st)
 
     def step(self, grad_scale=1.0):
         from . import ops
         self.step_count += 1
-        ops._call('dx_adam_step', self.flat_p.data_ptr(), self.sync.flat.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-                  self.flat_p.numel(), float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
-                  float(self.weight_decay), self.step_count, float(grad_scale), ops._st())
+        self.launch(self.step_count, grad_scale)
         ops.invalidate_packed_weights()   # raw-pointer update does not bump tensor versions
 
-    def zero_grad(self):
+    def last_grad_norm(self):
+        """Gradient norm of the last step (device->host read; needs grad_clip_thresh < inf or track_grad_norm)."""
+        return float(self.grad_stats[0].item())
+
+    def zero_grad(self, set_to_none=True):
         self.sync.zero_grad()
+
+    # -- torch.optim.Adam checkpoint format ---------------------------------------------------------------------------------
+    def state_dict(self):
+        state = {}
+        if self.step_count > 0:
+            for i, (p, off) in enumerate(zip(self.params, self.sync.offsets)):
+                n = p.numel()
+                state[i] = {'step': torch.tensor(float(self.step_count)),
+                            'exp_avg': self.m[off:off + n].view_as(p).clone(),
+                            'exp_avg_sq': self.v[off:off + n].view_as(p).clone()}
+        group = {k: v for k, v in self.param_groups[0].items() if k != 'params'}
+        group['params'] = list(range(len(self.params)))
+        return {'state': state, 'param_groups': [group]}
+
+    def load_state_dict(self, sd):
+        groups = sd['param_groups']
+        if len(groups) != 1 or len(groups[0]['params']) != len(self.params):
+            raise ValueError('FlatAdam.load_state_dict: expected one param group covering every parameter')
+        for k, v in groups[0].items():
+            if k != 'params' and k in self.param_groups[0]:
+                self.param_groups[0][k] = tuple(v) if k == 'betas' else v
+        self.m.zero_()
+        self.v.zero_()
+        steps = set()
+        with torch.no_grad():
+            for i, st in sd['state'].items():
+                off, p = self.sync.offsets[int(i)], self.params[int(i)]
+                n = p.numel()
+                self.m[off:off + n].copy_(st['exp_avg'].reshape(-1))
+                self.v[off:off + n].copy_(st['exp_avg_sq'].reshape(-1))
+                steps.add(int(float(st['step'])))
+        if len(steps) > 1:
+            raise ValueError('FlatAdam.load_state_dict: parameters with different step counts are not supported')
+        self.step_count = steps.pop() if steps else 0

@@ -10,7 +10,7 @@ _DEFAULTS = dict(
     # features (hparams.py:40-46)
     centered=True, sampling_rate=22050, n_mel_channels=80, filter_length=1024, hop_length=256,
     # training (hparams.py:58-67)
-    seed=1234, batch_size=16, accumulation_steps=3,
+    seed=1234, batch_size=16, accumulation_steps=3, grad_clip_thresh=float('inf'),
     # loss weights (hparams.py:70-76)
     lambda_reversal=1., adv_max_weight=1e-2, post_mult_weight=1e-3, dur_weight=1., energy_weight=1., pitch_weight=1.,
     mel_spec_weight=1.,

@@ -261,22 +261,50 @@ class DaftExprt(nn.Module):
         self.gaussian_upsampling = GaussianUpsamplingModule(hparams)
         self.frame_decoder = FrameDecoder(hparams)
         self._stats_cache = None
+        # weights written behind autograd's back (checkpoint load into re-pointed storage) must not meet stale packs
+        self.register_load_state_dict_post_hook(lambda module, incompatible: ops.invalidate_packed_weights())
 
     # -- model.py:727-753 ------------------------------------------------------------------------------------------------
     def parse_batch(self, gpu, batch):
-        (symbols, durations_float, durations_int, symbols_energy, symbols_pitch, input_lengths, frames_energy, frames_pitch,
-         mel_specs, output_lengths, speaker_ids, feature_dirs, feature_files) = batch
         dev = torch.device('cuda', gpu) if isinstance(gpu, int) else torch.device(gpu)
-        f = lambda t: t.to(dev, non_blocking=True).float()
-        i = lambda t: t.to(dev, non_blocking=True).long()
-        symbols, durations_int, input_lengths = i(symbols), i(durations_int), i(input_lengths)
-        output_lengths, speaker_ids = i(output_lengths), i(speaker_ids)
-        durations_float, symbols_energy, symbols_pitch = f(durations_float), f(symbols_energy), f(symbols_pitch)
-        frames_energy, frames_pitch, mel_specs = f(frames_energy), f(frames_pitch), f(mel_specs)
+        if hasattr(batch, 'to_device'):
+            # data.FlatBatch: the 11 tensors live in ONE (pinned) byte buffer -> ONE host->device copy, device views, no casts
+            self._check_ids(batch.tensors()[0], batch.tensors()[10], training_batch=True)
+            inputs = batch.to_device(dev)
+            targets = (inputs[1], inputs[3], inputs[4], inputs[8], inputs[10])
+            return inputs, targets, (batch.feature_dirs, batch.feature_files)
+        else:
+            (symbols, durations_float, durations_int, symbols_energy, symbols_pitch, input_lengths, frames_energy, frames_pitch,
+             mel_specs, output_lengths, speaker_ids, feature_dirs, feature_files) = batch
+            self._check_ids(symbols, speaker_ids, training_batch=True)
+            f = lambda t: t.to(dev, non_blocking=True).float()
+            i = lambda t: t.to(dev, non_blocking=True).long()
+            symbols, durations_int, input_lengths = i(symbols), i(durations_int), i(input_lengths)
+            output_lengths, speaker_ids = i(output_lengths), i(speaker_ids)
+            durations_float, symbols_energy, symbols_pitch = f(durations_float), f(symbols_energy), f(symbols_pitch)
+            frames_energy, frames_pitch, mel_specs = f(frames_energy), f(frames_pitch), f(mel_specs)
         inputs = (symbols, durations_float, durations_int, symbols_energy, symbols_pitch, input_lengths,
                   frames_energy, frames_pitch, mel_specs, output_lengths, speaker_ids)
         targets = (durations_float, symbols_energy, symbols_pitch, mel_specs, speaker_ids)
         return inputs, targets, (feature_dirs, feature_files)
+
+    def _check_ids(self, symbols, speaker_ids, training_batch):
+        """The reference raises on out-of-range ids (nn.Embedding IndexError, model.py:424,497; cross_entropy 'Target out of
+        bounds', loss.py:60 — the classifier has n_speakers - 1 classes, model.py:274).  The kernels clamp instead of faulting, so
+        the range is checked here, on the HOST copy of the batch (no device sync); device-resident ids are checked by
+        `inference` through its single read-back."""
+        if symbols.device.type != 'cpu' or symbols.numel() == 0:
+            return
+        n_sym = self.phoneme_encoder.symbols_embedding.num_embeddings
+        n_spk = self.prosody_encoder.spk_embedding.num_embeddings
+        lo, hi = int(symbols.min()), int(symbols.max())
+        if lo < 0 or hi >= n_sym:
+            raise IndexError(f'symbol id out of range [0, {n_sym}): min {lo}, max {hi}')
+        lo, hi = int(speaker_ids.min()), int(speaker_ids.max())
+        lim = n_spk - 1 if training_batch else n_spk
+        if lo < 0 or hi >= lim:
+            raise IndexError(f'speaker id out of range [0, {lim}): min {lo}, max {hi}'
+                             + (' (the speaker classifier has n_speakers - 1 classes)' if training_batch else ''))
 
     @staticmethod
     def _stack_films(films):
@@ -371,7 +399,13 @@ class DaftExprt(nn.Module):
         else:
             pitch_preds = self.pitch_multiply(pitch_preds, pitch_factors)
         totals, err = self._last_int_dur_status
-        status = torch.stack((totals.max(), err.max().long())).tolist()   # ONE read-back: T_max and the error flag
+        # ONE read-back: T_max, the error flag and the id ranges (the kernels clamp ids; the reference raises IndexError)
+        status = torch.stack((totals.max(), err.max().long(), symbols.max(), symbols.min(), speaker_ids.max(), speaker_ids.min())).tolist()
+        n_sym = self.phoneme_encoder.symbols_embedding.num_embeddings
+        n_spk = self.prosody_encoder.spk_embedding.num_embeddings
+        if status[3] < 0 or status[2] >= n_sym or status[5] < 0 or status[4] >= n_spk:
+            raise IndexError(f'symbol / speaker id out of range: symbols [{status[3]}, {status[2]}] vs {n_sym}, '
+                             f'speakers [{status[5]}, {status[4]}] vs {n_spk}')
         if status[1] != 0:
             raise IndexError('get_int_durations: predicted durations too short to cover the frame grid '
                              '(the reference raises here too, extract_features.py:88-92)')

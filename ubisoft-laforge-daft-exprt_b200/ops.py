@@ -30,7 +30,7 @@ _weights_epoch = 0
 _pack_cache = {}
 _desc_tables = {}
 _seed_counter = [0]
-_backend = [cabi.DX_GEMM_FP32_CUDA_CORES]
+_backend = [cabi.DX_GEMM_TCGEN05_BF16X3]   # same default as the library (cabi.cu: g_backend)
 launch_count = [0]   # number of C-ABI compute calls issued (each launches >= 1 of our kernels)
 
 
@@ -99,10 +99,28 @@ def _check_input(t, dtype=torch.float32):
 # ----------------------------------------------------------------------------------------------------------------------
 class PackedWeight:
     """fp32 packed layout [KW, N, K] + (bf16x3 backend) cached bf16 hi|lo planes of the same layout."""
-    __slots__ = ('w', 'planes', 'shape')
+    __slots__ = ('w', 'planes', 'shape', 'gen')
 
     def __init__(self, w, planes):
         self.w, self.planes, self.shape = w, planes, tuple(w.shape)
+        self.gen = 0   # bumped every time the buffers are refilled in place with new weight values
+
+
+def hold_packs(ctx, *packs):
+    """Remember the dgrad packs a backward will consume together with their fill generation."""
+    ctx.packed = packs if len(packs) != 1 else packs[0]
+    ctx.packed_gen = tuple(p.gen for p in packs)
+
+
+def held_packs(ctx):
+    """The packs saved by `hold_packs`; raises when one of them was refilled with NEWER weights since the forward (forward(A),
+    optimiser step, forward(B), backward(A) would otherwise silently use the new weights for A's dgrad)."""
+    packs = ctx.packed if isinstance(ctx.packed, (tuple, list)) else (ctx.packed,)
+    for p, g in zip(packs, ctx.packed_gen):
+        if p.gen != g:
+            raise RuntimeError('daft_exprt_b200: a packed weight was refilled (the parameters changed) between this forward and '
+                               'its backward; run backward before the next optimiser step + forward of the same model')
+    return ctx.packed
 
 
 def packed(weight):
@@ -123,6 +141,8 @@ def packed(weight):
     if hit is not None and hit[0][3] == ver[3] and hit[1].w.device == w.device:
         fwd, dgrad = hit[1], hit[2]                  # same weight, same backend: refill the existing buffers
         _call('dx_pack_conv_weight', _p(w), _p(fwd.w), _p(dgrad.w), _p(fwd.planes), _p(dgrad.planes), cout, cin, kw, rnd, _st())
+        fwd.gen += 1
+        dgrad.gen += 1
     else:
         fw = torch.empty(kw, cout, cin, device=w.device, dtype=torch.float32)
         dg = torch.empty(kw, cin, cout, device=w.device, dtype=torch.float32)
@@ -168,6 +188,8 @@ def prepack(weights):
     rnd = 1 if _backend[0] == cabi.DX_GEMM_TCGEN05_TF32 else 0
     _call('dx_pack_conv_weights_batched', _p(table[0]), len(stale), table[1], rnd, _st())
     for wt, _, ver, hit in stale:
+        hit[1].gen += 1
+        hit[2].gen += 1
         _pack_cache[id(wt)] = (ver, hit[1], hit[2], hit[3])
 
 
@@ -260,8 +282,9 @@ def conv_wgrad(x, dy, B, S, cin, cout, kw, shape, want_bias=True, ldx=None, alph
 
 
 def attention_planes(B, S, H, dh, device):
-    """Workspace for the tensor-core attention's operand planes (None with the exact-fp32 backend)."""
-    if _backend[0] == cabi.DX_GEMM_FP32_CUDA_CORES:
+    """Workspace for the tensor-core attention's operand planes; None when dx_attention_fwd will run the exact-fp32 kernels
+    (fp32 backend, or a head layout the tensor-core kernels do not cover), which never write planes."""
+    if not lib().dx_attention_uses_planes(H, dh):
         return None
     return torch.empty(lib().dx_attention_planes_bytes(B, S, H, dh), device=device, dtype=torch.uint8)
 
@@ -343,14 +366,14 @@ class AttentionSubLayer(torch.autograd.Function):
         proj = conv_gemm(att, out_wp, out_b, B, S, x_planes=attP, lens=lens)   # rows >= len are masked by the LayerNorm kernel
         y, xhat, rstd = ln_fwd(proj, x, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p_drop, seed_in=seed_out, emit_planes=True)
         ctx.save_for_backward(x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b, xP, attP, planes)
-        ctx.packed = (in_wd, out_wd)
+        hold_packs(ctx, in_wd, out_wd)
         ctx.cfg = (B, S, D, nb_heads, dh, float(p_drop), seed_attn, seed_out, in_w.shape, out_w.shape)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b, xP, attP, planes = ctx.saved_tensors
-        in_wd, out_wd = ctx.packed
+        in_wd, out_wd = held_packs(ctx)
         B, S, D, H, dh, p, seed_attn, seed_out, in_shape, out_shape = ctx.cfg
         dy = _check_input(dy)
         dv, dproj, dln_w, dln_b, _, dprojP, dpb = ln_bwd(dy, xhat, rstd, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p, seed_in=seed_out,
@@ -393,14 +416,14 @@ class ConvFFSubLayer(torch.autograd.Function):
             assert film.shape[1] == 2 * D   # reference model.py:232
         y, xhat, rstd = ln_fwd(o, x, ln_w, ln_b, film, 2 * D, lens, B, S, D, p_in=p_drop, seed_in=seed, emit_planes=True)
         ctx.save_for_backward(x, lens, h, xhat, rstd, ln_w, ln_b, film, xP, hP)
-        ctx.packed = (w1d, w2d)
+        hold_packs(ctx, w1d, w2d)
         ctx.cfg = (B, S, D, C, float(p_drop), seed, w1.shape, w2.shape)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, lens, h, xhat, rstd, ln_w, ln_b, film, xP, hP = ctx.saved_tensors
-        w1d, w2d = ctx.packed
+        w1d, w2d = held_packs(ctx)
         B, S, D, C, p, seed, w1_shape, w2_shape = ctx.cfg
         dy = _check_input(dy)
         dv, do, dln_w, dln_b, dfilm, doP, dob = ln_bwd(dy, xhat, rstd, ln_w, ln_b, film, 2 * D, lens, B, S, D, p_in=p, seed_in=seed,
@@ -450,7 +473,7 @@ class PreNet(torch.autograd.Function):
         ctx.halos = halos
         ctx.save_for_backward(*saved)
         ctx.in_planes = in_planes   # bf16 planes of each layer's input (not autograd tensors of interest: plain buffers)
-        ctx.packed = wds
+        hold_packs(ctx, *wds)
         ctx.cfg = (B, T, M, float(p_drop), seeds, (w0.shape, w1.shape, w2.shape))
         return cur
 
@@ -465,7 +488,7 @@ class PreNet(torch.autograd.Function):
         d = _check_input(dy)
         for i in (2, 1, 0):
             a, xhat, rstd, g, e, _y = layers[i]
-            wd = ctx.packed[i]
+            wd = held_packs(ctx)[i]
             cout, cin, kw = shapes[i]
             inp = x if i == 0 else layers[i - 1][5]
             dpre, _, dg, de, _, dpreP, dpreb = ln_bwd(d, xhat, rstd, g, e, None, 0, None, B, T, cout, relu_src=a, p_out=p,
@@ -565,14 +588,14 @@ class FilmHead(torch.autograd.Function):
                 outs.append(film[:, col: col + 2 * ch].contiguous())
                 col += 2 * ch
         ctx.save_for_backward(h, graw, braw, post)
-        ctx.packed = (gwd, bwd)
+        hold_packs(ctx, gwd, bwd)
         ctx.cfg = (B, NF, tuple(nb_blocks), tuple(channels), gw.shape, bw.shape)
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *douts):
         h, graw, braw, post = ctx.saved_tensors
-        gwd, bwd = ctx.packed
+        gwd, bwd = held_packs(ctx)
         B, NF, nb_blocks, channels, gshape, bshape = ctx.cfg
         parts, k = [], 0
         for nb, ch in zip(nb_blocks, channels):
@@ -605,14 +628,14 @@ class Linear(torch.autograd.Function):
         wp, wd = packed(w)
         y = linear_rows(x, wp, b, relu=relu)
         ctx.save_for_backward(x, y if relu else None)
-        ctx.packed = wd
+        hold_packs(ctx, wd)
         ctx.cfg = (relu, float(grad_in_scale), w.shape)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, y = ctx.saved_tensors
-        wd = ctx.packed
+        wd = held_packs(ctx)
         relu, scale, wshape = ctx.cfg
         dy = _check_input(dy)
         R, cout, cin = x.shape[0], wshape[0], wshape[1]
@@ -669,14 +692,14 @@ class Predictor(torch.autograd.Function):
         out = torch.empty(NO, B, L, device=x.device, dtype=torch.float32)
         _call('dx_narrow_linear_fwd', _p(y1), _p(pw), _p(pb), _p(lens), _p(out), B, L, C, NO, _st())
         ctx.save_for_backward(x, lens, film, a0, y0, xh0, rs0, a1, y1, xh1, rs1, g0, e0, g1, e1, pw)
-        ctx.packed = (w0d, w1d)
+        hold_packs(ctx, w0d, w1d)
         ctx.cfg = (B, L, D, C, NO, float(p_drop), s0, s1, w0.shape, w1.shape)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, lens, film, a0, y0, xh0, rs0, a1, y1, xh1, rs1, g0, e0, g1, e1, pw = ctx.saved_tensors
-        w0d, w1d = ctx.packed
+        w0d, w1d = held_packs(ctx)
         B, L, D, C, NO, p, s0, s1, w0s, w1s = ctx.cfg
         dout = _check_input(dout)
         dy1 = torch.empty(B, L, C, device=dout.device, dtype=torch.float32)
@@ -754,14 +777,14 @@ class MelProjection(torch.autograd.Function):
         mel = torch.empty(B, M, T, device=x.device, dtype=torch.float32)
         _call('dx_mask_transpose_fwd', _p(y), _p(lens), _p(mel), B, T, M, _st())
         ctx.save_for_backward(x, lens)
-        ctx.packed = wd
+        hold_packs(ctx, wd)
         ctx.cfg = (B, T, D, M, w.shape)
         return mel
 
     @staticmethod
     def backward(ctx, dmel):
         x, lens = ctx.saved_tensors
-        wd = ctx.packed
+        wd = held_packs(ctx)
         B, T, D, M, wshape = ctx.cfg
         dmel = _check_input(dmel)
         dy = torch.empty(B, T, M, device=dmel.device, dtype=torch.float32)
