@@ -118,6 +118,14 @@ int dx_attention_uses_planes(int H, int dh);
 size_t dx_attention_bwd_scratch_bytes(int B, int S, int H, int dh);
 /* ctx_planes (nullable, tensor-core backends): ctx additionally as bf16 hi|lo operand planes [2][B*S][H*dh] for the
  * out-projection GEMM (no split pass over ctx). */
+/* Fused in-projection -> attention operand planes (bf16x3 backend): qkv = x W_in^T + b_in (model.py:165, nn.MultiheadAttention's
+ * in_proj) is never materialised in fp32; the tcgen05 GEMM epilogue writes `planes` (the dx_attention_planes_bytes() workspace)
+ * directly: per-head bf16 hi|lo planes, q pre-scaled by 1/sqrt(dh), rows in [S, pad64(S)) zero.  Follow with
+ * dx_attention_fwd(qkv = NULL, ..., planes).  x_planes: bf16 hi|lo planes [2][B*S][Cin] of x; w_planes: planes of the packed
+ * in_proj weight [1][3*H*dh][Cin]; lens: rows >= lens[b] may be skipped (their keys are masked, their queries unused). */
+int dx_inproj_head_planes(const void* x_planes, const void* w_planes, const float* bias, void* head_planes, const int64_t* lens,
+                          int B, int S, int Cin, int H, int dh, void* stream);
+/* qkv may be NULL when `planes` was filled by dx_inproj_head_planes (tensor-core backends only). */
 int dx_attention_fwd(const float* qkv, const int64_t* lens, float* ctx, float* lse, void* planes, void* ctx_planes, int B, int S,
                      int H, int dh, float dropout_p, uint64_t seed, void* stream);
 /* scratch: dx_attention_bwd_scratch_bytes() bytes; dqkv [B,S,3*H*dh] is fully written */

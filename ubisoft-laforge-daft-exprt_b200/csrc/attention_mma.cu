@@ -615,7 +615,9 @@ int attention_fwd_mma(const AttnArgs& a_in, void* planes, cudaStream_t st) {
     DX_REQUIRE(planes != nullptr, "attention_fwd_mma: planes workspace required (dx_attention_planes_bytes)");
     bind_planes(a, planes);
     const int D = a.H * a.dh;
-    int rc = prep(a.qkv, 3 * D, a.B, a.S, a.Sp, 3 * a.H, a.dh, D, rsqrtf((float)a.dh), (__nv_bfloat16*)a.R, (__nv_bfloat16*)a.Tr, st);
+    // qkv == NULL: the in-projection GEMM already wrote the operand planes itself (dx_inproj_head_planes): no fp32 qkv exists
+    int rc = a.qkv ? prep(a.qkv, 3 * D, a.B, a.S, a.Sp, 3 * a.H, a.dh, D, rsqrtf((float)a.dh), (__nv_bfloat16*)a.R, (__nv_bfloat16*)a.Tr, st)
+                   : DX_OK;
     if (rc) return rc;
     if (attn_tc_enabled() && attention_fwd_tc_supported(a)) return attention_fwd_tc(a, st);   // tcgen05 / TMEM forward
     switch (a.dh) {

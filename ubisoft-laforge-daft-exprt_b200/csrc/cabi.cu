@@ -128,6 +128,26 @@ int dx_conv_gemm(const float* x, const void* x_planes, const float* w_packed, co
     return conv_gemm_simt(a, ST(stream));
 }
 
+int dx_inproj_head_planes(const void* x_planes, const void* w_planes, const float* bias, void* head_planes, const int64_t* lens,
+                          int B, int S, int Cin, int H, int dh, void* stream) {
+    DX_REQUIRE(g_backend == DX_GEMM_TCGEN05_BF16X3, "dx_inproj_head_planes: needs the bf16x3 tensor-core backend");
+    DX_REQUIRE(x_planes && w_planes && head_planes, "dx_inproj_head_planes: x_planes, w_planes and head_planes are required");
+    AttnArgs at;
+    memset(&at, 0, sizeof(at));
+    at.H = H; at.dh = dh;
+    DX_REQUIRE(attention_mma_supported(at), "dx_inproj_head_planes: head layout H=%d dh=%d has no tensor-core attention", H, dh);
+    const int D = H * dh;
+    ConvGemmArgs a = gemm_args(nullptr, x_planes, nullptr, w_planes, bias, nullptr, nullptr, nullptr, nullptr, 0, B, S, Cin, 3 * D, 1, Cin,
+                               3 * D, 1.f, 0, 0, lens, 0);
+    a.head_planes = (void*)(((uintptr_t)head_planes + 255) & ~(uintptr_t)255);   // same alignment rule as the attention kernels (bind_planes)
+    a.head_dim = dh;
+    a.head_Sp = (S + 63) / 64 * 64;
+    a.head_scale_cols = D;
+    a.head_scale = rsqrtf((float)dh);
+    DX_REQUIRE(Cin % 8 == 0 && Cin >= 16, "dx_inproj_head_planes: Cin=%d", Cin);
+    return conv_gemm_tc(a, ST(stream));
+}
+
 static ConvWgradArgs wgrad_args(const float* x, const void* x_planes, const float* dy, const void* dy_planes, float* dw,
                                 float* dbias, void* ws, size_t wsb, int B, int S, int Cin, int Cout, int KW, int ldx, float alpha,
                                 const int64_t* lens = nullptr, int halo = 0) {
@@ -186,6 +206,7 @@ int dx_attention_fwd(const float* qkv, const int64_t* lens, float* ctx, float* l
     a.dropout_p = dropout_p; a.seed = seed;
     a.dyn = g_step_state;
     if (g_backend != DX_GEMM_FP32_CUDA_CORES && attention_mma_supported(a)) return attention_fwd_mma(a, planes, ST(stream));
+    DX_REQUIRE(qkv != nullptr, "dx_attention_fwd: qkv == NULL (planes pre-filled by dx_inproj_head_planes) needs the tensor-core kernels");
     DX_REQUIRE(!ctx_planes, "dx_attention_fwd: ctx_planes is only written by the tensor-core kernels (dx_attention_uses_planes(%d, %d) == 0)", H, dh);
     return attention_fwd(a, ST(stream));
 }

@@ -177,6 +177,11 @@ struct TcParams {
     __nv_bfloat16* y_planes;            // optional: output as bf16 hi|lo planes [2][B*S][Cout] (Cout % 32 == 0)
     long long y_plane_elems;            // B*S*Cout
     int skip_y;                         // no fp32 output (planes only)
+    // head-plane output (attention in-projection, skip_y = 1): the 32-column chunks go to per-head operand planes
+    // R[2][B][hp_NH][hp_Sp][hp_dh] (map_y is the (dh, Sp, 2*B*NH) map over R); columns < hp_scale_cols are multiplied by hp_scale
+    // (q pre-scaled by 1/sqrt(dh)); rows >= S are written as zeros up to Sp.  hp_dh == 0: off.
+    int hp_dh, hp_NH, hp_scale_cols;
+    float hp_scale;
     int B, S, Cin, Cout, KW, ldy;
     int tiles_m_per_b, tiles_n, num_tiles, k_chunks;   // CONV: tiles over (b, s) x n;  WGRAD: tiles_m = co tiles, tiles_n = ci tiles
     int nsplit;                                         // WGRAD: batch ranges
@@ -589,6 +594,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
                         for (int i = 0; i < 32; ++i) o[i] = round_tf32(o[i]);
                     }
+                    if (p.hp_dh) {
+                        const float sc = !row_ok ? 0.f : (nb < p.hp_scale_cols ? p.hp_scale : 1.f);   // rows in [S, Sp): zeros
+                        if (sc != 1.f) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] *= sc;
+                        }
+                    }
                 }
                 if (MODE != MODE_WGRAD && p.colsum && !dead) {
                     // column sums of this warp's 32 rows x 32 columns by recursive halving across the lanes (31 shuffles):
@@ -626,6 +638,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) split_pair_u32(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
+                    if (p.skip_y && p.hp_dh == 16) {
+                        // head planes, head_dim 16: the chunk covers two heads; four dense [32 rows][32 B] tiles (hi head 0, hi head 1,
+                        // lo head 0, lo head 1; the map over R has a 16-column box and no swizzle)
+                        if (lane == 0) tma_store_wait_read<0>();
+                        __syncwarp();
+#pragma unroll
+                        for (int sub = 0; sub < 2; ++sub) {
+                            const uint32_t rb = wbuf + sub * 1024 + lane * 32;
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rb + 16 * c), "r"(hi[8 * sub + 4 * c]),
+                                             "r"(hi[8 * sub + 4 * c + 1]), "r"(hi[8 * sub + 4 * c + 2]), "r"(hi[8 * sub + 4 * c + 3]) : "memory");
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rb + 2048 + 16 * c), "r"(lo[8 * sub + 4 * c]),
+                                             "r"(lo[8 * sub + 4 * c + 1]), "r"(lo[8 * sub + 4 * c + 2]), "r"(lo[8 * sub + 4 * c + 3]) : "memory");
+                            }
+                        }
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            const int hh = nb >> 4, pl = p.B * p.hp_NH;
+#pragma unroll
+                            for (int sub = 0; sub < 2; ++sub) {
+                                tma_store_3d(&map_y, wbuf + sub * 1024, 0, t.o1 + quad * 32, t.o2 * p.hp_NH + hh + sub);
+                                tma_store_3d(&map_y, wbuf + 2048 + sub * 1024, 0, t.o1 + quad * 32, pl + t.o2 * p.hp_NH + hh + sub);
+                            }
+                            tma_store_commit();
+                        }
+                        continue;
+                    }
                     if (p.skip_y) {
                         // planes only: stage hi | lo tiles (2 KB each) in this warp's buffer and TMA-store both (map_y is the
                         // bf16 planes map; rows >= S are clipped by the store).  The arithmetic above ran while the previous
@@ -644,8 +685,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
                         if (!(p.debug & 64)) fence_async_smem();
                         __syncwarp();
                         if (lane == 0 && !(p.debug & 8)) {
-                            tma_store_3d(&map_y, wbuf, nb, t.o1 + quad * 32, t.o2);
-                            tma_store_3d(&map_y, wbuf + 2048, nb, t.o1 + quad * 32, p.B + t.o2);
+                            if (p.hp_dh) {   // head planes, head_dim 32 / 64: one head per chunk (column d0 inside the head)
+                                const int hh = nb / p.hp_dh, d0 = nb - hh * p.hp_dh;
+                                tma_store_3d(&map_y, wbuf, d0, t.o1 + quad * 32, t.o2 * p.hp_NH + hh);
+                                tma_store_3d(&map_y, wbuf + 2048, d0, t.o1 + quad * 32, (p.B + t.o2) * p.hp_NH + hh);
+                            } else {
+                                tma_store_3d(&map_y, wbuf, nb, t.o1 + quad * 32, t.o2);
+                                tma_store_3d(&map_y, wbuf + 2048, nb, t.o1 + quad * 32, p.B + t.o2);
+                            }
                             tma_store_commit();
                         }
                         continue;
@@ -781,7 +828,8 @@ EncodeTiledFn get_encode() {
 
 // 3-D tensor (d0 contiguous), box (b0, b1, b2), SWIZZLE_128B (or 64B), zero OOB fill.  esz = 4 (fp32) or 2 (bf16).
 int make_map_3d(CUtensorMap* map, const void* ptr, int esz, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
-                uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, bool swizzle64 = false, bool swizzle32 = false) {
+                uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, bool swizzle64 = false, bool swizzle32 = false,
+                bool swizzle_none = false) {
     EncodeTiledFn enc = get_encode();
     DX_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[3] = {d0, d1, d2};
@@ -790,7 +838,8 @@ int make_map_3d(CUtensorMap* map, const void* ptr, int esz, uint64_t d0, uint64_
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                      const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : (swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
+                     swizzle_none ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                  : (swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : (swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B)),
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) esz=%d dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u,%u)",
@@ -902,7 +951,18 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     if (a.y_colsum) DX_CUDA(cudaMemsetAsync(a.y_colsum, 0, (size_t)a.Cout * sizeof(float), st));
     p.y_plane_elems = (long long)a.B * a.S * a.Cout;
     p.skip_y = a.y == nullptr;
-    DX_REQUIRE(a.y || a.y_planes, "conv_gemm_tc: no output (y and y_planes are both NULL)");
+    p.hp_dh = 0; p.hp_NH = 0; p.hp_scale_cols = 0; p.hp_scale = 1.f;
+    if (a.head_planes) {
+        DX_REQUIRE(!a.y && !a.y_planes && !a.y_colsum && g_prec == PREC_BF16X3, "conv_gemm_tc: head_planes is a planes-only bf16x3 output");
+        DX_REQUIRE((a.head_dim == 16 || a.head_dim == 32 || a.head_dim == 64) && a.Cout % a.head_dim == 0 && a.Cout % 32 == 0 &&
+                       a.head_Sp >= a.S && a.head_Sp % 8 == 0 && ((uintptr_t)a.head_planes & 15) == 0,
+                   "conv_gemm_tc: head_planes needs head_dim in {16, 32, 64}, Cout %% 32 == 0, Sp >= S (dh=%d Cout=%d Sp=%d S=%d)", a.head_dim,
+                   a.Cout, a.head_Sp, a.S);
+        p.y_planes = (__nv_bfloat16*)a.head_planes;
+        p.skip_y = 1;
+        p.hp_dh = a.head_dim; p.hp_NH = a.Cout / a.head_dim; p.hp_scale_cols = a.head_scale_cols; p.hp_scale = a.head_scale;
+    }
+    DX_REQUIRE(a.y || a.y_planes || a.head_planes, "conv_gemm_tc: no output (y and y_planes are both NULL)");
     DX_REQUIRE(!(a.y_planes || a.relu_src_hi) || (a.Cout % 32 == 0 && (((uintptr_t)a.y_planes | (uintptr_t)a.relu_src_hi) & 15) == 0),
                "conv_gemm_tc: y_planes / relu_src_hi need Cout %% 32 == 0 and 16-byte alignment (Cout = %d)", a.Cout);
     p.B = a.B; p.S = a.S; p.Cin = a.Cin; p.Cout = a.Cout; p.KW = a.KW; p.ldy = a.ldy;
@@ -916,7 +976,14 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     p.trace = g_trace;
     CUtensorMap mxh, mxl, mwh, mwl, my;
     int rc;
-    if (a.y) {
+    if (a.head_planes) {
+        // (dh, Sp, 2 * B * NH) over R[2][B][NH][Sp][dh]; 32-row boxes of min(32, dh) columns (64-byte rows: SWIZZLE_64B like the
+        // plain planes map; 32-byte rows for head_dim 16: dense)
+        const uint32_t bw = a.head_dim < 32 ? a.head_dim : 32;
+        if ((rc = make_map_3d(&my, a.head_planes, 2, a.head_dim, a.head_Sp, 2ull * a.B * p.hp_NH, (uint64_t)a.head_dim * 2,
+                              (uint64_t)a.head_Sp * a.head_dim * 2, bw, 32, 1, bw == 32, false, bw != 32)))
+            return rc;
+    } else if (a.y) {
         if ((rc = make_map_3d(&my, a.y, 4, a.Cout, a.S, a.B, (uint64_t)a.ldy * 4, (uint64_t)a.S * a.ldy * 4, 32, 32, 1))) return rc;
     } else {
         // planes-only output: ONE bf16 map over [2][B*S][Cout] seen as (Cout, S, 2B): the lo plane is utterance index B + b;

@@ -20,6 +20,11 @@ struct ConvGemmArgs {
     void* y_planes;         // optional (tensor-core path, Cout % 32 == 0): the output as bf16 hi|lo planes [2][B*S][Cout], written by the epilogue
     const void* relu_src_hi;  // optional (tensor-core path, Cout % 32 == 0): ReLU mask source as the bf16 hi plane [B*S][Cout] of the forward activation
     float* y_colsum;        // optional (tensor-core path): [Cout] column sums of the stored output over all B*S rows (zeroed + accumulated inside)
+    // optional (bf16x3 tensor-core path, the ONLY output then): the output as per-head attention operand planes
+    // R[2][B][Cout / head_dim][head_Sp][head_dim] (bf16 hi|lo), columns < head_scale_cols multiplied by head_scale, rows in [S, head_Sp) zero
+    void* head_planes = nullptr;
+    int head_dim = 0, head_Sp = 0, head_scale_cols = 0;
+    float head_scale = 1.f;
     int B, S, Cin, Cout, KW;
     int ldx, ldy;
     float alpha;

@@ -281,6 +281,17 @@ def conv_wgrad(x, dy, B, S, cin, cout, kw, shape, want_bias=True, ldx=None, alph
     return dw, (dbias if dbias is not None else db)
 
 
+_fused_inproj = [True]
+
+
+def fused_inproj(on=None):
+    """Get / set: in-projection GEMM writes the attention operand planes directly (default on; off = fp32 qkv + conversion pass,
+    kept for A/B tests)."""
+    if on is not None:
+        _fused_inproj[0] = bool(on)
+    return _fused_inproj[0] and _backend[0] == cabi.DX_GEMM_TCGEN05_BF16X3
+
+
 def attention_planes(B, S, H, dh, device):
     """Workspace for the tensor-core attention's operand planes; None when dx_attention_fwd will run the exact-fp32 kernels
     (fp32 backend, or a head layout the tensor-core kernels do not cover), which never write planes."""
@@ -355,12 +366,18 @@ class AttentionSubLayer(torch.autograd.Function):
         in_wp, in_wd = packed(in_w)
         out_wp, out_wd = packed(out_w)
         xP = planes_of(x, B * S, D)
-        qkv = conv_gemm(x, in_wp, in_b, B, S, x_planes=xP, lens=lens)   # rows >= len: keys masked, queries skipped
         att = torch.empty(B, S, D, device=x.device, dtype=torch.float32)
         lse = torch.empty(B, nb_heads, S, device=x.device, dtype=torch.float32)
         seed_attn, seed_out = (next_seed(), next_seed()) if p_drop > 0 else (0, 0)
         planes = attention_planes(B, S, nb_heads, dh, x.device)
         attP = torch.empty(2, B * S, D, device=x.device, dtype=torch.bfloat16) if (planes is not None and _uses_planes(D)) else None
+        if fused_inproj() and planes is not None and xP is not None and in_wp.planes is not None:
+            # the in-projection's epilogue writes the attention operand planes itself (per-head bf16 hi|lo, q pre-scaled): no fp32
+            # qkv tensor, no conversion pass (north_star: QKV projection fused into the attention operand hand-over)
+            qkv = None
+            _call('dx_inproj_head_planes', _p(xP), _p(in_wp.planes), _p(in_b), _p(planes), _p(lens), B, S, D, nb_heads, dh, _st())
+        else:
+            qkv = conv_gemm(x, in_wp, in_b, B, S, x_planes=xP, lens=lens)   # rows >= len: keys masked, queries skipped
         _call('dx_attention_fwd', _p(qkv), _p(lens), _p(att), _p(lse), _p(planes), _p(attP), B, S, nb_heads, dh, float(p_drop), seed_attn,
               _st())   # the kernel writes ctx and its operand planes
         proj = conv_gemm(att, out_wp, out_b, B, S, x_planes=attP, lens=lens)   # rows >= len are masked by the LayerNorm kernel
