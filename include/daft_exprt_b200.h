@@ -118,6 +118,17 @@ int dx_attention_uses_planes(int H, int dh);
 size_t dx_attention_bwd_scratch_bytes(int B, int S, int H, int dh);
 /* ctx_planes (nullable, tensor-core backends): ctx additionally as bf16 hi|lo operand planes [2][B*S][H*dh] for the
  * out-projection GEMM (no split pass over ctx). */
+/* GEMM + sub-layer tail in ONE kernel (bf16x3 backend, 128 output channels = one column tile of the tcgen05 GEMM):
+ *     v = dropout_{p_in}(conv_KW(x) + bias) + res;   xhat = (v - mean_c v) * rstd;   y = mask(film_g * (xhat * ln_w + ln_b) + film_b)
+ * replaces  out_proj -> dropout -> + query -> LayerNorm -> masked_fill  (model.py:186-191,259; KW = 1, film = NULL) and
+ *           conv2 -> dropout -> + x -> LayerNorm -> FiLM -> masked_fill (model.py:226-235,262; KW = 3).
+ * x_planes [2][B*S][Cin] / w_planes [KW][128][Cin] hi|lo: bf16 operand planes; res [B,S,128] nullable; film nullable (gamma at
+ * film[b*film_stride + c], beta at film[b*film_stride + 128 + c]); lens: rows >= lens[b] are written as zeros (y, xhat, rstd).
+ * Outputs: y [B,S,128] fp32, y_planes (nullable) [2][B*S][128] bf16 hi|lo for the next GEMM, xhat [B,S,128] and rstd [B*S]
+ * (what dx_ln_bwd consumes).  Same dropout mask as dx_ln_fwd for the same seed. */
+int dx_conv_gemm_ln(const void* x_planes, const void* w_planes, const float* bias, const float* res, const float* ln_w, const float* ln_b,
+                    const float* film, int film_stride, const int64_t* lens, float* y, void* y_planes, float* xhat, float* rstd, int B, int S,
+                    int Cin, int KW, float p_in, uint64_t seed_in, void* stream);
 /* Fused in-projection -> attention operand planes (bf16x3 backend): qkv = x W_in^T + b_in (model.py:165, nn.MultiheadAttention's
  * in_proj) is never materialised in fp32; the tcgen05 GEMM epilogue writes `planes` (the dx_attention_planes_bytes() workspace)
  * directly: per-head bf16 hi|lo planes, q pre-scaled by 1/sqrt(dh), rows in [S, pad64(S)) zero.  Follow with

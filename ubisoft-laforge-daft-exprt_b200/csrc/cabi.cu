@@ -148,6 +148,21 @@ int dx_inproj_head_planes(const void* x_planes, const void* w_planes, const floa
     return conv_gemm_tc(a, ST(stream));
 }
 
+int dx_conv_gemm_ln(const void* x_planes, const void* w_planes, const float* bias, const float* res, const float* ln_w, const float* ln_b,
+                    const float* film, int film_stride, const int64_t* lens, float* y, void* y_planes, float* xhat, float* rstd, int B, int S,
+                    int Cin, int KW, float p_in, uint64_t seed_in, void* stream) {
+    DX_REQUIRE(g_backend == DX_GEMM_TCGEN05_BF16X3, "dx_conv_gemm_ln: needs the bf16x3 tensor-core backend");
+    DX_REQUIRE(x_planes && w_planes && y && xhat && rstd, "dx_conv_gemm_ln: x_planes, w_planes, y, xhat and rstd are required");
+    DX_REQUIRE(B > 0 && S > 0 && Cin >= 16 && Cin % 8 == 0 && (KW == 1 || KW == 3), "dx_conv_gemm_ln: bad shape B=%d S=%d Cin=%d KW=%d", B, S, Cin, KW);
+    ConvGemmArgs a = gemm_args(nullptr, x_planes, nullptr, w_planes, bias, nullptr, nullptr, y, nullptr, 0, B, S, Cin, 128, KW, Cin, 128, 1.f, 0,
+                               0, lens, 0, nullptr, y_planes);
+    LnEpilogueArgs l;
+    l.res = res; l.ln_w = ln_w; l.ln_b = ln_b; l.film = film; l.film_stride = film_stride; l.xhat = xhat; l.rstd = rstd;
+    l.p_in = p_in; l.seed_in = seed_in; l.dyn = g_step_state;
+    a.ln = &l;
+    return conv_gemm_tc(a, ST(stream));
+}
+
 static ConvWgradArgs wgrad_args(const float* x, const void* x_planes, const float* dy, const void* dy_planes, float* dw,
                                 float* dbias, void* ws, size_t wsb, int B, int S, int Cin, int Cout, int KW, int ldx, float alpha,
                                 const int64_t* lens = nullptr, int halo = 0) {

@@ -35,6 +35,12 @@ namespace {
 
 enum { PREC_TF32 = 0, PREC_BF16X3 = 1 };
 enum { MODE_CONV = 0, MODE_WGRAD = 1, MODE_HALO = 2 };
+// EPI_LN (Cout = 128 = ONE column tile, BF16X3): the epilogue finishes the reference's sub-layer tail in place of a separate kernel
+//   v = dropout(acc + bias) + residual;  xhat = (v - mean) * rstd;  y = mask(film_g * (xhat * ln_w + ln_b) + film_b)
+// (model.py:189-191,259 after the attention out-projection; model.py:226-235,262 after conv2) and writes y (fp32 + bf16 hi|lo
+// operand planes for the next GEMM), xhat and rstd (saved for backward).  The two epilogue warps that share a TMEM lane quarter
+// (64 columns each) exchange their partial row sums through shared memory.
+enum { EPI_STD = 0, EPI_LN = 1 };
 // MODE_HALO = MODE_CONV for KW = 3 (BF16X3 only): the three taps are three row-shifted views of ONE activation tile, so the
 // tile is fetched once per channel chunk with its halo (rows s0-1 .. s0+128) and each tap's MMAs read it through a UMMA
 // descriptor whose start address is advanced by tap rows.  A traffic drops 3x, total operand traffic by a third.
@@ -54,9 +60,13 @@ constexpr int HALO_ROWS = TM + 2;                      // KW = 3
 constexpr int A_HALO_BYTES = 17 * 1024;                // 130 rows x 128 B rounded up to the 1024-byte swizzle repeat
 constexpr int HALO_A_STAGES = 2, HALO_B_STAGES = 3;
 constexpr int HALO_A_STAGE_BYTES = 2 * A_HALO_BYTES, HALO_B_STAGE_BYTES = 2 * TILE_BYTES;
-template <int PREC, int MODE> constexpr int smem_bytes() {
+constexpr int XCH_BYTES = 2 * 2 * 128 * 4;             // EPI_LN: two exchange slots x two column halves x 128 rows
+// k=1 GEMMs with the LayerNorm epilogue (the out-projection: K = 128 = two chunks) run a 2-stage ring to make room for it
+template <int PREC, int MODE, int EPI> constexpr int num_stages() { return (EPI == EPI_LN && MODE == MODE_CONV) ? 2 : Cfg<PREC>::NSTAGE; }
+template <int PREC, int MODE, int EPI = EPI_STD> constexpr int smem_bytes() {
     return (MODE == MODE_HALO ? HALO_A_STAGES * HALO_A_STAGE_BYTES + HALO_B_STAGES * HALO_B_STAGE_BYTES
-                              : Cfg<PREC>::NSTAGE * stage_bytes<PREC>()) + 2 * OUT_BYTES + 256 + 1024;
+                              : num_stages<PREC, MODE, EPI>() * stage_bytes<PREC>()) + 2 * OUT_BYTES + 256 + 1024 +
+           (EPI == EPI_LN ? XCH_BYTES : 0);
 }
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------------------
@@ -182,6 +192,17 @@ struct TcParams {
     // (q pre-scaled by 1/sqrt(dh)); rows >= S are written as zeros up to Sp.  hp_dh == 0: off.
     int hp_dh, hp_NH, hp_scale_cols;
     float hp_scale;
+    // EPI_LN
+    const float* ln_res;                // residual [B*S][Cout] or nullptr
+    const float* ln_w;
+    const float* ln_b;
+    const float* film;                  // nullable: gamma at film[b * film_stride + c], beta at film[b * film_stride + Cout + c]
+    int film_stride;
+    float* ln_rstd;                     // [B*S]
+    float ln_p_in;                      // dropout on (acc + bias) before the residual add
+    unsigned long long ln_seed_in;
+    const StepState* dyn;
+    int ln_planes;                      // also write y as bf16 hi|lo planes (map_y3)
     int B, S, Cin, Cout, KW, ldy;
     int tiles_m_per_b, tiles_n, num_tiles, k_chunks;   // CONV: tiles over (b, s) x n;  WGRAD: tiles_m = co tiles, tiles_n = ci tiles
     int nsplit;                                         // WGRAD: batch ranges
@@ -259,13 +280,17 @@ __device__ __forceinline__ bool tile_dead(const TcParams& p, const TileCoord& t)
     return true;
 }
 
-template <int PREC, int MODE>
+template <int PREC, int MODE, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                                                          const __grid_constant__ CUtensorMap map_a_lo,
                                                          const __grid_constant__ CUtensorMap map_b_hi,
                                                          const __grid_constant__ CUtensorMap map_b_lo,
-                                                         const __grid_constant__ CUtensorMap map_y, TcParams p) {
-    constexpr int NSTAGE = Cfg<PREC>::NSTAGE, PLANES = Cfg<PREC>::PLANES, TKB = Cfg<PREC>::TKB;
+                                                         const __grid_constant__ CUtensorMap map_y,
+                                                         const __grid_constant__ CUtensorMap map_y2,   // EPI_LN: xhat (fp32)
+                                                         const __grid_constant__ CUtensorMap map_y3,   // EPI_LN: y planes (bf16)
+                                                         TcParams p) {
+    constexpr int NSTAGE = num_stages<PREC, MODE, EPI>(), PLANES = Cfg<PREC>::PLANES, TKB = Cfg<PREC>::TKB;
+    static_assert(EPI == EPI_STD || (PREC == PREC_BF16X3 && MODE != MODE_WGRAD), "EPI_LN is a BF16X3 forward epilogue");
     constexpr int STAGE_BYTES = stage_bytes<PREC>();
     static_assert(MODE != MODE_HALO || PREC == PREC_BF16X3, "MODE_HALO is a BF16X3 variant");
     extern __shared__ uint8_t smem_raw[];
@@ -276,7 +301,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     const uint32_t full0 = bars, empty0 = bars + 8 * NSTAGE, tfull0 = bars + 16 * NSTAGE, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
     const uint32_t afull0 = bars + 96, aempty0 = bars + 112;   // MODE_HALO: full0/empty0 are the B ring (NSTAGE = HALO_B_STAGES = 3)
-    static_assert(MODE != MODE_HALO || Cfg<PREC>::NSTAGE == HALO_B_STAGES, "B ring shares the full/empty barrier slots");
+    static_assert(MODE != MODE_HALO || NSTAGE == HALO_B_STAGES, "B ring shares the full/empty barrier slots");
+    const uint32_t xch = bars + 256;   // EPI_LN: [slot][half][row] fp32
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -518,6 +544,127 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
             const int s = t.o1 + row;
             const bool row_ok = MODE != MODE_WGRAD && s < p.S;
             const size_t grow = (size_t)t.o2 * p.S + s;
+            if constexpr (EPI == EPI_LN) {
+                // ---- LayerNorm epilogue: this thread owns columns [half * 64, +64) of output row `row` (Cout == 128) --------------
+                const int c0 = half * 64;
+                const bool valid = row_ok && (p.lens == nullptr || s < (int)p.lens[t.o2]);
+                float mean = 0.f, rstd = 0.f;
+                if (!dead) {
+                    const unsigned long long seed_in = dyn_seed(p.ln_seed_in, p.dyn);
+                    const float inv_keep = p.ln_p_in > 0.f ? 1.f / (1.f - p.ln_p_in) : 1.f;
+                    float psum = 0.f;
+#pragma unroll
+                    for (int c4 = 0; c4 < 16; ++c4) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + c4);
+                        float a[4] = {__uint_as_float(v[4 * c4]) * p.alpha + bv.x, __uint_as_float(v[4 * c4 + 1]) * p.alpha + bv.y,
+                                      __uint_as_float(v[4 * c4 + 2]) * p.alpha + bv.z, __uint_as_float(v[4 * c4 + 3]) * p.alpha + bv.w};
+                        if (p.ln_p_in > 0.f) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                a[e] *= dropout_scale(seed_in, (unsigned long long)grow * 128ull + (unsigned)(c0 + 4 * c4 + e), p.ln_p_in, inv_keep);
+                        }
+                        if (p.ln_res && row_ok) {
+                            const float4 r = __ldg(reinterpret_cast<const float4*>(p.ln_res + grow * 128 + c0) + c4);
+                            a[0] += r.x; a[1] += r.y; a[2] += r.z; a[3] += r.w;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { v[4 * c4 + e] = __float_as_uint(a[e]); psum += a[e]; }
+                    }
+                    // exchange the partial row sums with the warp that owns the other 64 columns of the same rows
+                    const uint32_t mine = xch + (uint32_t)(half * 128 + row) * 4u, other = xch + (uint32_t)((1 - half) * 128 + row) * 4u;
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(mine), "f"(psum) : "memory");
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+                    float osum;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(osum) : "r"(other) : "memory");
+                    mean = (psum + osum) * (1.f / 128.f);
+                    float psq = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) { const float d = __uint_as_float(v[i]) - mean; psq += d * d; }
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(mine + 1024u), "f"(psq) : "memory");
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+                    float osq;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(osq) : "r"(other + 1024u) : "memory");
+                    rstd = rsqrtf((psq + osq) * (1.f / 128.f) + 1e-5f);
+                }
+                if (half == 0 && row_ok) p.ln_rstd[grow] = (valid && !dead) ? rstd : 0.f;
+                const float keep = (valid && !dead) ? 1.f : 0.f;
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int nb = c0 + jj * 32;
+                    float o[32];
+                    // xhat chunk -> staging -> TMA store (map_y2)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = (__uint_as_float(v[jj * 32 + i]) - mean) * rstd * keep;
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+                    const uint32_t obuf = wbuf + lane * 128;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint32_t dst = obuf + ((c ^ (lane & 7)) << 4);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o[4 * c]), "f"(o[4 * c + 1]),
+                                     "f"(o[4 * c + 2]), "f"(o[4 * c + 3]) : "memory");
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_3d(&map_y2, wbuf, nb, t.o1 + quad * 32, t.o2); tma_store_commit(); }
+                    // y = mask(film_g * (xhat * w + b) + film_b)
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.ln_w + nb) + c4);
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_b + nb) + c4);
+                        o[4 * c4] = o[4 * c4] * w4.x + b4.x; o[4 * c4 + 1] = o[4 * c4 + 1] * w4.y + b4.y;
+                        o[4 * c4 + 2] = o[4 * c4 + 2] * w4.z + b4.z; o[4 * c4 + 3] = o[4 * c4 + 3] * w4.w + b4.w;
+                    }
+                    if (p.film) {
+                        const float* fg = p.film + (size_t)t.o2 * p.film_stride + nb;
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            const float4 g4 = __ldg(reinterpret_cast<const float4*>(fg) + c4);
+                            const float4 e4 = __ldg(reinterpret_cast<const float4*>(fg + 128) + c4);
+                            o[4 * c4] = g4.x * o[4 * c4] + e4.x; o[4 * c4 + 1] = g4.y * o[4 * c4 + 1] + e4.y;
+                            o[4 * c4 + 2] = g4.z * o[4 * c4 + 2] + e4.z; o[4 * c4 + 3] = g4.w * o[4 * c4 + 3] + e4.w;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] *= keep;
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint32_t dst = obuf + ((c ^ (lane & 7)) << 4);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o[4 * c]), "f"(o[4 * c + 1]),
+                                     "f"(o[4 * c + 2]), "f"(o[4 * c + 3]) : "memory");
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_3d(&map_y, wbuf, nb, t.o1 + quad * 32, t.o2); tma_store_commit(); }
+                    if (p.ln_planes) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) split_pair_u32(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
+                        if (lane == 0) tma_store_wait_read<0>();
+                        __syncwarp();
+                        const uint32_t rbuf = wbuf + lane * 64;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {   // SWIZZLE_64B
+                            const uint32_t off = (uint32_t)((c ^ ((lane >> 1) & 3)) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbuf + off), "r"(hi[4 * c]), "r"(hi[4 * c + 1]),
+                                         "r"(hi[4 * c + 2]), "r"(hi[4 * c + 3]) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbuf + 2048 + off), "r"(lo[4 * c]),
+                                         "r"(lo[4 * c + 1]), "r"(lo[4 * c + 2]), "r"(lo[4 * c + 3]) : "memory");
+                        }
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_3d(&map_y3, wbuf, nb, t.o1 + quad * 32, t.o2);
+                            tma_store_3d(&map_y3, wbuf + 2048, nb, t.o1 + quad * 32, p.B + t.o2);
+                            tma_store_commit();
+                        }
+                    }
+                }
+                if (!dead) ++it;
+                continue;
+            }
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const int nb = t.o0 + (half * 2 + jj) * 32;
@@ -595,10 +742,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
                         for (int i = 0; i < 32; ++i) o[i] = round_tf32(o[i]);
                     }
                     if (p.hp_dh) {
-                        const float sc = !row_ok ? 0.f : (nb < p.hp_scale_cols ? p.hp_scale : 1.f);   // rows in [S, Sp): zeros
-                        if (sc != 1.f) {
+                        if (!row_ok) {                                   // rows in [S, Sp): +0 (like the conversion pass wrote)
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) o[i] *= sc;
+                            for (int i = 0; i < 32; ++i) o[i] = 0.f;
+                        } else if (nb < p.hp_scale_cols) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] *= p.hp_scale;
                         }
                     }
                 }
@@ -861,16 +1010,18 @@ int num_sms() {
     return g_num_sms;
 }
 
-template <int PREC, int MODE>
+template <int PREC, int MODE, int EPI = EPI_STD>
 int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const CUtensorMap& my,
-           const TcParams& p, cudaStream_t st) {
+           const TcParams& p, cudaStream_t st, const CUtensorMap* my2 = nullptr, const CUtensorMap* my3 = nullptr) {
     static bool configured = false;
     if (!configured) {
-        DX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<PREC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<PREC, MODE>()));
+        DX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<PREC, MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     smem_bytes<PREC, MODE, EPI>()));
         configured = true;
     }
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    gemm_tc_kernel<PREC, MODE><<<grid, NTHREADS, smem_bytes<PREC, MODE>(), st>>>(ah, al, bh, bl, my, p);
+    gemm_tc_kernel<PREC, MODE, EPI><<<grid, NTHREADS, smem_bytes<PREC, MODE, EPI>(), st>>>(ah, al, bh, bl, my, my2 ? *my2 : my,
+                                                                                           my3 ? *my3 : my, p);
     ++g_tc_launches;
     return check_launch("gemm_tc");
 }
@@ -952,6 +1103,20 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     p.y_plane_elems = (long long)a.B * a.S * a.Cout;
     p.skip_y = a.y == nullptr;
     p.hp_dh = 0; p.hp_NH = 0; p.hp_scale_cols = 0; p.hp_scale = 1.f;
+    p.ln_res = nullptr; p.ln_w = nullptr; p.ln_b = nullptr; p.film = nullptr; p.film_stride = 0; p.ln_rstd = nullptr;
+    p.ln_p_in = 0.f; p.ln_seed_in = 0; p.dyn = nullptr; p.ln_planes = 0;
+    if (a.ln) {
+        const LnEpilogueArgs& l = *a.ln;
+        DX_REQUIRE(g_prec == PREC_BF16X3 && a.Cout == 128 && a.y && l.xhat && l.rstd && l.ln_w && l.ln_b && a.bias && !a.relu && !a.relu_src &&
+                       !a.relu_src_hi && !a.add_src && !a.y_colsum && !a.head_planes && a.ldy == 128,
+                   "conv_gemm_tc: the LayerNorm epilogue needs the bf16x3 backend, Cout == 128, bias, y / xhat / rstd outputs (Cout = %d)", a.Cout);
+        DX_REQUIRE((((uintptr_t)l.res | (uintptr_t)l.ln_w | (uintptr_t)l.ln_b | (uintptr_t)l.film | (uintptr_t)a.bias | (uintptr_t)l.xhat) & 15) == 0 &&
+                       (l.film == nullptr || l.film_stride % 4 == 0),
+                   "conv_gemm_tc: LayerNorm epilogue operands must be 16-byte aligned");
+        p.ln_res = l.res; p.ln_w = l.ln_w; p.ln_b = l.ln_b; p.film = l.film; p.film_stride = l.film_stride; p.ln_rstd = l.rstd;
+        p.ln_p_in = l.p_in; p.ln_seed_in = l.seed_in; p.dyn = l.dyn; p.ln_planes = a.y_planes != nullptr;
+        p.skip_y = 0;
+    }
     if (a.head_planes) {
         DX_REQUIRE(!a.y && !a.y_planes && !a.y_colsum && g_prec == PREC_BF16X3, "conv_gemm_tc: head_planes is a planes-only bf16x3 output");
         DX_REQUIRE((a.head_dim == 16 || a.head_dim == 32 || a.head_dim == 64) && a.Cout % a.head_dim == 0 && a.Cout % 32 == 0 &&
@@ -1036,6 +1201,20 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     if ((rc = make_map_3d(&mxl, xl, 2, a.Cin, a.S, a.B, xs1, xs2, 64, box_rows, 1))) return rc;
     if ((rc = make_map_3d(&mwh, wh, 2, a.Cin, a.Cout, a.KW, ws1, ws2, 64, TN, 1))) return rc;
     if ((rc = make_map_3d(&mwl, wl, 2, a.Cin, a.Cout, a.KW, ws1, ws2, 64, TN, 1))) return rc;
+    if (a.ln) {
+        CUtensorMap mxhat, mplanes;
+        if ((rc = make_map_3d(&mxhat, a.ln->xhat, 4, a.Cout, a.S, a.B, (uint64_t)a.Cout * 4, (uint64_t)a.S * a.Cout * 4, 32, 32, 1))) return rc;
+        if (a.y_planes) {
+            if ((rc = make_map_3d(&mplanes, a.y_planes, 2, a.Cout, a.S, 2 * (uint64_t)a.B, (uint64_t)a.Cout * 2, (uint64_t)a.S * a.Cout * 2, 32, 32,
+                                  1, true)))
+                return rc;
+        } else {
+            mplanes = mxhat;
+        }
+        DX_REQUIRE(a.KW == 1 || halo_mode, "conv_gemm_tc: LayerNorm epilogue with KW = %d needs the halo kernel", a.KW);
+        if (halo_mode) return launch<PREC_BF16X3, MODE_HALO, EPI_LN>(mxh, mxl, mwh, mwl, my, p, st, &mxhat, &mplanes);
+        return launch<PREC_BF16X3, MODE_CONV, EPI_LN>(mxh, mxl, mwh, mwl, my, p, st, &mxhat, &mplanes);
+    }
     if (halo_mode) return launch<PREC_BF16X3, MODE_HALO>(mxh, mxl, mwh, mwl, my, p, st);
     return launch<PREC_BF16X3, MODE_CONV>(mxh, mxl, mwh, mwl, my, p, st);
 }
@@ -1176,6 +1355,9 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
     TcParams p;
     p.bias = nullptr; p.relu_src = nullptr; p.add_src = nullptr;
     p.relu_src_hi = nullptr; p.y_planes = nullptr; p.colsum = nullptr; p.y_plane_elems = 0; p.skip_y = 0;
+    p.hp_dh = 0; p.hp_NH = 0; p.hp_scale_cols = 0; p.hp_scale = 1.f;
+    p.ln_res = nullptr; p.ln_w = nullptr; p.ln_b = nullptr; p.film = nullptr; p.film_stride = 0; p.ln_rstd = nullptr;
+    p.ln_p_in = 0.f; p.ln_seed_in = 0; p.dyn = nullptr; p.ln_planes = 0;
     p.B = a.B; p.S = a.S; p.Cin = a.Cin; p.Cout = a.Cout; p.KW = a.KW; p.ldy = a.Cin;
     p.tiles_m_per_b = ceil_div(a.Cout, TM);
     p.tiles_n = ceil_div(a.Cin, TN);

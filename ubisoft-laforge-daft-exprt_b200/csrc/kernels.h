@@ -7,6 +7,21 @@
 
 namespace dx {
 
+// LayerNorm epilogue of a Cout == 128 GEMM (bf16x3 tensor-core path): v = dropout_in(acc + bias) + res; xhat = (v - mean) * rstd;
+// y = mask(film_g * (xhat * ln_w + ln_b) + film_b) -> ConvGemmArgs::y (fp32) and ConvGemmArgs::y_planes (optional bf16 hi|lo planes)
+struct LnEpilogueArgs {
+    const float* res;       // [B, S, 128] or nullptr
+    const float* ln_w;
+    const float* ln_b;
+    const float* film;      // nullable; gamma at film[b*film_stride + c], beta at film[b*film_stride + 128 + c]
+    int film_stride;
+    float* xhat;            // [B, S, 128]  (saved for backward)
+    float* rstd;            // [B*S]
+    float p_in;
+    unsigned long long seed_in;
+    const StepState* dyn;
+};
+
 // y[b, s, n] = epi(alpha * sum_{tap, c} x[b, s + tap - pad, c] * w[tap][n][c] + bias[n]);  w is the packed layout
 // [KW][Cout][Cin].  epi: optional ReLU, optional multiply by (relu_src > 0) (ReLU backward fused into a dgrad), optional
 // round-to-tf32 of the stored value.
@@ -22,6 +37,7 @@ struct ConvGemmArgs {
     float* y_colsum;        // optional (tensor-core path): [Cout] column sums of the stored output over all B*S rows (zeroed + accumulated inside)
     // optional (bf16x3 tensor-core path, the ONLY output then): the output as per-head attention operand planes
     // R[2][B][Cout / head_dim][head_Sp][head_dim] (bf16 hi|lo), columns < head_scale_cols multiplied by head_scale, rows in [S, head_Sp) zero
+    const LnEpilogueArgs* ln = nullptr;   // optional: finish with the LayerNorm epilogue above (lens = the row mask)
     void* head_planes = nullptr;
     int head_dim = 0, head_Sp = 0, head_scale_cols = 0;
     float head_scale = 1.f;

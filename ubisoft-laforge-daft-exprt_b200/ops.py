@@ -282,6 +282,33 @@ def conv_wgrad(x, dy, B, S, cin, cout, kw, shape, want_bias=True, ldx=None, alph
 
 
 _fused_inproj = [True]
+_fused_ln = [True]
+
+
+def fused_ln(on=None):
+    """Get / set: the GEMMs that end a sub-layer (attention out-projection, conv2 of the feed-forward) finish dropout + residual +
+    LayerNorm + FiLM + mask in their own epilogue (default on; off = separate dx_ln_fwd launch, kept for A/B tests)."""
+    if on is not None:
+        _fused_ln[0] = bool(on)
+    return _fused_ln[0] and _backend[0] == cabi.DX_GEMM_TCGEN05_BF16X3
+
+
+def gemm_ln(x_planes, wp, bias, res, ln_w, ln_b, film, film_stride, lens, B, S, p_in=0.0, seed_in=0):
+    """(y, xhat, rstd) of dx_conv_gemm_ln; y carries its operand planes (attach_planes)."""
+    kw, cout, cin = wp.shape
+    dev = wp.w.device
+    y = torch.empty(B, S, cout, device=dev, dtype=torch.float32)
+    xhat = torch.empty(B, S, cout, device=dev, dtype=torch.float32)
+    rstd = torch.empty(B * S, device=dev, dtype=torch.float32)
+    yP = torch.empty(2, B * S, cout, device=dev, dtype=torch.bfloat16)
+    _call('dx_conv_gemm_ln', _p(x_planes), _p(wp.planes), _p(bias), _p(res), _p(ln_w), _p(ln_b), _p(film), film_stride, _p(lens), _p(y),
+          _p(yP), _p(xhat), _p(rstd), B, S, cin, kw, float(p_in), seed_in, _st())
+    attach_planes(y, yP)
+    return y, xhat, rstd
+
+
+def can_fuse_ln(x_planes, wp, bias, D):
+    return fused_ln() and D == 128 and x_planes is not None and wp.planes is not None and bias is not None and wp.shape[0] in (1, 3)
 
 
 def fused_inproj(on=None):
@@ -380,8 +407,11 @@ class AttentionSubLayer(torch.autograd.Function):
             qkv = conv_gemm(x, in_wp, in_b, B, S, x_planes=xP, lens=lens)   # rows >= len: keys masked, queries skipped
         _call('dx_attention_fwd', _p(qkv), _p(lens), _p(att), _p(lse), _p(planes), _p(attP), B, S, nb_heads, dh, float(p_drop), seed_attn,
               _st())   # the kernel writes ctx and its operand planes
-        proj = conv_gemm(att, out_wp, out_b, B, S, x_planes=attP, lens=lens)   # rows >= len are masked by the LayerNorm kernel
-        y, xhat, rstd = ln_fwd(proj, x, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p_drop, seed_in=seed_out, emit_planes=True)
+        if can_fuse_ln(attP, out_wp, out_b, D):   # out-projection + dropout + residual + LayerNorm + mask in ONE kernel
+            y, xhat, rstd = gemm_ln(attP, out_wp, out_b, x, ln_w, ln_b, None, 0, lens, B, S, p_in=p_drop, seed_in=seed_out)
+        else:
+            proj = conv_gemm(att, out_wp, out_b, B, S, x_planes=attP, lens=lens)   # rows >= len are masked by the LayerNorm kernel
+            y, xhat, rstd = ln_fwd(proj, x, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p_drop, seed_in=seed_out, emit_planes=True)
         ctx.save_for_backward(x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b, xP, attP, planes)
         hold_packs(ctx, in_wd, out_wd)
         ctx.cfg = (B, S, D, nb_heads, dh, float(p_drop), seed_attn, seed_out, in_w.shape, out_w.shape)
@@ -426,12 +456,15 @@ class ConvFFSubLayer(torch.autograd.Function):
         else:
             h = conv_gemm(x, w1p, b1, B, S, relu=True, round_out=True, x_planes=xP, lens=lens, halo=k2)
             hP = make_planes(h, B * S, C)
-        o = conv_gemm(h, w2p, b2, B, S, x_planes=hP, lens=lens)   # rows >= len are masked by the LayerNorm kernel
         seed = next_seed() if p_drop > 0 else 0
         if film is not None:
             film = _check_input(film)
             assert film.shape[1] == 2 * D   # reference model.py:232
-        y, xhat, rstd = ln_fwd(o, x, ln_w, ln_b, film, 2 * D, lens, B, S, D, p_in=p_drop, seed_in=seed, emit_planes=True)
+        if can_fuse_ln(hP, w2p, b2, D):   # conv2 + dropout + residual + LayerNorm + FiLM + mask in ONE kernel
+            y, xhat, rstd = gemm_ln(hP, w2p, b2, x, ln_w, ln_b, film, 2 * D, lens, B, S, p_in=p_drop, seed_in=seed)
+        else:
+            o = conv_gemm(h, w2p, b2, B, S, x_planes=hP, lens=lens)   # rows >= len are masked by the LayerNorm kernel
+            y, xhat, rstd = ln_fwd(o, x, ln_w, ln_b, film, 2 * D, lens, B, S, D, p_in=p_drop, seed_in=seed, emit_planes=True)
         ctx.save_for_backward(x, lens, h, xhat, rstd, ln_w, ln_b, film, xP, hP)
         hold_packs(ctx, w1d, w2d)
         ctx.cfg = (B, S, D, C, float(p_drop), seed, w1.shape, w2.shape)
