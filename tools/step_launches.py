@@ -21,7 +21,8 @@ crit = DaftExprtLoss(0, hp)
 params = list(model.parameters())
 sync = FlatGradSync(params, mode='gather')
 opt = FlatAdam(params, sync, lr=hp.initial_learning_rate, betas=hp.betas, eps=hp.epsilon, weight_decay=hp.weight_decay)
-inputs, targets, _ = model.parse_batch(0, bench.make_host_batch(0))
+cfg = bench.CONFIGS[os.environ.get('DX_CONFIG', 'train')]
+inputs, targets, _ = model.parse_batch(0, bench.with_ids(bench.rank_batch(cfg, 0)))
 
 
 def step(it):
