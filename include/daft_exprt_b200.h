@@ -42,6 +42,12 @@ uint64_t dx_tc_gemm_launch_count(void);
 int dx_device_check(void);
 int dx_set_gemm_backend(int backend);
 int dx_get_gemm_backend(void);
+/* DX_GEMM_TCGEN05_BF16X3 only: tensor-core passes per K-step issued by the GEMMs called from now on — conv_passes for dx_conv_gemm* /
+ * dx_inproj_head_planes (forward and input-gradient GEMMs), wgrad_passes for dx_conv_wgrad.  3 (default) = hi*hi + lo*hi + hi*lo:
+ * fp32-grade, the parity mode.  2 = hi*hi + lo*hi: the second operand (weights; x for wgrad) is rounded to bf16.  1 = hi*hi: plain
+ * bf16 operands, fp32 accumulation (the usual mixed-precision training arithmetic).  Reduced modes do not load the planes they skip.
+ * They are NOT parity modes: measured errors are in profiles/r2_pass_ablation.md. */
+int dx_set_gemm_passes(int conv_passes, int wgrad_passes);
 /* Attention kernels used with the tensor-core GEMM backends: DX_ATTENTION_TCGEN05 (default: tcgen05/TMEM/TMA forward and
  * backward for head_dim 64 and 16) or DX_ATTENTION_MMA_SYNC (the mma.sync flash kernels; always used for head_dim 32).
  * Initial value from the environment (DX_ATTN_TC=0 / DX_ATTN_BWD_TC=0 select mma.sync for forward / backward). */

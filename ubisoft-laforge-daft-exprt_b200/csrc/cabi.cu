@@ -68,6 +68,12 @@ int dx_set_gemm_backend(int backend) {
     return DX_OK;
 }
 int dx_get_gemm_backend(void) { return g_backend; }
+int dx_set_gemm_passes(int conv_passes, int wgrad_passes) {
+    DX_REQUIRE(conv_passes >= 1 && conv_passes <= 3 && wgrad_passes >= 1 && wgrad_passes <= 3, "dx_set_gemm_passes: 1..3 (got %d, %d)", conv_passes,
+               wgrad_passes);
+    set_tc_passes(conv_passes, wgrad_passes);
+    return DX_OK;
+}
 int dx_debug_set_trace(void* buf) { set_tc_trace((long long*)buf); return DX_OK; }
 int dx_set_attention_backend(int forward_backend, int backward_backend) {
     DX_REQUIRE((forward_backend == 0 || forward_backend == 1) && (backward_backend == 0 || backward_backend == 1),

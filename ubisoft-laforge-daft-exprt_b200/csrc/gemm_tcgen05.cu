@@ -203,6 +203,10 @@ struct TcParams {
     unsigned long long ln_seed_in;
     const StepState* dyn;
     int ln_planes;                      // also write y as bf16 hi|lo planes (map_y3)
+    // BF16X3 pass count (precision ablation / reduced-precision modes): 3 = hi*hi + lo*hi + hi*lo (default, fp32-grade);
+    // 2 = hi*hi + lo*hi (the B operand = weights / second operand rounded to bf16); 1 = hi*hi (plain bf16).  Planes that a mode
+    // does not use are not loaded.
+    int passes;
     int B, S, Cin, Cout, KW, ldy;
     int tiles_m_per_b, tiles_n, num_tiles, k_chunks;   // CONV: tiles over (b, s) x n;  WGRAD: tiles_m = co tiles, tiles_n = ci tiles
     int nsplit;                                         // WGRAD: batch ranges
@@ -339,9 +343,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
                     if (p.debug & 2) {
                         mbar_arrive(abar);
                     } else {   // rows s0-1 .. s0+128 of this channel chunk, both planes (out-of-range rows arrive as zeros)
-                        mbar_expect_tx(abar, 2 * HALO_ROWS * 128);
+                        mbar_expect_tx(abar, (p.passes >= 2 ? 2 : 1) * HALO_ROWS * 128);
                         tma_load_3d(sa, &map_a_hi, abar, kc * TKB, t.a1 - 1, t.a2);
-                        tma_load_3d(sa + A_HALO_BYTES, &map_a_lo, abar, kc * TKB, t.a1 - 1, t.a2);
+                        if (p.passes >= 2) tma_load_3d(sa + A_HALO_BYTES, &map_a_lo, abar, kc * TKB, t.a1 - 1, t.a2);
                     }
                     if (++as == HALO_A_STAGES) { as = 0; aph ^= 1; }
                     for (int tap = 0; tap < 3; ++tap) {
@@ -350,9 +354,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
                         if (p.debug & 2) {
                             mbar_arrive(bbar);
                         } else {
-                            mbar_expect_tx(bbar, HALO_B_STAGE_BYTES);
+                            mbar_expect_tx(bbar, p.passes >= 3 ? HALO_B_STAGE_BYTES : TILE_BYTES);
                             tma_load_3d(sb, &map_b_hi, bbar, kc * TKB, t.b1, tap);
-                            tma_load_3d(sb + TILE_BYTES, &map_b_lo, bbar, kc * TKB, t.b1, tap);
+                            if (p.passes >= 3) tma_load_3d(sb + TILE_BYTES, &map_b_lo, bbar, kc * TKB, t.b1, tap);
                         }
                         if (p.trace && blockIdx.x == 0 && gk < 256) p.trace[0 * 256 + gk] = clock64();
                         ++gk;
@@ -390,8 +394,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
                         for (int kk = 0; kk < ((p.debug & 1) ? 0 : 4); ++kk) {
                             umma<PREC>(tmem_d, a_hi + 2 * kk, b_hi + 2 * kk, idesc, started | (uint32_t)kk);
-                            umma<PREC>(tmem_d, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1u);
-                            umma<PREC>(tmem_d, a_hi + 2 * kk, b_lo + 2 * kk, idesc, 1u);
+                            if (p.passes >= 2) umma<PREC>(tmem_d, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1u);
+                            if (p.passes >= 3) umma<PREC>(tmem_d, a_hi + 2 * kk, b_lo + 2 * kk, idesc, 1u);
                         }
                         if (p.debug & 1) mbar_arrive(empty0 + 8 * bs);
                         else umma_commit(empty0 + 8 * bs);
@@ -426,7 +430,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
                         const uint32_t bar = full0 + 8 * stage;
                         const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + PLANES * TILE_BYTES;
                         if (p.debug & 2) { mbar_arrive(bar); if (++stage == NSTAGE) { stage = 0; phase ^= 1; } continue; }
-                        mbar_expect_tx(bar, STAGE_BYTES);
+                        mbar_expect_tx(bar, PLANES == 2 ? (uint32_t)(2 + (p.passes >= 2) + (p.passes >= 3)) * TILE_BYTES : (uint32_t)STAGE_BYTES);
                         int a0, a1, a2, b0, b1, b2;
                         if constexpr (MODE != MODE_WGRAD) {      // o = tap
                             a0 = kc * TKB; a1 = t.a1 + o - pad; a2 = t.a2;
@@ -439,16 +443,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
                             tma_load_3d(sa, &map_a_hi, bar, a0, a1, a2);
                             tma_load_3d(sb, &map_b_hi, bar, b0, b1, b2);
                             if constexpr (PLANES == 2) {
-                                tma_load_3d(sa + TILE_BYTES, &map_a_lo, bar, a0, a1, a2);
-                                tma_load_3d(sb + TILE_BYTES, &map_b_lo, bar, b0, b1, b2);
+                                if (p.passes >= 2) tma_load_3d(sa + TILE_BYTES, &map_a_lo, bar, a0, a1, a2);
+                                if (p.passes >= 3) tma_load_3d(sb + TILE_BYTES, &map_b_lo, bar, b0, b1, b2);
                             }
                         } else {                                // two 64-column MN chunks per 128-wide tile
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
                                 tma_load_3d(sa + j * 8192, &map_a_hi, bar, a0 + 64 * j, a1, a2);
                                 tma_load_3d(sb + j * 8192, &map_b_hi, bar, b0 + 64 * j, b1, b2);
-                                tma_load_3d(sa + TILE_BYTES + j * 8192, &map_a_lo, bar, a0 + 64 * j, a1, a2);
-                                tma_load_3d(sb + TILE_BYTES + j * 8192, &map_b_lo, bar, b0 + 64 * j, b1, b2);
+                                if (p.passes >= 2) tma_load_3d(sa + TILE_BYTES + j * 8192, &map_a_lo, bar, a0 + 64 * j, a1, a2);
+                                if (p.passes >= 3) tma_load_3d(sb + TILE_BYTES + j * 8192, &map_b_lo, bar, b0 + 64 * j, b1, b2);
                             }
                         }
                         if (p.trace && blockIdx.x == 0 && gk < 256) p.trace[0 * 256 + gk] = clock64();
@@ -488,8 +492,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
                         umma<PREC>(tmem_d, a_hi + kstep * kk, b_hi + kstep * kk, idesc, started | (uint32_t)kk);
                         if constexpr (PLANES == 2) {
                             const uint64_t a_lo = a_hi + (TILE_BYTES >> 4), b_lo = b_hi + (TILE_BYTES >> 4);
-                            umma<PREC>(tmem_d, a_lo + kstep * kk, b_hi + kstep * kk, idesc, 1u);
-                            umma<PREC>(tmem_d, a_hi + kstep * kk, b_lo + kstep * kk, idesc, 1u);
+                            if (p.passes >= 2) umma<PREC>(tmem_d, a_lo + kstep * kk, b_hi + kstep * kk, idesc, 1u);
+                            if (p.passes >= 3) umma<PREC>(tmem_d, a_hi + kstep * kk, b_lo + kstep * kk, idesc, 1u);
                         }
                     }
                     if (p.debug & 1) mbar_arrive(empty0 + 8 * stage);
@@ -1000,6 +1004,7 @@ int make_map_3d(CUtensorMap* map, const void* ptr, int esz, uint64_t d0, uint64_
 int g_num_sms = 0;
 int g_prec = PREC_BF16X3;
 unsigned long long g_tc_launches = 0;
+int g_passes_conv = 3, g_passes_wgrad = 3;   // BF16X3 passes issued by forward / dgrad GEMMs and by weight-gradient GEMMs
 
 int num_sms() {
     if (g_num_sms == 0) {
@@ -1061,6 +1066,8 @@ int make_tma_map_3d(void* map, const void* ptr, int esz, unsigned long long d0, 
 
 void set_tc_precision(int tf32) { g_prec = tf32 ? PREC_TF32 : PREC_BF16X3; }
 void set_tc_trace(long long* buf) { g_trace = buf; }
+void set_tc_passes(int conv, int wgrad) { g_passes_conv = conv; g_passes_wgrad = wgrad; }
+void get_tc_passes(int* conv, int* wgrad) { *conv = g_passes_conv; *wgrad = g_passes_wgrad; }
 unsigned long long tc_gemm_launches() { return g_tc_launches; }
 long long* tc_trace_buffer() { return g_trace; }
 
@@ -1105,6 +1112,7 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     p.hp_dh = 0; p.hp_NH = 0; p.hp_scale_cols = 0; p.hp_scale = 1.f;
     p.ln_res = nullptr; p.ln_w = nullptr; p.ln_b = nullptr; p.film = nullptr; p.film_stride = 0; p.ln_rstd = nullptr;
     p.ln_p_in = 0.f; p.ln_seed_in = 0; p.dyn = nullptr; p.ln_planes = 0;
+    p.passes = g_passes_conv;
     if (a.ln) {
         const LnEpilogueArgs& l = *a.ln;
         DX_REQUIRE(g_prec == PREC_BF16X3 && a.Cout == 128 && a.y && l.xhat && l.rstd && l.ln_w && l.ln_b && a.bias && !a.relu && !a.relu_src &&
@@ -1358,6 +1366,7 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
     p.hp_dh = 0; p.hp_NH = 0; p.hp_scale_cols = 0; p.hp_scale = 1.f;
     p.ln_res = nullptr; p.ln_w = nullptr; p.ln_b = nullptr; p.film = nullptr; p.film_stride = 0; p.ln_rstd = nullptr;
     p.ln_p_in = 0.f; p.ln_seed_in = 0; p.dyn = nullptr; p.ln_planes = 0;
+    p.passes = g_passes_wgrad;
     p.B = a.B; p.S = a.S; p.Cin = a.Cin; p.Cout = a.Cout; p.KW = a.KW; p.ldy = a.Cin;
     p.tiles_m_per_b = ceil_div(a.Cout, TM);
     p.tiles_n = ceil_div(a.Cin, TN);

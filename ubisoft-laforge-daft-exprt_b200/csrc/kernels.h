@@ -85,6 +85,8 @@ int pack_conv_weight(const float* w, float* fwd, float* dgrad, void* fwd_planes,
 // tcgen05 / TMEM / TMA path (gemm_tcgen05.cu)
 void set_tc_precision(int tf32);
 void set_tc_trace(long long* buf);
+void set_tc_passes(int conv, int wgrad);      // BF16X3 passes (1..3) of forward/dgrad GEMMs and of weight-gradient GEMMs
+void get_tc_passes(int* conv, int* wgrad);
 unsigned long long tc_gemm_launches();   // gemm_tc_kernel launches so far
 int split_weight_planes(const float* w, void* planes, size_t n, cudaStream_t st);
 int split_activation_planes(const float* x, int ld, void* planes, float* colsum_out, int rows, int C, cudaStream_t st);

@@ -114,6 +114,7 @@ class GraphedTrainStep:
         self.micro_total = 0         # dropout seed epoch
         self.hits = self.misses = 0
         self.stepped = False
+        self.before_forward = self.before_backward = None   # optional host callbacks run while the step is captured (tools)
         if self.acc_steps > 1:
             self.sync.flat.zero_()
 
@@ -132,7 +133,11 @@ class GraphedTrainStep:
         self.opt.zero_grad()
         ops.set_wgrad_deferral(True)   # gather mode: no gradient is read before the bucket is filled, so reduce them all at once
         try:
+            if self.before_forward is not None:
+                self.before_forward()
             out = self.criterion.forward_device(self.model(inputs), targets, 0)   # w_adv comes from the device block
+            if self.before_backward is not None:
+                self.before_backward()
             out[7].backward()
             ops.flush_wgrad()
         finally:
