@@ -774,7 +774,7 @@ def test_train_mode_step_matches_oracle_with_replayed_masks(dev):
     from daft_exprt_b200.loss import DaftExprtLoss
     set_backend('bf16x3')
     n_ids = 11
-    inputs = synthetic.make_batch(3, 37, 150, n_ids, seed=33)
+    inputs = synthetic.make_batch(6, 60, 300, n_ids, seed=33)
     model, hp, sd = build_model(n_ids, dev, train=True)
     crit = DaftExprtLoss(0, hp)
     din = to_dev(inputs, dev)
@@ -806,13 +806,12 @@ def test_train_mode_step_matches_oracle_with_replayed_masks(dev):
     for n, p in model.named_parameters():
         e, es = l2_rel_err(p.grad, sd_o[n].grad), scale_rel_err(p.grad, sd_o[n].grad)
         worst = max(worst, e if not n.startswith('gaussian_upsampling.') else 0.0)
-        # this batch is small (3 x 37 phonemes, 3 x 150 frames): ONE ReLU input within ~1e-6 of zero that lands on the other side of
-        # the kink than in the fp64 oracle moves a gradient entry by ~1/rows (see test_all_gradients_match_oracle_autograd), so the
-        # bounds are 1e-2 relative-L2 / 2e-2 element-wise here (the full-length test holds 5e-3 / 1e-2 on 8 x 1000 rows)
-        tg = 1e-2 if not n.startswith('gaussian_upsampling.') else 5e-2
-        if not (e < tg and es < max(tg, 2e-2)):
+        # same bounds as the full-length eval-mode test: 5e-3 relative-L2 / 1e-2 element-wise (measured: 1.1e-3 worst);
+        # gaussian_upsampling.* are ill-conditioned sums (see the golden test): 5e-2
+        tg = 5e-3 if not n.startswith('gaussian_upsampling.') else 5e-2
+        if not (e < tg and es < max(tg, 1e-2)):
             bad.append((n, e, es))
-    print('[train-mode bf16x3] worst gradient l2-rel:', worst)
+    print('[train-mode bf16x3] worst gradient l2-rel:', worst, 'offenders:', [(n, f'{e:.1e}', f'{es:.1e}') for n, e, es in bad[:8]])
     assert not bad, bad[:10]
 
 

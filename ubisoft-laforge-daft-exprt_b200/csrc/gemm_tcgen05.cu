@@ -47,9 +47,9 @@ enum { EPI_STD = 0, EPI_LN = 1 };
 
 constexpr int TM = 128, TN = 128;
 constexpr int TILE_BYTES = 128 * 128;                 // one operand tile: 128 rows x 128 bytes
-constexpr int OUT_BYTES = TM * 32 * 4;                // one 128 x 32 fp32 staging chunk
+constexpr int OUT_BYTES = TM * 32 * 4;                // 2 * OUT_BYTES = 16 epilogue warps x 2 KB of store staging
 constexpr int TMEM_COLS = 256;
-constexpr int NUM_EPI_WARPS = 8;                      // two per SM sub-partition
+constexpr int NUM_EPI_WARPS = 16;                     // four per SM sub-partition (see the epilogue)
 constexpr int NTHREADS = 64 + 32 * NUM_EPI_WARPS;     // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. = epilogue
 
 template <int PREC> struct Cfg;
@@ -60,7 +60,7 @@ constexpr int HALO_ROWS = TM + 2;                      // KW = 3
 constexpr int A_HALO_BYTES = 17 * 1024;                // 130 rows x 128 B rounded up to the 1024-byte swizzle repeat
 constexpr int HALO_A_STAGES = 2, HALO_B_STAGES = 3;
 constexpr int HALO_A_STAGE_BYTES = 2 * A_HALO_BYTES, HALO_B_STAGE_BYTES = 2 * TILE_BYTES;
-constexpr int XCH_BYTES = 2 * 2 * 128 * 4;             // EPI_LN: two exchange slots x two column halves x 128 rows
+constexpr int XCH_BYTES = 2 * 128 * 4 * 4;             // EPI_LN: two exchange slots x 128 rows x four column chunks
 // k=1 GEMMs with the LayerNorm epilogue (the out-projection: K = 128 = two chunks) run a 2-stage ring to make room for it
 template <int PREC, int MODE, int EPI> constexpr int num_stages() { return (EPI == EPI_LN && MODE == MODE_CONV) ? 2 : Cfg<PREC>::NSTAGE; }
 template <int PREC, int MODE, int EPI = EPI_STD> constexpr int smem_bytes() {
@@ -511,20 +511,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
             __syncwarp();
         }
     } else {
-        // epilogue: NUM_EPI_WARPS = 8 warps, two per SM sub-partition so one warp's TMEM / shared-memory / TMA latencies are
-        // covered by the other.  Warp w may only touch TMEM lanes [32*(w%4), +32) (thread <-> output row); the two warps of
-        // a lane quarter split the 128 accumulator columns (64 each = two 32-column chunks, both loaded up front so the
-        // accumulator goes back to the MMA warp before any arithmetic starts).
+        // epilogue: NUM_EPI_WARPS = 16 warps, FOUR per SM sub-partition.  Measured (round 2, tools/tc_trace.py + DX_TC_DEBUG masks): the
+        // epilogue of one 128 x 128 tile took 3-5 k cycles with two warps per scheduler — dependent-issue latency of ~1 k instructions
+        // per warp, not TMEM loads, bias loads or the TMA stores — and bounded every GEMM of the path (1 tensor-core pass instead of 3
+        // bought 12 %).  Warp w may only touch TMEM lanes [32*(w%4), +32) (thread <-> output row); the four warps of a lane quarter
+        // take one 32-column chunk each.  Staging: 2 KB per warp, used in two rounds (hi plane then lo plane; or columns 0-15 then
+        // 16-31 of an fp32 chunk), each a 32-row x 64-byte SWIZZLE_64B box stored by TMA.
         const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int part = (warp - 2) >> 2;                       // 32-column chunk of the tile
         const int row = quad * 32 + lane;
-        const uint32_t wbuf = sOut + (uint32_t)(warp - 2) * 4096u;   // one 4 KB staging buffer per epilogue warp
+        const uint32_t wbuf = sOut + (uint32_t)(warp - 2) * 2048u;
+        const uint32_t rbuf = wbuf + lane * 64;
+        // one round: 32 rows x 64 bytes (16 bytes per unit u) into the SWIZZLE_64B staging tile, then one TMA store
+        auto stage64 = [&](const uint32_t* w16) {   // w16: 16 x 32-bit words of this lane's row
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t off = (uint32_t)((c ^ ((lane >> 1) & 3)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbuf + off), "r"(w16[4 * c]), "r"(w16[4 * c + 1]), "r"(w16[4 * c + 2]),
+                             "r"(w16[4 * c + 3]) : "memory");
+            }
+            if (!(p.debug & 64)) fence_async_smem();
+            __syncwarp();
+        };
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const TileCoord t = tile_coord<MODE>(p, tile);
             const bool dead = tile_dead<MODE>(p, t);             // dead tiles are stored as zeros, no accumulator involved
             const int acc = it & 1, acc_phase = (it >> 1) & 1;
-            uint32_t v[64];
+            uint32_t v[32];
             if (!dead) {
                 mbar_wait(tfull0 + 8 * acc, acc_phase);
                 if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && it < 256) p.trace[2 * 256 + it] = clock64();
@@ -532,15 +548,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
             }
             if (dead || (p.debug & 4)) {
 #pragma unroll
-                for (int i = 0; i < 64; ++i) v[i] = 0u;
+                for (int i = 0; i < 32; ++i) v[i] = 0u;
             } else {
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN + half * 64;
-                tmem_ld32_nowait(taddr, v);
-                tmem_ld32_nowait(taddr + 32, v + 32);
+                tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN + part * 32, v);
                 tmem_ld_wait(v);
-                tmem_ld_wait(v + 32);
             }
-            if (!dead) {   // all TMEM reads of this warp are done: hand the accumulator back to the MMA warp
+            if (!dead) {   // this warp's TMEM reads are done: hand the accumulator back to the MMA warp
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
@@ -548,9 +561,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
             const int s = t.o1 + row;
             const bool row_ok = MODE != MODE_WGRAD && s < p.S;
             const size_t grow = (size_t)t.o2 * p.S + s;
+            const int nb = t.o0 + part * 32;
+            const int row0 = t.o1 + quad * 32;
             if constexpr (EPI == EPI_LN) {
-                // ---- LayerNorm epilogue: this thread owns columns [half * 64, +64) of output row `row` (Cout == 128) --------------
-                const int c0 = half * 64;
+                // ---- LayerNorm epilogue: this thread owns columns [part * 32, +32) of output row `row` (Cout == 128) --------------
                 const bool valid = row_ok && (p.lens == nullptr || s < (int)p.lens[t.o2]);
                 float mean = 0.f, rstd = 0.f;
                 if (!dead) {
@@ -558,323 +572,267 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
                     const float inv_keep = p.ln_p_in > 0.f ? 1.f / (1.f - p.ln_p_in) : 1.f;
                     float psum = 0.f;
 #pragma unroll
-                    for (int c4 = 0; c4 < 16; ++c4) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + c4);
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + c4);
                         float a[4] = {__uint_as_float(v[4 * c4]) * p.alpha + bv.x, __uint_as_float(v[4 * c4 + 1]) * p.alpha + bv.y,
                                       __uint_as_float(v[4 * c4 + 2]) * p.alpha + bv.z, __uint_as_float(v[4 * c4 + 3]) * p.alpha + bv.w};
                         if (p.ln_p_in > 0.f) {
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
-                                a[e] *= dropout_scale(seed_in, (unsigned long long)grow * 128ull + (unsigned)(c0 + 4 * c4 + e), p.ln_p_in, inv_keep);
+                                a[e] *= dropout_scale(seed_in, (unsigned long long)grow * 128ull + (unsigned)(nb + 4 * c4 + e), p.ln_p_in, inv_keep);
                         }
                         if (p.ln_res && row_ok) {
-                            const float4 r = __ldg(reinterpret_cast<const float4*>(p.ln_res + grow * 128 + c0) + c4);
+                            const float4 r = __ldg(reinterpret_cast<const float4*>(p.ln_res + grow * 128 + nb) + c4);
                             a[0] += r.x; a[1] += r.y; a[2] += r.z; a[3] += r.w;
                         }
 #pragma unroll
                         for (int e = 0; e < 4; ++e) { v[4 * c4 + e] = __float_as_uint(a[e]); psum += a[e]; }
                     }
-                    // exchange the partial row sums with the warp that owns the other 64 columns of the same rows
-                    const uint32_t mine = xch + (uint32_t)(half * 128 + row) * 4u, other = xch + (uint32_t)((1 - half) * 128 + row) * 4u;
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(mine), "f"(psum) : "memory");
-                    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-                    float osum;
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(osum) : "r"(other) : "memory");
-                    mean = (psum + osum) * (1.f / 128.f);
+                    // exchange the partial row sums among the four warps that own the four column chunks of the same rows
+                    const uint32_t xrow = xch + (uint32_t)row * 16u;          // [slot][row][part] fp32
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(xrow + 4u * part), "f"(psum) : "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");
+                    float4 q4;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q4.x), "=f"(q4.y), "=f"(q4.z), "=f"(q4.w) : "r"(xrow) : "memory");
+                    mean = ((q4.x + q4.y) + (q4.z + q4.w)) * (1.f / 128.f);
                     float psq = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) { const float d = __uint_as_float(v[i]) - mean; psq += d * d; }
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(mine + 1024u), "f"(psq) : "memory");
-                    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-                    float osq;
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(osq) : "r"(other + 1024u) : "memory");
-                    rstd = rsqrtf((psq + osq) * (1.f / 128.f) + 1e-5f);
+                    for (int i = 0; i < 32; ++i) { const float d = __uint_as_float(v[i]) - mean; psq += d * d; }
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(xrow + 2048u + 4u * part), "f"(psq) : "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q4.x), "=f"(q4.y), "=f"(q4.z), "=f"(q4.w) : "r"(xrow + 2048u) : "memory");
+                    rstd = rsqrtf(((q4.x + q4.y) + (q4.z + q4.w)) * (1.f / 128.f) + 1e-5f);
                 }
-                if (half == 0 && row_ok) p.ln_rstd[grow] = (valid && !dead) ? rstd : 0.f;
+                if (part == 0 && row_ok) p.ln_rstd[grow] = (valid && !dead) ? rstd : 0.f;
                 const float keep = (valid && !dead) ? 1.f : 0.f;
+                float o[32];
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    const int nb = c0 + jj * 32;
-                    float o[32];
-                    // xhat chunk -> staging -> TMA store (map_y2)
+                for (int i = 0; i < 32; ++i) o[i] = (__uint_as_float(v[i]) - mean) * rstd * keep;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) o[i] = (__uint_as_float(v[jj * 32 + i]) - mean) * rstd * keep;
-                    if (lane == 0) tma_store_wait_read<0>();
-                    __syncwarp();
-                    const uint32_t obuf = wbuf + lane * 128;
+                for (int hh = 0; hh < 2; ++hh) {   // xhat: columns [nb + 16 hh, +16) -> map_y2
+                    stage64(reinterpret_cast<const uint32_t*>(o) + 16 * hh);
+                    if (lane == 0) { tma_store_3d(&map_y2, wbuf, nb + 16 * hh, row0, t.o2); tma_store_commit(); }
+                }
+                // y = mask(film_g * (xhat * w + b) + film_b)
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const uint32_t dst = obuf + ((c ^ (lane & 7)) << 4);
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o[4 * c]), "f"(o[4 * c + 1]),
-                                     "f"(o[4 * c + 2]), "f"(o[4 * c + 3]) : "memory");
-                    }
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) { tma_store_3d(&map_y2, wbuf, nb, t.o1 + quad * 32, t.o2); tma_store_commit(); }
-                    // y = mask(film_g * (xhat * w + b) + film_b)
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.ln_w + nb) + c4);
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_b + nb) + c4);
+                    o[4 * c4] = o[4 * c4] * w4.x + b4.x; o[4 * c4 + 1] = o[4 * c4 + 1] * w4.y + b4.y;
+                    o[4 * c4 + 2] = o[4 * c4 + 2] * w4.z + b4.z; o[4 * c4 + 3] = o[4 * c4 + 3] * w4.w + b4.w;
+                }
+                if (p.film) {
+                    const float* fg = p.film + (size_t)t.o2 * p.film_stride + nb;
 #pragma unroll
                     for (int c4 = 0; c4 < 8; ++c4) {
-                        const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.ln_w + nb) + c4);
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_b + nb) + c4);
-                        o[4 * c4] = o[4 * c4] * w4.x + b4.x; o[4 * c4 + 1] = o[4 * c4 + 1] * w4.y + b4.y;
-                        o[4 * c4 + 2] = o[4 * c4 + 2] * w4.z + b4.z; o[4 * c4 + 3] = o[4 * c4 + 3] * w4.w + b4.w;
+                        const float4 g4 = __ldg(reinterpret_cast<const float4*>(fg) + c4);
+                        const float4 e4 = __ldg(reinterpret_cast<const float4*>(fg + 128) + c4);
+                        o[4 * c4] = g4.x * o[4 * c4] + e4.x; o[4 * c4 + 1] = g4.y * o[4 * c4 + 1] + e4.y;
+                        o[4 * c4 + 2] = g4.z * o[4 * c4 + 2] + e4.z; o[4 * c4 + 3] = g4.w * o[4 * c4 + 3] + e4.w;
                     }
-                    if (p.film) {
-                        const float* fg = p.film + (size_t)t.o2 * p.film_stride + nb;
+                }
 #pragma unroll
-                        for (int c4 = 0; c4 < 8; ++c4) {
-                            const float4 g4 = __ldg(reinterpret_cast<const float4*>(fg) + c4);
-                            const float4 e4 = __ldg(reinterpret_cast<const float4*>(fg + 128) + c4);
-                            o[4 * c4] = g4.x * o[4 * c4] + e4.x; o[4 * c4 + 1] = g4.y * o[4 * c4 + 1] + e4.y;
-                            o[4 * c4 + 2] = g4.z * o[4 * c4 + 2] + e4.z; o[4 * c4 + 3] = g4.w * o[4 * c4 + 3] + e4.w;
-                        }
-                    }
+                for (int i = 0; i < 32; ++i) o[i] *= keep;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) o[i] *= keep;
-                    if (lane == 0) tma_store_wait_read<0>();
-                    __syncwarp();
+                for (int hh = 0; hh < 2; ++hh) {   // y -> map_y
+                    stage64(reinterpret_cast<const uint32_t*>(o) + 16 * hh);
+                    if (lane == 0) { tma_store_3d(&map_y, wbuf, nb + 16 * hh, row0, t.o2); tma_store_commit(); }
+                }
+                if (p.ln_planes) {
+                    uint32_t hl[32];                 // 16 hi words | 16 lo words
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const uint32_t dst = obuf + ((c ^ (lane & 7)) << 4);
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o[4 * c]), "f"(o[4 * c + 1]),
-                                     "f"(o[4 * c + 2]), "f"(o[4 * c + 3]) : "memory");
-                    }
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) { tma_store_3d(&map_y, wbuf, nb, t.o1 + quad * 32, t.o2); tma_store_commit(); }
-                    if (p.ln_planes) {
-                        uint32_t hi[16], lo[16];
+                    for (int i = 0; i < 16; ++i) split_pair_u32(o[2 * i], o[2 * i + 1], hl[i], hl[16 + i]);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) split_pair_u32(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
-                        if (lane == 0) tma_store_wait_read<0>();
-                        __syncwarp();
-                        const uint32_t rbuf = wbuf + lane * 64;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {   // SWIZZLE_64B
-                            const uint32_t off = (uint32_t)((c ^ ((lane >> 1) & 3)) << 4);
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbuf + off), "r"(hi[4 * c]), "r"(hi[4 * c + 1]),
-                                         "r"(hi[4 * c + 2]), "r"(hi[4 * c + 3]) : "memory");
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbuf + 2048 + off), "r"(lo[4 * c]),
-                                         "r"(lo[4 * c + 1]), "r"(lo[4 * c + 2]), "r"(lo[4 * c + 3]) : "memory");
-                        }
-                        fence_async_smem();
-                        __syncwarp();
-                        if (lane == 0) {
-                            tma_store_3d(&map_y3, wbuf, nb, t.o1 + quad * 32, t.o2);
-                            tma_store_3d(&map_y3, wbuf + 2048, nb, t.o1 + quad * 32, p.B + t.o2);
-                            tma_store_commit();
-                        }
+                    for (int pl = 0; pl < 2; ++pl) {
+                        stage64(hl + 16 * pl);
+                        if (lane == 0) { tma_store_3d(&map_y3, wbuf, nb, row0, pl * p.B + t.o2); tma_store_commit(); }
                     }
                 }
                 if (!dead) ++it;
                 continue;
             }
+            float o[32];
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                const int nb = t.o0 + (half * 2 + jj) * 32;
-                float o[32];
+            for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]);
+            if (MODE != MODE_WGRAD && !dead) {
+                // every condition below is warp-uniform except row_ok; columns >= Cout are clipped by the TMA store
+                const bool full = nb + 32 <= p.Cout;
+                if (p.alpha != 1.f) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[jj * 32 + i]);
-                if (MODE != MODE_WGRAD && !dead) {
-                    // every condition below is warp-uniform except row_ok; columns >= Cout are clipped by the TMA store
-                    const bool full = nb + 32 <= p.Cout;
-                    if (p.alpha != 1.f) {
+                    for (int i = 0; i < 32; ++i) o[i] *= p.alpha;
+                }
+                if (p.bias && !(p.debug & 256)) {
+                    if (full) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] *= p.alpha;
-                    }
-                    if (p.bias && !(p.debug & 256)) {
-                        if (full) {
-#pragma unroll
-                            for (int c = 0; c < 8; ++c) {
-                                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + c);
-                                o[4 * c] += bv.x; o[4 * c + 1] += bv.y; o[4 * c + 2] += bv.z; o[4 * c + 3] += bv.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (nb + i < p.Cout) o[i] += __ldg(p.bias + nb + i);
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + c);
+                            o[4 * c] += bv.x; o[4 * c + 1] += bv.y; o[4 * c + 2] += bv.z; o[4 * c + 3] += bv.w;
                         }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (nb + i < p.Cout) o[i] += __ldg(p.bias + nb + i);
                     }
-                    if (p.relu) {
+                }
+                if (p.relu) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = fmaxf(o[i], 0.f);
-                    }
-                    if (p.relu_src && row_ok) {
-                        const float* src = p.relu_src + grow * p.Cout + nb;
-                        if (full) {
+                    for (int i = 0; i < 32; ++i) o[i] = fmaxf(o[i], 0.f);
+                }
+                if (p.relu_src && row_ok) {
+                    const float* src = p.relu_src + grow * p.Cout + nb;
+                    if (full) {
 #pragma unroll
-                            for (int c = 0; c < 8; ++c) {
-                                const float4 m = __ldg(reinterpret_cast<const float4*>(src) + c);
-                                o[4 * c] = m.x > 0.f ? o[4 * c] : 0.f; o[4 * c + 1] = m.y > 0.f ? o[4 * c + 1] : 0.f;
-                                o[4 * c + 2] = m.z > 0.f ? o[4 * c + 2] : 0.f; o[4 * c + 3] = m.w > 0.f ? o[4 * c + 3] : 0.f;
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (nb + i < p.Cout) o[i] = __ldg(src + i) > 0.f ? o[i] : 0.f;
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 m = __ldg(reinterpret_cast<const float4*>(src) + c);
+                            o[4 * c] = m.x > 0.f ? o[4 * c] : 0.f; o[4 * c + 1] = m.y > 0.f ? o[4 * c + 1] : 0.f;
+                            o[4 * c + 2] = m.z > 0.f ? o[4 * c + 2] : 0.f; o[4 * c + 3] = m.w > 0.f ? o[4 * c + 3] : 0.f;
                         }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (nb + i < p.Cout) o[i] = __ldg(src + i) > 0.f ? o[i] : 0.f;
                     }
-                    if (p.relu_src_hi && row_ok) {   // mask from the bf16 hi plane of the forward activation: hi > 0 <=> fp32 value > 0
-                        const uint4* src = reinterpret_cast<const uint4*>(p.relu_src_hi + grow * p.Cout + nb);
+                }
+                if (p.relu_src_hi && row_ok) {   // mask from the bf16 hi plane of the forward activation: hi > 0 <=> fp32 value > 0
+                    const uint4* src = reinterpret_cast<const uint4*>(p.relu_src_hi + grow * p.Cout + nb);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const uint4 m = __ldg(src + c);
-                            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+                    for (int c = 0; c < 4; ++c) {
+                        const uint4 m = __ldg(src + c);
+                        const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                o[8 * c + 2 * k] = (short)(mw[k] & 0xffffu) > 0 ? o[8 * c + 2 * k] : 0.f;
-                                o[8 * c + 2 * k + 1] = ((int)mw[k] >> 16) > 0 ? o[8 * c + 2 * k + 1] : 0.f;
-                            }
-                        }
-                    }
-                    if (p.add_src && row_ok) {
-                        const float* src = p.add_src + grow * p.ldy + nb;
-                        if (full) {
-#pragma unroll
-                            for (int c = 0; c < 8; ++c) {
-                                const float4 a4 = __ldg(reinterpret_cast<const float4*>(src) + c);
-                                o[4 * c] += a4.x; o[4 * c + 1] += a4.y; o[4 * c + 2] += a4.z; o[4 * c + 3] += a4.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (nb + i < p.Cout) o[i] += __ldg(src + i);
-                        }
-                    }
-                    if (p.round_tf32) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = round_tf32(o[i]);
-                    }
-                    if (p.hp_dh) {
-                        if (!row_ok) {                                   // rows in [S, Sp): +0 (like the conversion pass wrote)
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) o[i] = 0.f;
-                        } else if (nb < p.hp_scale_cols) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) o[i] *= p.hp_scale;
+                        for (int k = 0; k < 4; ++k) {
+                            o[8 * c + 2 * k] = (short)(mw[k] & 0xffffu) > 0 ? o[8 * c + 2 * k] : 0.f;
+                            o[8 * c + 2 * k + 1] = ((int)mw[k] >> 16) > 0 ? o[8 * c + 2 * k + 1] : 0.f;
                         }
                     }
                 }
-                if (MODE != MODE_WGRAD && p.colsum && !dead) {
-                    // column sums of this warp's 32 rows x 32 columns by recursive halving across the lanes (31 shuffles):
-                    // afterwards lane l holds the sum of column l
-                    const float rk = row_ok ? 1.f : 0.f;
-                    float r16[16], r8[8], r4[4], r2[2];
+                if (p.add_src && row_ok) {
+                    const float* src = p.add_src + grow * p.ldy + nb;
+                    if (full) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const bool up = lane & 16;
-                        const float keep = (up ? o[i + 16] : o[i]) * rk, send = (up ? o[i] : o[i + 16]) * rk;
-                        r16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                    }
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 a4 = __ldg(reinterpret_cast<const float4*>(src) + c);
+                            o[4 * c] += a4.x; o[4 * c + 1] += a4.y; o[4 * c + 2] += a4.z; o[4 * c + 3] += a4.w;
+                        }
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const bool up = lane & 8;
-                        r8[i] = (up ? r16[i + 8] : r16[i]) + __shfl_xor_sync(0xffffffffu, up ? r16[i] : r16[i + 8], 8);
+                        for (int i = 0; i < 32; ++i)
+                            if (nb + i < p.Cout) o[i] += __ldg(src + i);
                     }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const bool up = lane & 4;
-                        r4[i] = (up ? r8[i + 4] : r8[i]) + __shfl_xor_sync(0xffffffffu, up ? r8[i] : r8[i + 4], 4);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const bool up = lane & 2;
-                        r2[i] = (up ? r4[i + 2] : r4[i]) + __shfl_xor_sync(0xffffffffu, up ? r4[i] : r4[i + 2], 2);
-                    }
-                    const bool up1 = lane & 1;
-                    const float tot = (up1 ? r2[1] : r2[0]) + __shfl_xor_sync(0xffffffffu, up1 ? r2[0] : r2[1], 1);
-                    if (nb + lane < p.Cout) atomicAdd(p.colsum + nb + lane, tot);
                 }
-                if (MODE != MODE_WGRAD && p.y_planes) {
-                    // the consumer GEMMs read bf16 hi|lo operand planes: emit them here instead of a later split pass over an
-                    // fp32 copy (32 columns = 64 bytes per row and plane)
-                    uint32_t hi[16], lo[16];
+                if (p.round_tf32) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) split_pair_u32(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
-                    if (p.skip_y && p.hp_dh == 16) {
-                        // head planes, head_dim 16: the chunk covers two heads; four dense [32 rows][32 B] tiles (hi head 0, hi head 1,
-                        // lo head 0, lo head 1; the map over R has a 16-column box and no swizzle)
+                    for (int i = 0; i < 32; ++i) o[i] = round_tf32(o[i]);
+                }
+                if (p.hp_dh) {
+                    if (!row_ok) {                                   // rows in [S, Sp): +0 (like the conversion pass wrote)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = 0.f;
+                    } else if (nb < p.hp_scale_cols) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] *= p.hp_scale;
+                    }
+                }
+            }
+            if (MODE != MODE_WGRAD && p.colsum && !dead) {
+                // column sums of this warp's 32 rows x 32 columns by recursive halving across the lanes (31 shuffles):
+                // afterwards lane l holds the sum of column l
+                const float rk = row_ok ? 1.f : 0.f;
+                float r16[16], r8[8], r4[4], r2[2];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const bool up = lane & 16;
+                    const float keep = (up ? o[i + 16] : o[i]) * rk, send = (up ? o[i] : o[i + 16]) * rk;
+                    r16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const bool up = lane & 8;
+                    r8[i] = (up ? r16[i + 8] : r16[i]) + __shfl_xor_sync(0xffffffffu, up ? r16[i] : r16[i + 8], 8);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const bool up = lane & 4;
+                    r4[i] = (up ? r8[i + 4] : r8[i]) + __shfl_xor_sync(0xffffffffu, up ? r8[i] : r8[i + 4], 4);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const bool up = lane & 2;
+                    r2[i] = (up ? r4[i + 2] : r4[i]) + __shfl_xor_sync(0xffffffffu, up ? r4[i] : r4[i + 2], 2);
+                }
+                const bool up1 = lane & 1;
+                const float tot = (up1 ? r2[1] : r2[0]) + __shfl_xor_sync(0xffffffffu, up1 ? r2[0] : r2[1], 1);
+                if (nb + lane < p.Cout) atomicAdd(p.colsum + nb + lane, tot);
+            }
+            if (MODE != MODE_WGRAD && p.y_planes) {
+                // the consumer GEMMs read bf16 hi|lo operand planes: emit them here instead of a later split pass over an
+                // fp32 copy (32 columns = 64 bytes per row and plane)
+                uint32_t hl[32];                     // 16 hi words | 16 lo words
+#pragma unroll
+                for (int i = 0; i < 16; ++i) split_pair_u32(o[2 * i], o[2 * i + 1], hl[i], hl[16 + i]);
+                if (p.skip_y && p.hp_dh == 16) {
+                    // head planes, head_dim 16: the chunk covers two heads; per plane two dense [32 rows][32 B] tiles (the map over R
+                    // has a 16-column box and no swizzle)
+                    const int hh = nb >> 4, pls = p.B * p.hp_NH;
+#pragma unroll
+                    for (int pl = 0; pl < 2; ++pl) {
                         if (lane == 0) tma_store_wait_read<0>();
                         __syncwarp();
 #pragma unroll
                         for (int sub = 0; sub < 2; ++sub) {
                             const uint32_t rb = wbuf + sub * 1024 + lane * 32;
 #pragma unroll
-                            for (int c = 0; c < 2; ++c) {
-                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rb + 16 * c), "r"(hi[8 * sub + 4 * c]),
-                                             "r"(hi[8 * sub + 4 * c + 1]), "r"(hi[8 * sub + 4 * c + 2]), "r"(hi[8 * sub + 4 * c + 3]) : "memory");
-                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rb + 2048 + 16 * c), "r"(lo[8 * sub + 4 * c]),
-                                             "r"(lo[8 * sub + 4 * c + 1]), "r"(lo[8 * sub + 4 * c + 2]), "r"(lo[8 * sub + 4 * c + 3]) : "memory");
-                            }
+                            for (int c = 0; c < 2; ++c)
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rb + 16 * c), "r"(hl[16 * pl + 8 * sub + 4 * c]),
+                                             "r"(hl[16 * pl + 8 * sub + 4 * c + 1]), "r"(hl[16 * pl + 8 * sub + 4 * c + 2]),
+                                             "r"(hl[16 * pl + 8 * sub + 4 * c + 3]) : "memory");
                         }
                         fence_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            const int hh = nb >> 4, pl = p.B * p.hp_NH;
-#pragma unroll
-                            for (int sub = 0; sub < 2; ++sub) {
-                                tma_store_3d(&map_y, wbuf + sub * 1024, 0, t.o1 + quad * 32, t.o2 * p.hp_NH + hh + sub);
-                                tma_store_3d(&map_y, wbuf + 2048 + sub * 1024, 0, t.o1 + quad * 32, pl + t.o2 * p.hp_NH + hh + sub);
-                            }
+                            tma_store_3d(&map_y, wbuf, 0, row0, pl * pls + t.o2 * p.hp_NH + hh);
+                            tma_store_3d(&map_y, wbuf + 1024, 0, row0, pl * pls + t.o2 * p.hp_NH + hh + 1);
                             tma_store_commit();
                         }
-                        continue;
                     }
-                    if (p.skip_y) {
-                        // planes only: stage hi | lo tiles (2 KB each) in this warp's buffer and TMA-store both (map_y is the
-                        // bf16 planes map; rows >= S are clipped by the store).  The arithmetic above ran while the previous
-                        // store was still reading the buffer.
-                        if (lane == 0) tma_store_wait_read<0>();
-                        __syncwarp();
-                        const uint32_t rbuf = wbuf + lane * 64;
+                    if (!dead) ++it;
+                    continue;
+                }
+                if (p.skip_y) {
+                    // planes only: hi tile then lo tile (2 KB each) through this warp's buffer (map_y is the bf16 planes map; rows >= S
+                    // are clipped by the store)
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {   // SWIZZLE_64B: 16-byte chunk c of row r lands at chunk c ^ ((r >> 1) & 3)
-                            const uint32_t off = (uint32_t)((c ^ ((lane >> 1) & 3)) << 4);
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbuf + off), "r"(hi[4 * c]), "r"(hi[4 * c + 1]),
-                                         "r"(hi[4 * c + 2]), "r"(hi[4 * c + 3]) : "memory");
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbuf + 2048 + off), "r"(lo[4 * c]),
-                                         "r"(lo[4 * c + 1]), "r"(lo[4 * c + 2]), "r"(lo[4 * c + 3]) : "memory");
-                        }
-                        if (!(p.debug & 64)) fence_async_smem();
-                        __syncwarp();
+                    for (int pl = 0; pl < 2; ++pl) {
+                        stage64(hl + 16 * pl);
                         if (lane == 0 && !(p.debug & 8)) {
                             if (p.hp_dh) {   // head planes, head_dim 32 / 64: one head per chunk (column d0 inside the head)
                                 const int hh = nb / p.hp_dh, d0 = nb - hh * p.hp_dh;
-                                tma_store_3d(&map_y, wbuf, d0, t.o1 + quad * 32, t.o2 * p.hp_NH + hh);
-                                tma_store_3d(&map_y, wbuf + 2048, d0, t.o1 + quad * 32, (p.B + t.o2) * p.hp_NH + hh);
+                                tma_store_3d(&map_y, wbuf, d0, row0, (pl * p.B + t.o2) * p.hp_NH + hh);
                             } else {
-                                tma_store_3d(&map_y, wbuf, nb, t.o1 + quad * 32, t.o2);
-                                tma_store_3d(&map_y, wbuf + 2048, nb, t.o1 + quad * 32, p.B + t.o2);
+                                tma_store_3d(&map_y, wbuf, nb, row0, pl * p.B + t.o2);
                             }
                             tma_store_commit();
                         }
-                        continue;
                     }
-                    if (row_ok) {   // fp32 output AND planes requested: direct (slower) global stores for the planes
-                        uint4* dh = reinterpret_cast<uint4*>(p.y_planes + grow * p.Cout + nb);
-                        uint4* dl = reinterpret_cast<uint4*>(p.y_planes + p.y_plane_elems + grow * p.Cout + nb);
+                    if (!dead) ++it;
+                    continue;
+                }
+                if (row_ok) {   // fp32 output AND planes requested: direct (slower) global stores for the planes
+                    uint4* dh = reinterpret_cast<uint4*>(p.y_planes + grow * p.Cout + nb);
+                    uint4* dl = reinterpret_cast<uint4*>(p.y_planes + p.y_plane_elems + grow * p.Cout + nb);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            dh[c] = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-                            dl[c] = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
-                        }
+                    for (int c = 0; c < 4; ++c) {
+                        dh[c] = make_uint4(hl[4 * c], hl[4 * c + 1], hl[4 * c + 2], hl[4 * c + 3]);
+                        dl[c] = make_uint4(hl[16 + 4 * c], hl[16 + 4 * c + 1], hl[16 + 4 * c + 2], hl[16 + 4 * c + 3]);
                     }
                 }
-                // each epilogue warp stages and stores its own 32 rows x 32 columns (4 KB): no cross-warp barrier.  The TMA
-                // store that last read the buffer (previous chunk) must be done reading before it is overwritten.
-                if (lane == 0) tma_store_wait_read<0>();
-                __syncwarp();
-                const uint32_t obuf = wbuf + lane * 128;
+            }
+            // fp32 output: two rounds of 32 rows x 16 columns (64-byte rows) through this warp's 2 KB buffer
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {   // 16-byte chunk c of this row lands at chunk (c ^ (row & 7)): SWIZZLE_128B
-                    const uint32_t dst = obuf + ((c ^ (lane & 7)) << 4);
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o[4 * c]), "f"(o[4 * c + 1]),
-                                 "f"(o[4 * c + 2]), "f"(o[4 * c + 3]) : "memory");
-                }
-                if (!(p.debug & 64)) fence_async_smem();
-                __syncwarp();
+            for (int hh = 0; hh < 2; ++hh) {
+                stage64(reinterpret_cast<const uint32_t*>(o) + 16 * hh);
                 if (lane == 0 && !(p.debug & 8)) {
-                    tma_store_3d(&map_y, wbuf, nb, t.o1 + quad * 32, t.o2);
+                    tma_store_3d(&map_y, wbuf, nb + 16 * hh, row0, t.o2);
                     tma_store_commit();
                 }
             }
@@ -1157,7 +1115,8 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
                               (uint64_t)a.head_Sp * a.head_dim * 2, bw, 32, 1, bw == 32, false, bw != 32)))
             return rc;
     } else if (a.y) {
-        if ((rc = make_map_3d(&my, a.y, 4, a.Cout, a.S, a.B, (uint64_t)a.ldy * 4, (uint64_t)a.S * a.ldy * 4, 32, 32, 1))) return rc;
+        // fp32 output: 32-row x 16-column boxes (64-byte rows, SWIZZLE_64B), two per epilogue warp and tile
+        if ((rc = make_map_3d(&my, a.y, 4, a.Cout, a.S, a.B, (uint64_t)a.ldy * 4, (uint64_t)a.S * a.ldy * 4, 16, 32, 1, true))) return rc;
     } else {
         // planes-only output: ONE bf16 map over [2][B*S][Cout] seen as (Cout, S, 2B): the lo plane is utterance index B + b;
         // 32 x 32 boxes of 64-byte rows, SWIZZLE_64B (the epilogue writes the staging tile with the matching xor)
@@ -1211,7 +1170,7 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     if ((rc = make_map_3d(&mwl, wl, 2, a.Cin, a.Cout, a.KW, ws1, ws2, 64, TN, 1))) return rc;
     if (a.ln) {
         CUtensorMap mxhat, mplanes;
-        if ((rc = make_map_3d(&mxhat, a.ln->xhat, 4, a.Cout, a.S, a.B, (uint64_t)a.Cout * 4, (uint64_t)a.S * a.Cout * 4, 32, 32, 1))) return rc;
+        if ((rc = make_map_3d(&mxhat, a.ln->xhat, 4, a.Cout, a.S, a.B, (uint64_t)a.Cout * 4, (uint64_t)a.S * a.Cout * 4, 16, 32, 1, true))) return rc;
         if (a.y_planes) {
             if ((rc = make_map_3d(&mplanes, a.y_planes, 2, a.Cout, a.S, 2 * (uint64_t)a.B, (uint64_t)a.Cout * 2, (uint64_t)a.S * a.Cout * 2, 32, 32,
                                   1, true)))
@@ -1384,7 +1343,7 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
     if ((rc = make_map_3d(&mal, dl, 2, a.Cout, a.S, a.B, d1, d2, 64, 64, 1))) return rc;
     if ((rc = make_map_3d(&mbh, xh, 2, a.Cin, a.S, a.B, x1, x2, 64, 64, 1))) return rc;
     if ((rc = make_map_3d(&mbl, xl, 2, a.Cin, a.S, a.B, x1, x2, 64, 64, 1))) return rc;
-    if ((rc = make_map_3d(&my, part, 4, a.Cin, a.Cout, (uint64_t)nsplit * a.KW, (uint64_t)a.Cin * 4, (uint64_t)a.Cout * a.Cin * 4, 32, 32, 1)))
+    if ((rc = make_map_3d(&my, part, 4, a.Cin, a.Cout, (uint64_t)nsplit * a.KW, (uint64_t)a.Cin * 4, (uint64_t)a.Cout * a.Cin * 4, 16, 32, 1, true)))
         return rc;
     if ((rc = launch<PREC_BF16X3, MODE_WGRAD>(mah, mal, mbh, mbl, my, p, st))) return rc;
     const size_t per = (size_t)a.KW * a.Cout * a.Cin;
