@@ -191,6 +191,18 @@ def cpu_reference_run(cfg, steps, warmup):
     return frames / dt, dt, {'value': frames / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample}
 
 
+def cpu_baseline_subprocess(config_name):
+    """The cpu_baseline leg of the `ours` arm: the reference arm itself in a FRESH process (clean OpenMP state: torchrun exports
+    OMP_NUM_THREADS=1 and this process has long initialised its thread pools), all host threads."""
+    env = {k: v for k, v in os.environ.items() if k not in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'RANK', 'WORLD_SIZE', 'LOCAL_RANK')}
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--config', config_name, '--steps', '1', '--warmup', '0'],
+                         capture_output=True, text=True, env=env, timeout=900)
+    try:
+        return json.loads(out.stdout.strip().splitlines()[-1])['cpu_baseline']
+    except Exception:
+        return {'unavailable': (out.stderr or out.stdout)[-300:]}
+
+
 def run_reference_arm(args, cfg):
     """--impl reference: the reference's algorithm on the host CPU (the Python reference cannot travel to the GPU box, so this
     is the pinned oracle port, all host threads), same metric/config, each step a bounded sample of the workload.  Under torchrun
@@ -594,7 +606,7 @@ def main():
             torch.cuda.empty_cache()
             line['gpu_eager_baseline'] = gpu_eager_baseline(cfg, dev)
         if not args.no_cpu_baseline:
-            line['cpu_baseline'] = cpu_reference_run(CONFIGS['train'] if args.config != 'stress' else cfg, 1, 0)[2]
+            line['cpu_baseline'] = cpu_baseline_subprocess('train' if args.config != 'stress' else 'stress')
         if args.config == 'stress':
             prof = os.path.join(ROOT, 'profiles', 'r2_stress_dram.json')
             if os.path.exists(prof):   # sum of dram__bytes_read + dram__bytes_write over the ncu launch list of ONE step of this config
@@ -604,7 +616,13 @@ def main():
                                         'dram_bytes_per_step': d['dram_bytes_per_step'], 'source': d.get('source')}
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
+        # the other ranks wait for rank 0's CPU / eager legs on the rendezvous store (a blocking socket wait: an NCCL barrier would
+        # spin one host core per rank and steal them from the CPU baseline)
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set('dx_bench_done', '1')
+        else:
+            store.wait(['dx_bench_done'])
         dist.destroy_process_group()
 
 

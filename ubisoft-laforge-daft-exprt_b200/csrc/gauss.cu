@@ -96,11 +96,18 @@ __global__ void __launch_bounds__(256) gauss_upsample_fwd_kernel(GaussArgs p) {
     extern __shared__ __align__(16) float sm[];
     float (*Ws)[FT + 1] = reinterpret_cast<float (*)[FT + 1]>(sm);  // [L][33]
     float* Zs = sm + (size_t)p.L * (FT + 1);                        // [8][32] partial column sums, then [32] totals
+    // band of phonemes whose Gaussian is non-zero (in fp32, exactly) on at least one of this CTA's 32 frames: the centres grow
+    // monotonically with the phoneme index, so the band is a short contiguous range (~20 of 200) and the weighted sum below only
+    // walks it — an exact skip, every term left out is multiplied by w == 0.0f
+    int* band = reinterpret_cast<int*>(Zs + 256);                   // [lo, hi]
     const int b = blockIdx.y, t0 = blockIdx.x * FT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int len = min((int)p.lens[b], p.L);
     const float tt = (float)(t0 + lane) + 0.5f;
+    if (threadIdx.x == 0) { band[0] = p.L; band[1] = -1; }
+    __syncthreads();
     float part = 0.f;
+    int my_lo = p.L, my_hi = -1;
     for (int i = warp; i < p.L; i += 8) {
         float pr = 0.f;
         if (i < len) {
@@ -110,7 +117,9 @@ __global__ void __launch_bounds__(256) gauss_upsample_fwd_kernel(GaussArgs p) {
         }
         Ws[i][lane] = pr;
         part += pr;
+        if (__ballot_sync(0xffffffffu, pr != 0.f)) { my_lo = min(my_lo, i); my_hi = i; }
     }
+    if (lane == 0 && my_hi >= 0) { atomicMin(&band[0], my_lo); atomicMax(&band[1], my_hi); }
     Zs[warp * 32 + lane] = part;
     __syncthreads();
     if (warp == 0) {
@@ -128,13 +137,14 @@ __global__ void __launch_bounds__(256) gauss_upsample_fwd_kernel(GaussArgs p) {
     }
     __syncthreads();
     // up[t0 + f][c] = sum_i w[i][f] * xp[i][c] : warp -> frames 4*warp..+3, lane -> channels 4*lane..+3 (+128 per pass)
+    const int i_lo = band[0], i_hi = min(band[1], len - 1);
     for (int c0 = lane * 4; c0 < p.D; c0 += 128) {
         float acc[4][4];
 #pragma unroll
         for (int f = 0; f < 4; ++f)
 #pragma unroll
             for (int k = 0; k < 4; ++k) acc[f][k] = 0.f;
-        for (int i = 0; i < len; ++i) {
+        for (int i = i_lo; i <= i_hi; ++i) {
             const float4 xv = *reinterpret_cast<const float4*>(p.xp + ((size_t)b * p.L + i) * p.D + c0);
 #pragma unroll
             for (int f = 0; f < 4; ++f) {
@@ -155,7 +165,7 @@ __global__ void __launch_bounds__(256) gauss_upsample_fwd_kernel(GaussArgs p) {
 
 int gauss_upsample_fwd(const GaussArgs& a, cudaStream_t st) {
     DX_REQUIRE(a.D % 128 == 0, "gauss_upsample: D=%d must be a multiple of 128", a.D);
-    const size_t smem = ((size_t)a.L * (FT + 1) + 256) * sizeof(float);
+    const size_t smem = ((size_t)a.L * (FT + 1) + 256 + 4) * sizeof(float);   // weight tile, column partials, band bounds
     DX_REQUIRE(smem <= 200 * 1024, "gauss_upsample: L=%d too large for the shared-memory weight tile", a.L);
     DX_CUDA(cudaFuncSetAttribute(gauss_upsample_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(a.T, FT), a.B);
