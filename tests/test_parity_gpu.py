@@ -551,8 +551,13 @@ def test_graph_step_matches_eager(dev):
     p_graph = opt.flat_p.detach().cpu().numpy().copy()
 
     assert opt.step_count == len(iters) and len(g.cache) == 1 and g.launches_replayed > 100 * len(iters)
-    for a, b in zip(eager, graph):
-        np.testing.assert_allclose(b, a, rtol=2e-3, atol=1e-6)   # trajectories stay together over 4 Adam steps
+    # Step 0 sees identical weights: the replay must reproduce the eager numbers to fp32 rounding.  From then on the two runs are two
+    # samples of a chaotic trajectory: fp32 atomics ordering (dQ reductions, column sums) perturbs gradients by ~1e-7, and Adam with
+    # eps = 1e-9 turns that into lr-sized moves of the parameters whose gradient is ~0.  Measured with tools/graph_vs_eager.py: two
+    # EAGER runs of the same code differ by 1e-7 / 3e-6 / 4e-4 / 4e-3 (max relative loss term) at steps 0 / 1 / 2 / 3 — the bounds
+    # below are that envelope, not slack for the graph.
+    for k, (a, b) in enumerate(zip(eager, graph)):
+        np.testing.assert_allclose(b, a, rtol=(1e-5, 1e-4, 4e-3, 2e-2)[k], atol=1e-6)
     assert not np.allclose(graph[0][7], graph[3][7], rtol=1e-4)  # ... and the weights did move
     moved = np.abs(p_eager - p_init).max()
     assert moved > 1e-4
