@@ -10,8 +10,14 @@
  *     every workspace; the library never allocates persistent device memory and never frees caller memory);
  *   - activations are channels-last fp32 `[B, S, C]` (row = one phoneme / mel frame); lengths / ids are int64 device arrays,
  *     exactly the tensors `DaftExprt.parse_batch` (model.py:727-753) produces;
- *   - every call is asynchronous on `stream` (a `cudaStream_t` passed as void*; pass torch's current stream) and re-entrant
- *     per stream; no host synchronisation inside;
+ *   - every COMPUTE call is asynchronous on `stream` (a `cudaStream_t` passed as void*; pass torch's current stream), keeps no
+ *     state of its own between calls and does no host synchronisation, so different streams may be driven concurrently as long
+ *     as the CONFIGURATION below is not changed meanwhile;
+ *   - configuration is PROCESS-GLOBAL and not thread-safe (set it once, or between steps, from one thread): the GEMM backend and
+ *     pass count (dx_set_gemm_backend / dx_set_gemm_passes), the attention kernel choice (dx_set_attention_backend), the per-step
+ *     device block (dx_set_step_state) and the deferred weight-gradient reduction list (dx_wgrad_defer / dx_wgrad_flush: entries
+ *     recorded by dx_conv_wgrad calls are flushed by the next dx_wgrad_flush on whatever stream it names).  One model per process
+ *     and one stream at a time inside a deferred backward is the supported pattern (the reference runs one model per process too);
  *   - return 0 on success, negative on error (DX_ERR_*); `dx_last_error()` returns a thread-local message; no exceptions
  *     cross the ABI;
  *   - dropout: `p == 0` disables; masks are regenerated from (seed, element index) in backward, never stored.
@@ -145,7 +151,16 @@ int dx_inproj_head_planes(const void* x_planes, const void* w_planes, const floa
 /* qkv may be NULL when `planes` was filled by dx_inproj_head_planes (tensor-core backends only). */
 int dx_attention_fwd(const float* qkv, const int64_t* lens, float* ctx, float* lse, void* planes, void* ctx_planes, int B, int S,
                      int H, int dh, float dropout_p, uint64_t seed, void* stream);
-/* scratch: dx_attention_bwd_scratch_bytes() bytes; dqkv [B,S,3*H*dh] is fully written */
+/* Backward counterpart of dx_inproj_head_planes: d(ctx) = d(proj) W_out (the input gradient of nn.MultiheadAttention's out_proj,
+ * model.py:165) is never materialised in fp32; the GEMM epilogue writes the per-head bf16 hi|lo planes of dO AND
+ * delta[b,h,s] = sum_d dO * O (softmax-backward row term) into `bwd_scratch` (dx_attention_bwd_scratch_bytes()), in the layout
+ * dx_attention_bwd builds for itself.  Follow with dx_attention_bwd(qkv = NULL, ..., dctx = NULL, ..., scratch = bwd_scratch).
+ * dy_planes: planes [2][B*S][Cin] of d(proj); w_dgrad_planes: planes of the dgrad pack [1][H*dh][Cin] of out_proj.weight; ctx: the
+ * forward attention output [B,S,H*dh] fp32. */
+int dx_outproj_dgrad_head_planes(const void* dy_planes, const void* w_dgrad_planes, const float* ctx, void* bwd_scratch, const int64_t* lens,
+                                 int B, int S, int Cin, int H, int dh, void* stream);
+/* scratch: dx_attention_bwd_scratch_bytes() bytes; dqkv [B,S,3*H*dh] is fully written.  qkv may be NULL (tensor-core kernels read
+ * `planes` only); dctx may be NULL when `scratch` was filled by dx_outproj_dgrad_head_planes. */
 int dx_attention_bwd(const float* qkv, const void* planes, const int64_t* lens, const float* ctx, const float* lse,
                      const float* dctx, float* dqkv, void* scratch, int B, int S, int H, int dh, float dropout_p, uint64_t seed,
                      void* stream);

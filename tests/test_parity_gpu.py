@@ -1093,3 +1093,36 @@ def test_gemm_layernorm_epilogue_matches_separate_kernels(dev, cfg):
             ref = film[:, None, :D].double() * ref + film[:, None, D:].double()
         ref = ref * (torch.arange(S)[None, :] < lens[:, None])[:, :, None]
         assert scale_rel_err(y1, ref) < 5e-5
+
+
+@pytest.mark.parametrize('cfg', [(3, 300, 2, 64, 0.0), (2, 257, 8, 16, 0.1), (2, 130, 4, 32, 0.0)])
+def test_attention_sublayer_fused_projections_match_unfused(dev, cfg):
+    """The whole attention sub-layer with the projection GEMMs writing the attention operand planes themselves (in-projection ->
+    q|k|v planes; out-projection input gradient -> dO planes + delta) against the path with fp32 qkv / d(ctx) tensors and conversion
+    passes: same forward bits, gradients equal to fp32 reduction-order noise."""
+    from daft_exprt_b200 import ops
+    set_backend('bf16x3')
+    B, S, H, dh, p = cfg
+    D = H * dh
+    g = torch.Generator().manual_seed(S + dh)
+    lens = torch.randint(1, S + 1, (B,), generator=g)
+    lens[0] = S
+    x0 = torch.randn(B, S, D, generator=g) * (torch.arange(S)[None, :] < lens[:, None])[:, :, None]
+    ws = [torch.randn(3 * D, D, generator=g) / np.sqrt(D), torch.randn(3 * D, generator=g) * 0.1, torch.randn(D, D, generator=g) / np.sqrt(D),
+          torch.randn(D, generator=g) * 0.1, torch.rand(D, generator=g) + 0.5, torch.randn(D, generator=g) * 0.1]
+    dy = torch.randn(B, S, D, generator=g)
+    res = []
+    for fused in (False, True):
+        ops.fused_inproj(fused)
+        ops._seed_counter[0] = 1000                       # same dropout seeds in both runs
+        x = x0.clone().to(dev).requires_grad_(True)
+        params = [w.clone().to(dev).requires_grad_(True) for w in ws]
+        y = ops.AttentionSubLayer.apply(x, lens.to(dev), *params, H, p)
+        y.backward(dy.to(dev))
+        res.append((y.detach().clone(), x.grad.clone(), [q.grad.clone() for q in params]))
+    ops.fused_inproj(True)
+    (y0, dx0, g0), (y1, dx1, g1) = res
+    assert torch.equal(y0, y1)
+    assert scale_rel_err(dx1, dx0) < 1e-5
+    for a, b in zip(g1, g0):
+        assert scale_rel_err(a, b) < 1e-5

@@ -641,7 +641,8 @@ int attention_bwd_mma(const AttnArgs& a_in, void* planes, void* scratch, cudaStr
     const int D = a.H * a.dh;
     DX_CUDA(cudaMemsetAsync(a.dqkv, 0, (size_t)a.B * a.S * 3 * D * sizeof(float), st));   // dq is accumulated with atomics
     // dO planes and delta = rowsum(dO * O) per head in ONE pass over dctx
-    int rc = prep(a.dctx, D, a.B, a.S, a.Sp, a.H, a.dh, 0, 1.f, (__nv_bfloat16*)a.GR, (__nv_bfloat16*)a.GTr, st, a.ctx, a.delta);
+    // dctx == NULL: the out-projection's input-gradient GEMM already wrote the dO planes and delta itself (dx_outproj_dgrad_head_planes)
+    int rc = a.dctx ? prep(a.dctx, D, a.B, a.S, a.Sp, a.H, a.dh, 0, 1.f, (__nv_bfloat16*)a.GR, (__nv_bfloat16*)a.GTr, st, a.ctx, a.delta) : DX_OK;
     if (rc) return rc;
     if (attn_bwd_tc_enabled(a.dh) && attention_bwd_tc_supported(a)) return attention_bwd_tc(a, st);   // tcgen05 / TMEM backward
     switch (a.dh) {

@@ -154,6 +154,28 @@ int dx_inproj_head_planes(const void* x_planes, const void* w_planes, const floa
     return conv_gemm_tc(a, ST(stream));
 }
 
+int dx_outproj_dgrad_head_planes(const void* dy_planes, const void* w_dgrad_planes, const float* ctx, void* bwd_scratch, const int64_t* lens,
+                                 int B, int S, int Cin, int H, int dh, void* stream) {
+    DX_REQUIRE(g_backend == DX_GEMM_TCGEN05_BF16X3, "dx_outproj_dgrad_head_planes: needs the bf16x3 tensor-core backend");
+    DX_REQUIRE(dy_planes && w_dgrad_planes && ctx && bwd_scratch, "dx_outproj_dgrad_head_planes: dy_planes, w_dgrad_planes, ctx and bwd_scratch are required");
+    AttnArgs at;
+    memset(&at, 0, sizeof(at));
+    at.H = H; at.dh = dh;
+    DX_REQUIRE(attention_mma_supported(at) && Cin % 8 == 0 && Cin >= 16, "dx_outproj_dgrad_head_planes: H=%d dh=%d Cin=%d", H, dh, Cin);
+    const int D = H * dh, Sp = (S + 63) / 64 * 64;
+    ConvGemmArgs a = gemm_args(nullptr, dy_planes, nullptr, w_dgrad_planes, nullptr, nullptr, nullptr, nullptr, nullptr, 0, B, S, Cin, D, 1, Cin, D,
+                               1.f, 0, 0, lens, 0);
+    // same layout as dx_attention_bwd builds itself: [dO planes hi|lo : 2 * B * H * Sp * dh bf16][delta : B * H * S fp32], 256-byte aligned
+    uint8_t* sb = (uint8_t*)(((uintptr_t)bwd_scratch + 255) & ~(uintptr_t)255);
+    a.head_planes = sb;
+    a.head_dim = dh;
+    a.head_Sp = Sp;
+    a.head_scale_cols = 0;
+    a.head_dot_src = ctx;
+    a.head_dot_out = (float*)(sb + (size_t)2 * B * H * Sp * dh * 2);
+    return conv_gemm_tc(a, ST(stream));
+}
+
 int dx_conv_gemm_ln(const void* x_planes, const void* w_planes, const float* bias, const float* res, const float* ln_w, const float* ln_b,
                     const float* film, int film_stride, const int64_t* lens, float* y, void* y_planes, float* xhat, float* rstd, int B, int S,
                     int Cin, int KW, float p_in, uint64_t seed_in, void* stream) {
@@ -241,6 +263,8 @@ int dx_attention_bwd(const float* qkv, const void* planes, const int64_t* lens, 
     a.B = B; a.S = S; a.H = H; a.dh = dh; a.dropout_p = dropout_p; a.seed = seed;
     a.dyn = g_step_state;
     DX_REQUIRE(scratch != nullptr, "dx_attention_bwd: scratch (dx_attention_bwd_scratch_bytes) required");
+    DX_REQUIRE(dctx != nullptr || (g_backend != DX_GEMM_FP32_CUDA_CORES && attention_mma_supported(a)),
+               "dx_attention_bwd: dctx == NULL (scratch pre-filled by dx_outproj_dgrad_head_planes) needs the tensor-core kernels");
     if (g_backend != DX_GEMM_FP32_CUDA_CORES && attention_mma_supported(a))
         return attention_bwd_mma(a, (void*)planes, scratch, ST(stream));
     a.delta = (float*)scratch;

@@ -192,6 +192,10 @@ struct TcParams {
     // (q pre-scaled by 1/sqrt(dh)); rows >= S are written as zeros up to Sp.  hp_dh == 0: off.
     int hp_dh, hp_NH, hp_scale_cols;
     float hp_scale;
+    // optional with head planes (attention backward): hp_dot_out[b][head][s] += sum over the head's columns of out * hp_dot_src
+    // (delta = rowsum(dO * O) of the softmax backward; zero-initialised by the launcher), hp_dot_src fp32 [B*S][Cout]
+    const float* hp_dot_src;
+    float* hp_dot_out;
     // EPI_LN
     const float* ln_res;                // residual [B*S][Cout] or nullptr
     const float* ln_w;
@@ -724,6 +728,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
                     for (int i = 0; i < 32; ++i) o[i] = round_tf32(o[i]);
                 }
+                if (p.hp_dot_src && row_ok) {
+                    const float4* src = reinterpret_cast<const float4*>(p.hp_dot_src + grow * p.Cout + nb);
+                    float d0 = 0.f, d1 = 0.f;                         // columns [0, 16) and [16, 32) of the chunk
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 a4 = __ldg(src + c);
+                        const float t = o[4 * c] * a4.x + o[4 * c + 1] * a4.y + o[4 * c + 2] * a4.z + o[4 * c + 3] * a4.w;
+                        if (c < 4) d0 += t; else d1 += t;
+                    }
+                    if (p.hp_dh == 16) {                              // two heads per chunk: each entry has exactly one writer
+                        float* dst = p.hp_dot_out + ((size_t)t.o2 * p.hp_NH + (nb >> 4)) * p.S + s;
+                        dst[0] = d0;
+                        dst[p.S] = d1;
+                    } else {                                          // dh / 32 chunks per head: order-independent sum of <= 2 addends
+                        atomicAdd(p.hp_dot_out + ((size_t)t.o2 * p.hp_NH + nb / p.hp_dh) * p.S + s, d0 + d1);
+                    }
+                }
                 if (p.hp_dh) {
                     if (!row_ok) {                                   // rows in [S, Sp): +0 (like the conversion pass wrote)
 #pragma unroll
@@ -1067,7 +1088,7 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     if (a.y_colsum) DX_CUDA(cudaMemsetAsync(a.y_colsum, 0, (size_t)a.Cout * sizeof(float), st));
     p.y_plane_elems = (long long)a.B * a.S * a.Cout;
     p.skip_y = a.y == nullptr;
-    p.hp_dh = 0; p.hp_NH = 0; p.hp_scale_cols = 0; p.hp_scale = 1.f;
+    p.hp_dh = 0; p.hp_NH = 0; p.hp_scale_cols = 0; p.hp_scale = 1.f; p.hp_dot_src = nullptr; p.hp_dot_out = nullptr;
     p.ln_res = nullptr; p.ln_w = nullptr; p.ln_b = nullptr; p.film = nullptr; p.film_stride = 0; p.ln_rstd = nullptr;
     p.ln_p_in = 0.f; p.ln_seed_in = 0; p.dyn = nullptr; p.ln_planes = 0;
     p.passes = g_passes_conv;
@@ -1092,6 +1113,11 @@ int conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
         p.y_planes = (__nv_bfloat16*)a.head_planes;
         p.skip_y = 1;
         p.hp_dh = a.head_dim; p.hp_NH = a.Cout / a.head_dim; p.hp_scale_cols = a.head_scale_cols; p.hp_scale = a.head_scale;
+        if (a.head_dot_src) {
+            DX_REQUIRE(a.head_dot_out && (((uintptr_t)a.head_dot_src | (uintptr_t)a.head_dot_out) & 15) == 0, "conv_gemm_tc: head_dot_src / head_dot_out");
+            p.hp_dot_src = a.head_dot_src; p.hp_dot_out = a.head_dot_out;
+            DX_CUDA(cudaMemsetAsync(a.head_dot_out, 0, (size_t)a.B * p.hp_NH * a.S * sizeof(float), st));
+        }
     }
     DX_REQUIRE(a.y || a.y_planes || a.head_planes, "conv_gemm_tc: no output (y and y_planes are both NULL)");
     DX_REQUIRE(!(a.y_planes || a.relu_src_hi) || (a.Cout % 32 == 0 && (((uintptr_t)a.y_planes | (uintptr_t)a.relu_src_hi) & 15) == 0),
@@ -1322,7 +1348,7 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
     TcParams p;
     p.bias = nullptr; p.relu_src = nullptr; p.add_src = nullptr;
     p.relu_src_hi = nullptr; p.y_planes = nullptr; p.colsum = nullptr; p.y_plane_elems = 0; p.skip_y = 0;
-    p.hp_dh = 0; p.hp_NH = 0; p.hp_scale_cols = 0; p.hp_scale = 1.f;
+    p.hp_dh = 0; p.hp_NH = 0; p.hp_scale_cols = 0; p.hp_scale = 1.f; p.hp_dot_src = nullptr; p.hp_dot_out = nullptr;
     p.ln_res = nullptr; p.ln_w = nullptr; p.ln_b = nullptr; p.film = nullptr; p.film_stride = 0; p.ln_rstd = nullptr;
     p.ln_p_in = 0.f; p.ln_seed_in = 0; p.dyn = nullptr; p.ln_planes = 0;
     p.passes = g_passes_wgrad;

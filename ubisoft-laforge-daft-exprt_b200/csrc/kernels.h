@@ -41,6 +41,9 @@ struct ConvGemmArgs {
     void* head_planes = nullptr;
     int head_dim = 0, head_Sp = 0, head_scale_cols = 0;
     float head_scale = 1.f;
+    // optional with head_planes: head_dot_out[b][head][s] = sum_d out[b,s,head,d] * head_dot_src[b,s,head*dh + d] (fp32 [B*S][Cout])
+    const float* head_dot_src = nullptr;
+    float* head_dot_out = nullptr;
     int B, S, Cin, Cout, KW;
     int ldx, ldy;
     float alpha;

@@ -432,10 +432,15 @@ class AttentionSubLayer(torch.autograd.Function):
         dy = _check_input(dy)
         dv, dproj, dln_w, dln_b, _, dprojP, dpb = ln_bwd(dy, xhat, rstd, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p, seed_in=seed_out,
                                                          emit_planes=True)
-        datt = conv_gemm(dproj, out_wd, None, B, S, x_planes=dprojP, lens=lens)   # dproj == 0 beyond len: exact
+        scratch = torch.empty(lib().dx_attention_bwd_scratch_bytes(B, S, H, dh), device=dy.device, dtype=torch.uint8)
+        if fused_inproj() and planes is not None and dprojP is not None and out_wd.planes is not None:
+            # the out-projection's input-gradient GEMM writes the dO operand planes and delta = rowsum(dO * O) itself: no fp32 d(ctx)
+            datt = None
+            _call('dx_outproj_dgrad_head_planes', _p(dprojP), _p(out_wd.planes), _p(att), _p(scratch), _p(lens), B, S, D, H, dh, _st())
+        else:
+            datt = conv_gemm(dproj, out_wd, None, B, S, x_planes=dprojP, lens=lens)   # dproj == 0 beyond len: exact
         d_out_w, d_out_b = conv_wgrad(att, dproj, B, S, D, D, 1, out_shape, x_planes=attP, dy_planes=dprojP, dbias=dpb, lens=lens)
         dqkv = torch.empty(B, S, 3 * D, device=dy.device, dtype=torch.float32)
-        scratch = torch.empty(lib().dx_attention_bwd_scratch_bytes(B, S, H, dh), device=dy.device, dtype=torch.uint8)
         _call('dx_attention_bwd', _p(qkv), _p(planes), _p(lens), _p(att), _p(lse), _p(datt), _p(dqkv), _p(scratch), B, S, H, dh, p,
               seed_attn, _st())
         dqkvP, dqb = make_planes(dqkv, B * S, 3 * D, want_colsum=True)
