@@ -6,7 +6,7 @@ from daft_exprt_b200 import ops
 ops.set_backend('bf16x3')
 dev = torch.device('cuda', 0)
 import bench
-lens = bench.make_host_batch(0)[9].to(dev)   # output_lengths of the bench batch
+lens = bench.rank_batch(bench.CONFIGS['train'], 0)[9].to(dev)   # output_lengths of the bench batch
 flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 for (B, S, H, dh, p) in [(32, 1000, 2, 64, 0.1), (32, 1000, 8, 16, 0.1), (32, 1000, 2, 64, 0.0), (32, 1000, 8, 16, 0.0)]:
     D = H * dh

@@ -7,5 +7,7 @@ entry.build()
 import bench
 from daft_exprt_b200 import ops
 ops.set_backend('bf16x3')
-flops, t = bench.time_dominant_kernel(torch.device('cuda', 0), iters=4)
+dev = torch.device('cuda', 0)
+flush = torch.empty(512 * 1024 * 1024 // 4, device=dev)
+flops, t = bench.time_dominant_kernel(bench.CONFIGS['train'], dev, flush)
 print(f'{flops / t / 1e12:.1f} algorithmic TFLOP/s, {t * 1e6:.1f} us per launch')

@@ -5,6 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from daft_exprt_b200 import ops, cabi
 ops.set_backend('bf16x3')
+ops.set_gemm_passes(int(os.environ.get('DX_PASSES', '3')), 3)
 dev = torch.device('cuda', 0)
 shape = tuple(int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else '32,1000,128,1024,3').split(','))
 planes = len(sys.argv) > 2
