@@ -1126,3 +1126,41 @@ def test_attention_sublayer_fused_projections_match_unfused(dev, cfg):
     assert scale_rel_err(dx1, dx0) < 1e-5
     for a, b in zip(g1, g0):
         assert scale_rel_err(a, b) < 1e-5
+
+
+@pytest.mark.parametrize('backend', ['fp32', 'bf16x3'])
+def test_two_predictor_blocks_match_oracle(dev, backend):
+    """hparams the reference accepts but round 1 rejected: local_prosody_predictor.nb_blocks = 2 (model.py:526-543: the second block
+    takes conv_channels inputs, FiLM per block, ONE mask after the last block).  Forward, loss and all gradients vs the fp64 oracle."""
+    from daft_exprt_b200.hparams import default_hparams
+    from daft_exprt_b200.loss import DaftExprtLoss
+    from daft_exprt_b200.model import DaftExprt
+    set_backend(backend)
+    n_ids = 5
+    hp = default_hparams(n_speakers=n_ids + 1)
+    hp.local_prosody_predictor['nb_blocks'] = 2
+    model = DaftExprt(hp)
+    sd = synthetic.synthetic_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, 77)
+    assert len(sd) == 201 and 'prosody_predictor.blocks.1.4.conv.weight' in sd
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    crit = DaftExprtLoss(0, hp)
+    inputs = synthetic.make_batch(3, 33, 140, n_ids, seed=12)
+    din = to_dev(inputs, dev)
+    out = model(din)
+    total, _ = crit(out, targets_of(din), 1500)
+    total.backward()
+    ohp = oracle.OracleHParams(n_speakers=n_ids + 1)
+    ohp.local_prosody_predictor = dict(ohp.local_prosody_predictor, nb_blocks=2)
+    sd_o = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    in64 = tuple(t.double() if t.is_floating_point() else t for t in inputs)
+    ref = oracle.forward(sd_o, ohp, in64)
+    tot_o, _ = oracle.loss(ohp, ref, targets_of(in64), 1500)
+    tot_o.backward()
+    tol = {'fp32': 1e-4, 'bf16x3': 1e-3}[backend]
+    for got, want in zip(out[2][:3], ref[2][:3]):
+        assert scale_rel_err(got.detach(), want.detach()) < tol
+    assert scale_rel_err(out[3][0].detach(), ref[3][0].detach()) < tol
+    assert abs(total.item() - tot_o.item()) < 1e-4 * abs(tot_o.item())
+    bad = [(n, scale_rel_err(p.grad, sd_o[n].grad)) for n, p in model.named_parameters() if not scale_rel_err(p.grad, sd_o[n].grad) < 1e-2]
+    assert not bad, bad[:8]

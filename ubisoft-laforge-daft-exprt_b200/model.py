@@ -196,19 +196,18 @@ class LocalProsodyPredictor(nn.Module):  # model.py:512-575
         D = hp.phoneme_encoder['hidden_embed_dim']
         cfg = hp.local_prosody_predictor
         C, k = cfg['conv_channels'], cfg['conv_kernel']
-        if cfg['nb_blocks'] != 1:
-            raise NotImplementedError('local_prosody_predictor.nb_blocks != 1 is not supported by the fused predictor kernel chain')
         self.p = cfg['conv_dropout']
-        self.blocks = nn.ModuleList([_Slots(_0=_Conv(D, C, k, 'relu'), _2=nn.LayerNorm(C),
-                                            _4=_Conv(C, C, k, 'relu'), _6=nn.LayerNorm(C))])
+        self.blocks = nn.ModuleList([_Slots(_0=_Conv(D if i == 0 else C, C, k, 'relu'), _2=nn.LayerNorm(C),
+                                            _4=_Conv(C, C, k, 'relu'), _6=nn.LayerNorm(C)) for i in range(cfg['nb_blocks'])])
         self.projection = _Lin(C, 3, 'linear')
 
     def forward(self, x, films, input_lengths):
-        b = self.blocks[0]
-        out = ops.Predictor.apply(x, input_lengths, films[0], b[0].conv.weight, b[0].conv.bias, b[2].weight, b[2].bias,
-                                  b[4].conv.weight, b[4].conv.bias, b[6].weight, b[6].bias,
-                                  self.projection.linear_layer.weight, self.projection.linear_layer.bias,
-                                  self.p if self.training else 0.0)
+        p = self.p if self.training else 0.0
+        for i, b in enumerate(self.blocks):
+            last = i == len(self.blocks) - 1   # the reference masks once, after the last block's FiLM (model.py:567-568)
+            x = ops.PredictorBlock.apply(x, input_lengths if last else None, films[i], b[0].conv.weight, b[0].conv.bias, b[2].weight,
+                                         b[2].bias, b[4].conv.weight, b[4].conv.bias, b[6].weight, b[6].bias, p)
+        out = ops.PredictorHead.apply(x, input_lengths, self.projection.linear_layer.weight, self.projection.linear_layer.bias)
         return out[0], out[1], out[2]
 
 

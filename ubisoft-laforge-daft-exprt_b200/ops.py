@@ -11,7 +11,7 @@ the fusions live below the ABI:
   FilmHead            gammas/betas predictors + post-multipliers          model.py:427-461
   Linear              LinearNorm (+ReLU), gradient reversal folded in     model.py:27-38, :276-283
   EmbedPE             symbols embedding + PE + mask                       model.py:497-504
-  Predictor           LocalProsodyPredictor.forward                       model.py:549-575
+  PredictorBlock/Head LocalProsodyPredictor.forward (any nb_blocks)       model.py:549-575
   GaussUpsample       GaussianUpsamplingModule.forward                    model.py:608-662
   MelProjection       Linear(128->80) + mask + transpose                  model.py:706-708
   Loss                DaftExprtLoss.forward                               loss.py:30-106
@@ -732,12 +732,12 @@ class EmbedPE(torch.autograd.Function):
         return None, None, demb, None
 
 
-class Predictor(torch.autograd.Function):
-    """conv(128->256,k3)+ReLU -> LN -> drop -> conv(256->256,k3)+ReLU -> LN -> drop -> FiLM -> mask -> Linear(256->3) -> mask.
-    Returns preds [3, B, L] (duration, energy, pitch planes)."""
+class PredictorBlock(torch.autograd.Function):
+    """One block of LocalProsodyPredictor (model.py:526-543,559-566): conv(k3)+ReLU -> LN -> drop -> conv(k3)+ReLU -> LN -> drop -> FiLM,
+    followed by the padding mask when `lens` is given (the reference masks once, after the LAST block, model.py:567-568)."""
 
     @staticmethod
-    def forward(ctx, x, lens, film, w0, b0, g0, e0, w1, b1, g1, e1, pw, pb, p_drop):
+    def forward(ctx, x, lens, film, w0, b0, g0, e0, w1, b1, g1, e1, p_drop):
         x = _check_input(x)
         B, L, D = x.shape
         C = w0.shape[0]
@@ -750,24 +750,17 @@ class Predictor(torch.autograd.Function):
         y0, xh0, rs0 = ln_fwd(a0, None, g0, e0, None, 0, None, B, L, C, p_out=p_drop, seed_out=s0)
         a1 = conv_gemm(y0, w1p, b1, B, L, relu=True)
         y1, xh1, rs1 = ln_fwd(a1, None, g1, e1, film, 2 * C, lens, B, L, C, p_out=p_drop, seed_out=s1)
-        NO = pw.shape[0]
-        out = torch.empty(NO, B, L, device=x.device, dtype=torch.float32)
-        _call('dx_narrow_linear_fwd', _p(y1), _p(pw), _p(pb), _p(lens), _p(out), B, L, C, NO, _st())
-        ctx.save_for_backward(x, lens, film, a0, y0, xh0, rs0, a1, y1, xh1, rs1, g0, e0, g1, e1, pw)
+        ctx.save_for_backward(x, lens, film, a0, y0, xh0, rs0, a1, xh1, rs1, g0, e0, g1, e1)
         hold_packs(ctx, w0d, w1d)
-        ctx.cfg = (B, L, D, C, NO, float(p_drop), s0, s1, w0.shape, w1.shape)
-        return out
+        ctx.cfg = (B, L, D, C, float(p_drop), s0, s1, w0.shape, w1.shape)
+        return y1
 
     @staticmethod
-    def backward(ctx, dout):
-        x, lens, film, a0, y0, xh0, rs0, a1, y1, xh1, rs1, g0, e0, g1, e1, pw = ctx.saved_tensors
+    def backward(ctx, dy1):
+        x, lens, film, a0, y0, xh0, rs0, a1, xh1, rs1, g0, e0, g1, e1 = ctx.saved_tensors
         w0d, w1d = held_packs(ctx)
-        B, L, D, C, NO, p, s0, s1, w0s, w1s = ctx.cfg
-        dout = _check_input(dout)
-        dy1 = torch.empty(B, L, C, device=dout.device, dtype=torch.float32)
-        dpw = torch.empty(NO, C, device=dout.device, dtype=torch.float32)
-        dpb = torch.empty(NO, device=dout.device, dtype=torch.float32)
-        _call('dx_narrow_linear_bwd', _p(dout), _p(y1), _p(pw), _p(lens), _p(dy1), _p(dpw), _p(dpb), B, L, C, NO, _st())
+        B, L, D, C, p, s0, s1, w0s, w1s = ctx.cfg
+        dy1 = _check_input(dy1)
         dpre1, _, dg1, de1, dfilm = ln_bwd(dy1, xh1, rs1, g1, e1, film, 2 * C, lens, B, L, C, relu_src=a1, p_out=p,
                                            seed_out=s1, want_film=True)
         dy0 = conv_gemm(dpre1, w1d, None, B, L)
@@ -775,7 +768,33 @@ class Predictor(torch.autograd.Function):
         dpre0, _, dg0, de0, _ = ln_bwd(dy0, xh0, rs0, g0, e0, None, 0, None, B, L, C, relu_src=a0, p_out=p, seed_out=s0)
         dx = conv_gemm(dpre0, w0d, None, B, L)
         dw0, db0 = conv_wgrad(x, dpre0, B, L, D, C, w0s[2], w0s)
-        return dx, None, dfilm, dw0, db0, dg0, de0, dw1, db1, dg1, de1, dpw, dpb, None
+        return dx, None, dfilm, dw0, db0, dg0, de0, dw1, db1, dg1, de1, None
+
+
+class PredictorHead(torch.autograd.Function):
+    """Linear(C -> 3) + mask (model.py:569-575) on the masked block output.  Returns preds [3, B, L] (duration, energy, pitch planes)."""
+
+    @staticmethod
+    def forward(ctx, y, lens, pw, pb):
+        y = _check_input(y)
+        B, L, C = y.shape
+        NO = pw.shape[0]
+        out = torch.empty(NO, B, L, device=y.device, dtype=torch.float32)
+        _call('dx_narrow_linear_fwd', _p(y), _p(pw), _p(pb), _p(lens), _p(out), B, L, C, NO, _st())
+        ctx.save_for_backward(y, lens, pw)
+        ctx.cfg = (B, L, C, NO)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, lens, pw = ctx.saved_tensors
+        B, L, C, NO = ctx.cfg
+        dout = _check_input(dout)
+        dy = torch.empty(B, L, C, device=dout.device, dtype=torch.float32)
+        dpw = torch.empty(NO, C, device=dout.device, dtype=torch.float32)
+        dpb = torch.empty(NO, device=dout.device, dtype=torch.float32)
+        _call('dx_narrow_linear_bwd', _p(dout), _p(y), _p(pw), _p(lens), _p(dy), _p(dpw), _p(dpb), B, L, C, NO, _st())
+        return dy, None, dpw, dpb
 
 
 class GaussUpsample(torch.autograd.Function):
