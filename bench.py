@@ -48,7 +48,7 @@ CONFIGS = {
                              'mel T<=1000, pitch_transform=add, eval mode; frames = GENERATED mel frames'),
 }
 # e2e: (L_max, T_max) of the host batches cycled through the public API, as fractions of the config maxima
-E2E_SHAPES = ((1.0, 1.0), (0.96, 0.96), (0.92, 0.9), (0.88, 1.0), (1.0, 0.88), (0.84, 0.84))
+E2E_SHAPES = ((1.0, 1.0), (0.96, 0.97), (0.94, 0.93), (1.0, 0.89), (0.95, 0.88), (0.98, 0.99))
 
 
 def host_threads():
@@ -133,10 +133,10 @@ def e2e_host_batches(cfg, rank):
     col = BucketedCollate(None, l_step=64, t_step=128, l_max=cfg['L'], t_max=cfg['T'])
     out = []
     # the stress config keeps ~26 GB of captured activations per bucket shape: two shapes there, four in the headline config
-    shapes = E2E_SHAPES if cfg['B'] * cfg['T'] <= 64000 else (E2E_SHAPES[0], E2E_SHAPES[5])
+    shapes = E2E_SHAPES if cfg['B'] * cfg['T'] <= 64000 else (E2E_SHAPES[0], E2E_SHAPES[4])
     for k, (fl, ft) in enumerate(shapes):
         L, T = max(8, int(round(cfg['L'] * fl))), max(16, int(round(cfg['T'] * ft)))
-        fb = col(with_ids(rank_batch(cfg, rank, L, T, seed=k)))
+        fb = col(with_ids(rank_batch(cfg, rank, L, T, seed=0)))   # same length profile as the fixed-shape batch, scaled to (L, T)
         out.append((fb.pin_memory() if torch.cuda.is_available() else fb, (L, T)))
     return out
 
