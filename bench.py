@@ -418,7 +418,7 @@ def main():
     from daft_exprt_b200.ddp import FlatAdam, FlatGradSync, broadcast_parameters
     from daft_exprt_b200.graph import GraphedTrainStep
     from daft_exprt_b200.hparams import default_hparams
-    from daft_exprt_b200.loss import DaftExprtLoss
+    from daft_exprt_b200.loss import DaftExprtLoss, LossReadback
     from daft_exprt_b200.model import DaftExprt
 
     assert torch.cuda.is_available(), 'bench.py (impl=ours) needs a CUDA device: there is no CPU fallback'
@@ -468,6 +468,7 @@ def main():
         return eager_step(inputs, targets, it)
 
     prefetch = BatchPrefetcher(model, local_rank)   # the package's loader-side helper: parse_batch one step ahead on a side stream
+    readback = LossReadback()                       # loss floats of step i collected while step i + 1 is in flight
     e2e_frames = [0]
 
     def make_e2e(batches):
@@ -482,7 +483,7 @@ def main():
             if graphed is not None:
                 out = graphed.step(inp, tgt, it)                          # replay enqueued first ...
                 prefetch.submit(batches[(it + 1) % len(batches)])         # ... then the next step's copy, while the GPU is busy
-                return out.tolist()                                       # ONE D2H read of the 8 loss floats
+                return readback.submit(out)                               # ONE D2H copy of the 8 loss floats per step (values: one step late)
             prefetch.submit(batches[(it + 1) % len(batches)])
             return eager_step(inp, tgt, it, read_back=True)
         return step_e2e
@@ -500,6 +501,7 @@ def main():
         e0.record()
         for i in range(steps):
             fn(first_it + warmup + i)
+        readback.flush()   # the loss of the last e2e step is read inside the timed region too
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -562,8 +564,9 @@ def main():
                 'ms_per_step': ms_e2e, 'valid_frames_per_step': frames_var.item() / steps_var,
                 'shapes': [list(s) for _, s in varied], 'bucket_shapes': sorted({(fb.key()[0][1], fb.key()[8][2]) for fb, _ in varied}),
                 'graph_hits': hits, 'graph_misses': misses, 'graph_hit_rate': hits / max(1, hits + misses),
-                'note': 'every step takes a different pinned host batch (6 batches, bucket-padded FlatBatch, one H2D each) + loss read-back; '
-                        'graph_hit_rate covers warm-up (captures) + timed steps',
+                'note': 'every step takes a different pinned host batch (6 batches, bucket-padded FlatBatch, one H2D each) + one D2H copy of its 8 loss '
+                        'floats (loss.LossReadback: values collected one step late, the last one before the clock stops); graph_hit_rate covers '
+                        'warm-up (captures) + timed steps',
                 'fixed_shape': {'value': total_frames / (ms_e2e_fixed * 1e-3), 'ms_per_step': ms_e2e_fixed,
                                 'h2d_bytes_per_step': sum(t.numel() * t.element_size() for t in host_batch[:11])},
                 'eager_no_graph_ms_per_step': ms_eager},

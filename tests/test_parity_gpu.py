@@ -1164,3 +1164,14 @@ def test_two_predictor_blocks_match_oracle(dev, backend):
     assert abs(total.item() - tot_o.item()) < 1e-4 * abs(tot_o.item())
     bad = [(n, scale_rel_err(p.grad, sd_o[n].grad)) for n, p in model.named_parameters() if not scale_rel_err(p.grad, sd_o[n].grad) < 1e-2]
     assert not bad, bad[:8]
+
+
+def test_loss_readback_is_one_step_late_and_exact(dev):
+    from daft_exprt_b200.loss import LossReadback
+    rb = LossReadback(slots=2)
+    vals = [torch.arange(8, dtype=torch.float32, device=dev) * (k + 1) for k in range(5)]
+    got = [rb.submit(v) for v in vals]
+    assert got[0] is None
+    for k in range(1, 5):
+        assert got[k] == vals[k - 1].tolist()
+    assert rb.flush() == [vals[4].tolist()] and rb.flush() == []

@@ -49,3 +49,37 @@ class DaftExprtLoss(nn.Module):
         vals = out.detach().tolist()   # the single device->host read of the step
         individual_loss = {k: vals[i] for i, k in enumerate(TERMS)}
         return out[7], individual_loss
+
+
+class LossReadback:
+    """One-step-delayed read-back of the 8 loss floats: the device->host copy of step i is enqueued right behind step i (pinned
+    ring slot, async) and its VALUES are collected when step i + 1 is submitted, so the host never stalls on the step it has just
+    launched (the reference blocks on 8 `.item()` calls per micro-batch, loss.py:102-104, train.py:382).  `flush()` returns what is
+    still in flight (call it before reading the clock / at the end of an epoch)."""
+
+    def __init__(self, slots=4):
+        self.host = torch.zeros(slots, 8, dtype=torch.float32).pin_memory()
+        self.pending = []          # (slot, event)
+        self.k = 0
+
+    def submit(self, out8):
+        """Enqueue the copy of this step's loss tensor; returns the floats of the PREVIOUS submitted step (None for the first)."""
+        slot = self.k % self.host.shape[0]
+        self.k += 1
+        self.host[slot].copy_(out8.detach(), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        prev = self._collect() if self.pending else None
+        self.pending.append((slot, ev))
+        return prev
+
+    def _collect(self):
+        slot, ev = self.pending.pop(0)
+        ev.synchronize()
+        return self.host[slot].tolist()
+
+    def flush(self):
+        out = []
+        while self.pending:
+            out.append(self._collect())
+        return out
