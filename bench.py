@@ -197,7 +197,7 @@ def cpu_baseline_subprocess(config_name):
     """The cpu_baseline leg of the `ours` arm: the reference arm itself in a FRESH process (clean OpenMP state: torchrun exports
     OMP_NUM_THREADS=1 and this process has long initialised its thread pools), all host threads."""
     env = {k: v for k, v in os.environ.items() if k not in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'RANK', 'WORLD_SIZE', 'LOCAL_RANK')}
-    out = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--config', config_name, '--steps', '1', '--warmup', '0'],
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--config', config_name, '--steps', '2', '--warmup', '1'],
                          capture_output=True, text=True, env=env, timeout=900)
     try:
         return json.loads(out.stdout.strip().splitlines()[-1])['cpu_baseline']

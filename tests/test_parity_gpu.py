@@ -1140,7 +1140,7 @@ def test_two_predictor_blocks_match_oracle(dev, backend):
     hp = default_hparams(n_speakers=n_ids + 1)
     hp.local_prosody_predictor['nb_blocks'] = 2
     model = DaftExprt(hp)
-    sd = synthetic.synthetic_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, 77)
+    sd = synthetic.synthetic_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, 1234)   # same weight seed as the other tests
     assert len(sd) == 201 and 'prosody_predictor.blocks.1.4.conv.weight' in sd
     model.load_state_dict(sd)
     model = model.to(dev).eval()
@@ -1162,6 +1162,8 @@ def test_two_predictor_blocks_match_oracle(dev, backend):
         assert scale_rel_err(got.detach(), want.detach()) < tol
     assert scale_rel_err(out[3][0].detach(), ref[3][0].detach()) < tol
     assert abs(total.item() - tot_o.item()) < 1e-4 * abs(tot_o.item())
+    # element-wise 1e-2 (the bound of test_all_gradients_match_oracle_autograd); the phoneme-side gradients inherit the conditioning
+    # of the Gaussian-upsampling path (~1e3, see the golden test): measured 7e-3 worst on bf16x3, 3e-4 on fp32
     bad = [(n, scale_rel_err(p.grad, sd_o[n].grad)) for n, p in model.named_parameters() if not scale_rel_err(p.grad, sd_o[n].grad) < 1e-2]
     assert not bad, bad[:8]
 
