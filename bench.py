@@ -394,6 +394,7 @@ def main():
     ap.add_argument('--no-eager-baseline', action='store_true', help='skip the PyTorch-eager-on-GPU baseline leg')
     ap.add_argument('--eval', action='store_true', help='eval mode (dropout off)')
     ap.add_argument('--profile-step', action='store_true', help='bracket ONE extra step with cudaProfilerStart/Stop (for ncu --profile-from-start off)')
+    ap.add_argument('--nccl-allreduce', action='store_true', help='N > 1: NCCL all-reduce + Adam instead of the fused reduce-scatter + Adam + all-gather kernel')
     ap.add_argument('--no-graph', action='store_true', help='issue the launches of a step eagerly instead of replaying the captured CUDA graph')
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
@@ -415,7 +416,7 @@ def main():
         entry.build()
     from daft_exprt_b200 import cabi, ops
     from daft_exprt_b200.data import BatchPrefetcher
-    from daft_exprt_b200.ddp import FlatAdam, FlatGradSync, broadcast_parameters
+    from daft_exprt_b200.ddp import FlatAdam, FlatGradSync, FusedShardedAdam, broadcast_parameters
     from daft_exprt_b200.graph import GraphedTrainStep
     from daft_exprt_b200.hparams import default_hparams
     from daft_exprt_b200.loss import DaftExprtLoss, LossReadback
@@ -445,6 +446,25 @@ def main():
     sync = FlatGradSync(params, mode='gather')
     opt = FlatAdam(params, sync, lr=hp.initial_learning_rate, betas=hp.betas, eps=hp.epsilon, weight_decay=hp.weight_decay)
 
+    # N > 1: the gradient exchange fused with the optimiser over NVLink peer memory (symmetric memory; NVSwitch multicast when mapped);
+    # falls back to NCCL all-reduce + Adam when symmetric memory cannot be set up on this system (every rank takes the same branch)
+    fused, exchange = None, 'none (one GPU)'
+    if world > 1:
+        exchange = 'NCCL all-reduce of the flat bucket + fused Adam'
+        if not args.nccl_allreduce:
+            ok = torch.ones(1, device=dev)
+            try:
+                fused = FusedShardedAdam(sync, opt)
+            except Exception as e:   # noqa: BLE001
+                ok.zero_()
+                if rank == 0:
+                    print(f'[bench] fused gradient exchange unavailable ({type(e).__name__}: {str(e)[:200]}); using NCCL all-reduce', file=sys.stderr)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                fused = None
+            else:
+                exchange = f'fused reduce-scatter + Adam + all-gather kernel over symmetric memory: {fused.mode}'
+
     host_batch = with_ids(tuple(t.pin_memory() for t in rank_batch(cfg, rank)))
     frames_rank = int(host_batch[9].sum())
     inputs, targets, _ = model.parse_batch(local_rank, host_batch)
@@ -452,14 +472,17 @@ def main():
     torch.cuda.synchronize()
     torch.cuda.reset_peak_memory_stats()
 
-    graphed = None if args.no_graph else GraphedTrainStep(model, crit, sync, opt)
+    graphed = None if args.no_graph else GraphedTrainStep(model, crit, sync, opt, fused_exchange=fused)
 
     def eager_step(inp, tgt, it, read_back=False):
         opt.zero_grad()
         out = crit.forward_device(model(inp), tgt, it)
         out[7].backward()
-        sync.all_reduce_mean()
-        opt.step()
+        if fused is not None:
+            fused.step()
+        else:
+            sync.all_reduce_mean()
+            opt.step()
         return out.tolist() if read_back else out
 
     def step_resident(it):
@@ -555,7 +578,7 @@ def main():
                   'tf32': 'tf32', 'fp32': 'f32'}[args.backend],
         'data': 'synthetic',
         'config': {'workload': workload, 'global_batch': cfg['B'] * world, 'valid_frames_per_step': total_frames,
-                   'padded_frames_per_step': cfg['B'] * world * cfg['T'], 'parallelism': f'dp{world}',
+                   'padded_frames_per_step': cfg['B'] * world * cfg['T'], 'parallelism': f'dp{world}', 'grad_exchange': exchange,
                    'per_rank_batches': 'same lengths on every rank (equal valid-frame totals), per-rank content',
                    'launch': 'eager' if graphed is None else 'cuda-graph replay (graph.py); gpu_launches = kernels of libdaftexprt_b200.so executed by the replays',
                    'l2': 'per-step working set (several GB of activations) >> 126 MB L2; no explicit flush needed',

@@ -281,6 +281,17 @@ size_t dx_step_state_bytes(void);
 /* clip (nullable): the device buffer dx_grad_norm_clip filled; its coefficient out[1] multiplies grad_scale (train.py:399). */
 int dx_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
                  float weight_decay, int step, float grad_scale, const float* clip, void* stream);
+/* Multi-GPU: gradient exchange FUSED with the optimiser over NVLink / NVSwitch peer memory — replaces DDP's all-reduce + optimizer.step()
+ * (train.py:293,391,401) by one kernel per rank: reduce-scatter of this rank's shard of the flat gradient (sum over `world` ranks; ONE
+ * multimem.ld_reduce per 16 bytes when grad_multicast != NULL: the NVSwitch adds the copies), Adam on the shard (m, v are only touched
+ * inside the shard), all-gather of the updated parameters into every rank's buffer (multimem.st, or `world` peer stores).
+ * The flat gradient and parameter buffers must be symmetric-memory allocations mapped on every rank (torch.distributed._symmetric_memory):
+ * *_multicast = their multicast addresses (NULL: use the HOST arrays *_peer_ptrs of `world` per-rank device addresses).  shard_begin /
+ * shard_n in elements, multiples of 4.  grad_scale = 1 / world for the mean.  The caller issues a cross-GPU barrier on the stream before
+ * (every rank's gradients written) and after (every rank's parameters visible) the call.  Honours dx_set_step_state like dx_adam_step. */
+int dx_fused_reduce_adam(const void* grad_multicast, const uint64_t* grad_peer_ptrs, void* param_multicast, const uint64_t* param_peer_ptrs,
+                         const float* param_local, float* m, float* v, size_t shard_begin, size_t shard_n, int world, float lr, float beta1,
+                         float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 /* torch.nn.utils.clip_grad_norm_(parameters, max_norm) (train.py:399) over the flat gradient buffer, without a host sync:
  * out[0] = || grad_scale * g ||_2 (what the reference logs as grad_norm), out[1] = min(1, max_norm / (out[0] + 1e-6)),
  * out[2] = scratch.  max_norm = INFINITY only measures the norm.  out: 3 floats of device memory. */

@@ -458,6 +458,13 @@ int dx_adam_step(float* p, const float* g, float* m, float* v, size_t n, float l
                  float weight_decay, int step, float grad_scale, const float* clip, void* stream) {
     return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, g_step_state, clip, ST(stream));
 }
+int dx_fused_reduce_adam(const void* grad_multicast, const uint64_t* grad_peer_ptrs, void* param_multicast, const uint64_t* param_peer_ptrs,
+                         const float* param_local, float* m, float* v, size_t shard_begin, size_t shard_n, int world, float lr, float beta1,
+                         float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
+    return fused_reduce_adam((const float*)grad_multicast, (const unsigned long long*)grad_peer_ptrs, (float*)param_multicast,
+                             (const unsigned long long*)param_peer_ptrs, param_local, m, v, shard_begin, shard_n, world, lr, beta1, beta2, eps,
+                             weight_decay, step, grad_scale, g_step_state, ST(stream));
+}
 int dx_grad_norm_clip(const float* g, size_t n, float grad_scale, float max_norm, float* out, void* stream) {
     return grad_norm_clip(g, n, grad_scale, max_norm, out, ST(stream));
 }

@@ -277,6 +277,13 @@ int pitch_multiply(float* pitch, const float* factors, int B, int L, cudaStream_
 // fused Adam step over a flat parameter buffer (optim.cu): torch.optim.Adam semantics (L2 weight decay added to grad)
 int adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
               float weight_decay, int step, float grad_scale, const StepState* dyn, const float* clip, cudaStream_t st);
+// reduce-scatter (sum over ranks) + Adam on this rank's shard + all-gather of the updated parameters, one kernel over symmetric
+// memory: g_mc / p_mc = NVSwitch multicast addresses of the flat gradient / parameter buffers (or nullptr), g_peers / p_peers = HOST
+// arrays of the `world` per-rank device addresses of the same buffers (used when there is no multicast mapping), p_local / m / v =
+// this rank's own buffers; the shard is elements [begin, begin + n) of the flat layout
+int fused_reduce_adam(const float* g_mc, const unsigned long long* g_peers, float* p_mc, const unsigned long long* p_peers, const float* p_local,
+                      float* m, float* v, size_t begin, size_t n, int world, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      int step, float grad_scale, const StepState* dyn, cudaStream_t st);
 // clip_grad_norm_ on the device: out[3] = {norm of grad_scale * g, clip coefficient, scratch}; `clip` above = this buffer
 int grad_norm_clip(const float* g, size_t n, float grad_scale, float max_norm, float* out, cudaStream_t st);
 

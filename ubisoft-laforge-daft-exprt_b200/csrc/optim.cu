@@ -71,4 +71,90 @@ int grad_norm_clip(const float* g, size_t n, float grad_scale, float max_norm, f
     return check_launch("grad_clip_finalize");
 }
 
+
+// ---- fused gradient exchange + optimiser over NVLink peer memory -------------------------------------------------------------------
+// Replaces `NCCL all-reduce of the flat gradient bucket -> Adam over the whole bucket` (reference: DDP all-reduce + torch.optim.Adam,
+// train.py:293,391,401) by ONE kernel per rank over symmetric memory (every rank's flat gradient / parameter buffers mapped into every
+// other rank's address space, torch.distributed._symmetric_memory):
+//     reduce-scatter : this rank sums ITS shard [begin, begin + n) of the gradient over all ranks — one `multimem.ld_reduce` per 16 bytes
+//                      when the buffers have an NVSwitch multicast mapping (the switch adds the N copies), else N peer loads;
+//     Adam           : on the shard only (moments exist per shard: ZeRO-1 style);
+//     all-gather     : the updated parameters are written to every rank — one `multimem.st` per 16 bytes, else N peer stores.
+// NVLink traffic per rank = shard in + shard out (x N without multicast), no intermediate buffers, no second launch.
+// The caller brackets the launch with cross-GPU barriers (all gradients written before / all parameters visible after).
+__device__ __forceinline__ float4 ld_peer(const float* p) {   // remote HBM: system-scope, never from a stale L1 line
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_peer(float* p, float4 v) {
+    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 mc_ld_reduce(const float* p) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st(float* p, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+struct PeerPtrs { unsigned long long p[16]; };
+
+__global__ void __launch_bounds__(256) fused_reduce_adam_kernel(const float* g_mc, PeerPtrs g_peers, float* p_mc, PeerPtrs p_peers,
+                                                                const float* p_local, float* m, float* v, size_t begin4, size_t n4, int world,
+                                                                float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                                                                float grad_scale, const StepState* dyn) {
+    if (dyn) { lr = dyn->lr; bc1 = dyn->bc1; bc2_sqrt = dyn->bc2_sqrt; }
+    const float step = lr / bc1;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = (begin4 + i) * 4;
+        float4 g;
+        if (g_mc) {
+            g = mc_ld_reduce(g_mc + e);
+        } else {
+            g = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < world; ++r) {
+                const float4 t = ld_peer(reinterpret_cast<const float*>(g_peers.p[r]) + e);
+                g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+            }
+        }
+        const float4 pv = *reinterpret_cast<const float4*>(p_local + e);
+        float4 mv = *reinterpret_cast<const float4*>(m + e), vv = *reinterpret_cast<const float4*>(v + e);
+        float pa[4] = {pv.x, pv.y, pv.z, pv.w}, ga[4] = {g.x, g.y, g.z, g.w}, ma[4] = {mv.x, mv.y, mv.z, mv.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gi = ga[k] * grad_scale + wd * pa[k];
+            ma[k] = b1 * ma[k] + (1.f - b1) * gi;
+            va[k] = b2 * va[k] + (1.f - b2) * gi * gi;
+            pa[k] = pa[k] - step * (ma[k] / (sqrtf(va[k]) / bc2_sqrt + eps));
+        }
+        *reinterpret_cast<float4*>(m + e) = make_float4(ma[0], ma[1], ma[2], ma[3]);
+        *reinterpret_cast<float4*>(v + e) = make_float4(va[0], va[1], va[2], va[3]);
+        const float4 pn = make_float4(pa[0], pa[1], pa[2], pa[3]);
+        if (p_mc) {
+            mc_st(p_mc + e, pn);
+        } else {
+            for (int r = 0; r < world; ++r) st_peer(reinterpret_cast<float*>(p_peers.p[r]) + e, pn);
+        }
+    }
+}
+
+int fused_reduce_adam(const float* g_mc, const unsigned long long* g_peers, float* p_mc, const unsigned long long* p_peers, const float* p_local,
+                      float* m, float* v, size_t begin, size_t n, int world, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      int step, float grad_scale, const StepState* dyn, cudaStream_t st) {
+    DX_REQUIRE(step >= 1 && world >= 1 && world <= 16, "fused_reduce_adam: step %d world %d (1..16 ranks)", step, world);
+    DX_REQUIRE(begin % 4 == 0 && n % 4 == 0, "fused_reduce_adam: the shard must start and end on 16-byte boundaries (begin %zu n %zu)", begin, n);
+    DX_REQUIRE((g_mc || g_peers) && (p_mc || p_peers) && p_local && m && v, "fused_reduce_adam: missing buffers");
+    PeerPtrs gp = {}, pp = {};
+    for (int r = 0; r < world; ++r) { gp.p[r] = g_peers ? g_peers[r] : 0ull; pp.p[r] = p_peers ? p_peers[r] : 0ull; }
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+    if (n == 0) return DX_OK;
+    fused_reduce_adam_kernel<<<grid_1d(n / 4, 256, 148 * 8), 256, 0, st>>>(g_mc, gp, p_mc, pp, p_local, m, v, begin / 4, n / 4, world, lr, beta1, beta2,
+                                                                         eps, weight_decay, bc1, bc2_sqrt, grad_scale, dyn);
+    return check_launch("fused_reduce_adam");
+}
+
 }  // namespace dx

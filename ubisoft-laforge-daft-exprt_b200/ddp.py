@@ -44,6 +44,16 @@ class FlatGradSync:
             for p, v in zip(self.params, self.views):
                 p.grad = v   # autograd accumulates in place into existing .grad
 
+    def rebind(self, new_flat):
+        """Move the bucket into another allocation of the same size (e.g. a symmetric-memory buffer mapped on every rank)."""
+        assert new_flat.numel() == self.padded_numel and new_flat.dtype == self.flat.dtype
+        new_flat.copy_(self.flat)
+        self.flat = new_flat
+        self.views = [self.flat[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
+        if self.mode == 'alias':
+            for p, v in zip(self.params, self.views):
+                p.grad = v
+
     def zero_grad(self):
         if self.mode == 'alias':
             self.flat.zero_()
@@ -146,6 +156,17 @@ class FlatAdam:
     weight_decay = property(lambda self: self.param_groups[0]['weight_decay'],
                             lambda self, v: self.param_groups[0].__setitem__('weight_decay', v))
 
+    def rebind(self, new_flat_p):
+        """Move the flat parameter buffer (and every `p.data` view of it) into another allocation of the same size."""
+        assert new_flat_p.numel() == self.flat_p.numel()
+        with torch.no_grad():
+            new_flat_p.copy_(self.flat_p)
+            self.flat_p = new_flat_p
+            for p, off in zip(self.params, self.sync.offsets):
+                p.data = self.flat_p[off:off + p.numel()].view_as(p)
+        from . import ops
+        ops.invalidate_packed_weights()
+
     def wants_clip(self):
         return self.track_grad_norm or self.grad_clip_thresh != float('inf')
 
@@ -208,3 +229,73 @@ class FlatAdam:
         if len(steps) > 1:
             raise ValueError('FlatAdam.load_state_dict: parameters with different step counts are not supported')
         self.step_count = steps.pop() if steps else 0
+
+
+class FusedShardedAdam:
+    """Gradient exchange fused with the optimiser over NVLink / NVSwitch peer memory (multi-GPU, one process per GPU).
+
+    Replaces `all-reduce of the flat bucket -> Adam over the whole bucket` (the reference: DDP all-reduce + torch.optim.Adam,
+    train.py:293,391,401) by ONE kernel per rank (`dx_fused_reduce_adam`): reduce-scatter of this rank's shard of the gradient
+    (`multimem.ld_reduce`: the NVSwitch adds the N copies; peer loads when the buffers have no multicast mapping), Adam on the shard,
+    all-gather of the updated parameters (`multimem.st` / peer stores), bracketed by two device-side cross-GPU barriers.  The flat
+    gradient and parameter buffers move into symmetric memory (`torch.distributed._symmetric_memory`); the Adam moments are only
+    maintained for the own shard (ZeRO-1 style; `full_moments()` reassembles them for a checkpoint).
+
+    Construction is a COLLECTIVE (every rank must call it); it raises if symmetric memory cannot be set up on this system — callers
+    keep the NCCL all-reduce path then (`bench.py` does).  Gradient clipping needs the global norm and is not supported here."""
+
+    def __init__(self, sync: FlatGradSync, opt: 'FlatAdam', group=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        assert dist.is_available() and dist.is_initialized(), 'FusedShardedAdam needs an initialised process group'
+        assert not opt.wants_clip(), 'FusedShardedAdam: clip_grad_norm_ needs the global gradient norm (use the all-reduce path)'
+        self.sync, self.opt = sync, opt
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        assert self.world <= 16
+        dev, P = sync.flat.device, sync.padded_numel
+        g = symm.empty(P, dtype=torch.float32, device=dev)
+        p = symm.empty(P, dtype=torch.float32, device=dev)
+        self.hg = symm.rendezvous(g, self.group)
+        self.hp = symm.rendezvous(p, self.group)
+        sync.rebind(g)
+        opt.rebind(p)
+        shard = (P + self.world - 1) // self.world
+        shard = (shard + ALIGN - 1) // ALIGN * ALIGN
+        self.begin = min(self.rank * shard, P)
+        self.n = min(shard, P - self.begin)
+        self.g_mc = int(getattr(self.hg, 'multicast_ptr', 0) or 0)
+        self.p_mc = int(getattr(self.hp, 'multicast_ptr', 0) or 0)
+        if not (self.g_mc and self.p_mc):
+            self.g_mc = self.p_mc = 0
+        self.g_peers = (ctypes.c_uint64 * self.world)(*[int(x) for x in self.hg.buffer_ptrs])
+        self.p_peers = (ctypes.c_uint64 * self.world)(*[int(x) for x in self.hp.buffer_ptrs])
+        self.mode = 'multimem (in-switch reduction)' if self.g_mc else 'peer loads / stores'
+        torch.cuda.synchronize()
+        dist.barrier(self.group)
+
+    def launch(self, step):
+        """barrier -> reduce-scatter + Adam + all-gather -> barrier, all on the current stream; `step` = optimiser step number
+        (ignored while a per-step device block is registered: lr and the bias corrections come from it)."""
+        import ctypes
+        from . import ops
+        opt = self.opt
+        self.hg.barrier(channel=0)          # every rank has finished writing its gradients
+        ops._call('dx_fused_reduce_adam', self.g_mc or None, ctypes.addressof(self.g_peers), self.p_mc or None, ctypes.addressof(self.p_peers),
+                  opt.flat_p.data_ptr(), opt.m.data_ptr(), opt.v.data_ptr(), self.begin, self.n, self.world, float(opt.lr),
+                  float(opt.betas[0]), float(opt.betas[1]), float(opt.eps), float(opt.weight_decay), int(step), 1.0 / self.world, ops._st())
+        self.hp.barrier(channel=1)          # every rank's parameter shard has landed everywhere
+
+    def step(self):
+        from . import ops
+        self.sync.gather()
+        self.opt.step_count += 1
+        self.launch(self.opt.step_count)
+        ops.invalidate_packed_weights()
+
+    def full_moments(self):
+        """(exp_avg, exp_avg_sq) over the whole flat layout: every rank holds its own shard only (the rest is zero) -> sum over ranks."""
+        m, v = self.opt.m.clone(), self.opt.v.clone()
+        dist.all_reduce(m, group=self.group)
+        dist.all_reduce(v, group=self.group)
+        return m, v

@@ -92,7 +92,7 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model, criterion, sync, opt, lr_schedule=None, seed=None, max_graphs=8, warmup=2, accumulation_steps=1,
-                 hparams=None):
+                 hparams=None, fused_exchange=None):
         self.model, self.criterion, self.sync, self.opt = model, criterion, sync, opt
         if lr_schedule is None and hparams is not None:
             lr_schedule = reference_lr_schedule(hparams)
@@ -106,6 +106,7 @@ class GraphedTrainStep:
         self.cache = OrderedDict()
         self.world = sync.world_size()
         assert sync.mode == 'gather', 'GraphedTrainStep needs FlatGradSync(mode="gather") (deferred weight-gradient reduction)'
+        self.fused = fused_exchange   # ddp.FusedShardedAdam: reduce-scatter + Adam + all-gather in one kernel instead of all-reduce + graph B
         self.merged_adam = self.world == 1 and self.acc_steps == 1 and not opt.wants_clip()
         self.graph_b = None          # clip + Adam (+ zero the bucket when accumulating): independent of the batch shape
         self.launches_b = 0
@@ -192,7 +193,7 @@ class GraphedTrainStep:
             if self.merged_adam:
                 self._body_adam()
         c.launches = int(lib.dx_launch_count() - l0)   # kernels of libdaftexprt_b200.so per replay
-        if not self.merged_adam and self.graph_b is None:
+        if not self.merged_adam and self.graph_b is None and self.fused is None:
             l0 = lib.dx_launch_count()
             self.graph_b = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_b):
@@ -245,7 +246,12 @@ class GraphedTrainStep:
             if self.stepped:
                 self.micro = 0
                 self.opt.step_count += 1
-                if not self.merged_adam:
+                if self.fused is not None:
+                    self.fused.launch(self.opt.step_count)     # lr / bias corrections come from the device block
+                    self.launches_replayed += 1
+                    if self.acc_steps > 1:
+                        self.sync.flat.zero_()
+                elif not self.merged_adam:
                     self._all_reduce()
                     self.graph_b.replay()
                     self.launches_replayed += self.launches_b
