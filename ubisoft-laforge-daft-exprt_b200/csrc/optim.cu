@@ -108,35 +108,50 @@ __global__ void __launch_bounds__(256) fused_reduce_adam_kernel(const float* g_m
                                                                 float grad_scale, const StepState* dyn) {
     if (dyn) { lr = dyn->lr; bc1 = dyn->bc1; bc2_sqrt = dyn->bc2_sqrt; }
     const float step = lr / bc1;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t e = (begin4 + i) * 4;
-        float4 g;
-        if (g_mc) {
-            g = mc_ld_reduce(g_mc + e);
-        } else {
-            g = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int r = 0; r < world; ++r) {
-                const float4 t = ld_peer(reinterpret_cast<const float*>(g_peers.p[r]) + e);
-                g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    constexpr int U = 4;   // independent 16-byte NVLink loads in flight per thread (remote latency, not issue rate, is the limit)
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < n4; i0 += U * stride) {
+        float4 g[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t i = i0 + u * stride;
+            g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n4) {
+                const size_t e = (begin4 + i) * 4;
+                if (g_mc) {
+                    g[u] = mc_ld_reduce(g_mc + e);
+                } else {
+                    for (int r = 0; r < world; ++r) {
+                        const float4 t = ld_peer(reinterpret_cast<const float*>(g_peers.p[r]) + e);
+                        g[u].x += t.x; g[u].y += t.y; g[u].z += t.z; g[u].w += t.w;
+                    }
+                }
             }
         }
-        const float4 pv = *reinterpret_cast<const float4*>(p_local + e);
-        float4 mv = *reinterpret_cast<const float4*>(m + e), vv = *reinterpret_cast<const float4*>(v + e);
-        float pa[4] = {pv.x, pv.y, pv.z, pv.w}, ga[4] = {g.x, g.y, g.z, g.w}, ma[4] = {mv.x, mv.y, mv.z, mv.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float gi = ga[k] * grad_scale + wd * pa[k];
-            ma[k] = b1 * ma[k] + (1.f - b1) * gi;
-            va[k] = b2 * va[k] + (1.f - b2) * gi * gi;
-            pa[k] = pa[k] - step * (ma[k] / (sqrtf(va[k]) / bc2_sqrt + eps));
-        }
-        *reinterpret_cast<float4*>(m + e) = make_float4(ma[0], ma[1], ma[2], ma[3]);
-        *reinterpret_cast<float4*>(v + e) = make_float4(va[0], va[1], va[2], va[3]);
-        const float4 pn = make_float4(pa[0], pa[1], pa[2], pa[3]);
-        if (p_mc) {
-            mc_st(p_mc + e, pn);
-        } else {
-            for (int r = 0; r < world; ++r) st_peer(reinterpret_cast<float*>(p_peers.p[r]) + e, pn);
+        for (int u = 0; u < U; ++u) {
+            const size_t i = i0 + u * stride;
+            if (i >= n4) break;
+            const size_t e = (begin4 + i) * 4;
+            const float4 pv = *reinterpret_cast<const float4*>(p_local + e);
+            const float4 mv = *reinterpret_cast<const float4*>(m + e), vv = *reinterpret_cast<const float4*>(v + e);
+            float pa[4] = {pv.x, pv.y, pv.z, pv.w}, ga[4] = {g[u].x, g[u].y, g[u].z, g[u].w}, ma[4] = {mv.x, mv.y, mv.z, mv.w},
+                  va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float gi = ga[k] * grad_scale + wd * pa[k];
+                ma[k] = b1 * ma[k] + (1.f - b1) * gi;
+                va[k] = b2 * va[k] + (1.f - b2) * gi * gi;
+                pa[k] = pa[k] - step * (ma[k] / (sqrtf(va[k]) / bc2_sqrt + eps));
+            }
+            *reinterpret_cast<float4*>(m + e) = make_float4(ma[0], ma[1], ma[2], ma[3]);
+            *reinterpret_cast<float4*>(v + e) = make_float4(va[0], va[1], va[2], va[3]);
+            const float4 pn = make_float4(pa[0], pa[1], pa[2], pa[3]);
+            if (p_mc) {
+                mc_st(p_mc + e, pn);
+            } else {
+                for (int r = 0; r < world; ++r) st_peer(reinterpret_cast<float*>(p_peers.p[r]) + e, pn);
+            }
         }
     }
 }
@@ -152,7 +167,7 @@ int fused_reduce_adam(const float* g_mc, const unsigned long long* g_peers, floa
     const float bc1 = 1.f - powf(beta1, (float)step);
     const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
     if (n == 0) return DX_OK;
-    fused_reduce_adam_kernel<<<grid_1d(n / 4, 256, 148 * 8), 256, 0, st>>>(g_mc, gp, p_mc, pp, p_local, m, v, begin / 4, n / 4, world, lr, beta1, beta2,
+    fused_reduce_adam_kernel<<<grid_1d(n / 16 + 1, 256, 148 * 8), 256, 0, st>>>(g_mc, gp, p_mc, pp, p_local, m, v, begin / 4, n / 4, world, lr, beta1, beta2,
                                                                          eps, weight_decay, bc1, bc2_sqrt, grad_scale, dyn);
     return check_launch("fused_reduce_adam");
 }
