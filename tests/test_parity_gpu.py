@@ -1177,3 +1177,18 @@ def test_loss_readback_is_one_step_late_and_exact(dev):
     for k in range(1, 5):
         assert got[k] == vals[k - 1].tolist()
     assert rb.flush() == [vals[4].tolist()] and rb.flush() == []
+
+
+def test_fused_gradient_exchange_matches_nccl_allreduce_two_gpus(dev):
+    """ddp.FusedShardedAdam (reduce-scatter + Adam + all-gather in one kernel over symmetric memory) == NCCL all-reduce + FlatAdam on two
+    ranks (tools/fused_exchange_check.py asserts parameters, both moments and the cross-rank parameter checksum).  Needs >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs (run with gpurun --gpus 2)')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                        '--master-port', '29577', os.path.join(root, 'tools', 'fused_exchange_check.py')], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert 'fused exchange mode' in r.stdout
