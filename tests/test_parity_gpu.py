@@ -564,6 +564,9 @@ def test_graph_step_matches_eager(dev):
     # Adam normalises the update, so an fp32-ordering difference on a near-zero gradient can flip a whole lr-sized step:
     # compare in l2 over all 14.7 M parameters instead of element-wise
     assert l2_rel_err(p_graph - p_init, p_eager - p_init) < 5e-2
+    # the big weight gradients were written straight into the flat bucket (no copy when the bucket is packed)
+    in_place = sum(p.numel() for p, v in zip(sync.params, sync.views) if p.grad is not None and p.grad.data_ptr() == v.data_ptr())
+    assert in_place > 0.9 * sync.numel, (in_place, sync.numel)
     # the eager path is untouched afterwards (device block unregistered)
     out = crit.forward_device(model(inputs), targets, 2004)
     assert np.isfinite(out.detach().cpu().numpy()).all()

@@ -43,6 +43,14 @@ class FlatGradSync:
         if mode == 'alias':
             for p, v in zip(self.params, self.views):
                 p.grad = v   # autograd accumulates in place into existing .grad
+        self._register_slots()
+
+    def _register_slots(self):
+        """mode 'gather' on CUDA: tell the weight-gradient GEMMs where each parameter's gradient lives in the bucket (ops.grad_slot);
+        used while `ops.use_grad_slots(True)` (one micro-batch per optimiser step: graph.GraphedTrainStep / bench switch it on)."""
+        if self.mode == 'gather' and self.flat.is_cuda:
+            from . import ops
+            ops.register_grad_slots({id(p): v for p, v in zip(self.params, self.views)})
 
     def rebind(self, new_flat):
         """Move the bucket into another allocation of the same size (e.g. a symmetric-memory buffer mapped on every rank)."""
@@ -53,6 +61,7 @@ class FlatGradSync:
         if self.mode == 'alias':
             for p, v in zip(self.params, self.views):
                 p.grad = v
+        self._register_slots()
 
     def zero_grad(self):
         if self.mode == 'alias':
@@ -69,10 +78,11 @@ class FlatGradSync:
         for p, v in zip(self.params, self.views):
             if p.grad is None:
                 v.zero_()
-            else:
+            elif p.grad.data_ptr() != v.data_ptr():   # (gradients written straight into their slot need no copy: ops.grad_slot)
                 views.append(v)
                 grads.append(p.grad)
-        torch._foreach_copy_(views, grads)
+        if views:
+            torch._foreach_copy_(views, grads)
 
     def accumulate(self, alpha=1.0):
         """mode='gather', gradient accumulation (reference train.py:379,391: loss / accumulation_steps, backward per micro-batch):

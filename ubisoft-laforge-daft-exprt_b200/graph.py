@@ -133,6 +133,7 @@ class GraphedTrainStep:
     def _body_backward(self, inputs, targets):
         self.opt.zero_grad()
         ops.set_wgrad_deferral(True)   # gather mode: no gradient is read before the bucket is filled, so reduce them all at once
+        ops.use_grad_slots(self.acc_steps == 1)   # one micro-batch per optimiser step: the big weight gradients are written into the bucket
         try:
             if self.before_forward is not None:
                 self.before_forward()
@@ -143,6 +144,7 @@ class GraphedTrainStep:
             ops.flush_wgrad()
         finally:
             ops.set_wgrad_deferral(False)
+            ops.use_grad_slots(False)
         if self.acc_steps == 1:
             self.sync.gather()
         else:

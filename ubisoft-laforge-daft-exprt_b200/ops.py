@@ -271,11 +271,35 @@ def linear_rows(x2d, wp, bias, **kw):
     return conv_gemm(x2d, wp, bias, 1, R, **kw).view(R, -1)
 
 
+_grad_slots = {}          # id(parameter) -> view of the flat gradient bucket (ddp.FlatGradSync, mode 'gather')
+_use_grad_slots = [False]
+
+
+def register_grad_slots(slots):
+    """ddp.FlatGradSync: where each parameter's gradient lives in the flat bucket.  While `use_grad_slots(True)`, the weight-gradient
+    GEMMs of the big weights write THERE (their result tensor is a fresh alias of the slot, which autograd's AccumulateGrad adopts as
+    `p.grad`), so packing the bucket before the gradient exchange has nothing left to copy for them."""
+    _grad_slots.clear()
+    _grad_slots.update(slots)
+
+
+def use_grad_slots(on):
+    _use_grad_slots[0] = bool(on)
+
+
+def grad_slot(w):
+    return _grad_slots.get(id(w)) if _use_grad_slots[0] else None
+
+
 def conv_wgrad(x, dy, B, S, cin, cout, kw, shape, want_bias=True, ldx=None, alpha=1.0, x_planes=None, dy_planes=None, dbias=None,
-               lens=None, halo=0):
-    """-> (dw in the parameter's own layout `shape`, dbias [Cout] or None).  `dbias`: already computed (fused into make_planes)."""
+               lens=None, halo=0, slot=None):
+    """-> (dw in the parameter's own layout `shape`, dbias [Cout] or None).  `dbias`: already computed (fused into make_planes).
+    slot: the parameter's view of the flat gradient bucket (grad_slot()): dw is written there."""
     dev = (dy if dy is not None else dy_planes).device   # x / dy may be None when their planes are handed over
-    dw = torch.empty(tuple(shape), device=dev, dtype=torch.float32)
+    if slot is not None and tuple(slot.shape) == tuple(shape) and slot.is_contiguous():
+        dw = slot.detach()        # a fresh alias: AccumulateGrad adopts it without a copy when nothing else refers to it
+    else:
+        dw = torch.empty(tuple(shape), device=dev, dtype=torch.float32)
     if dbias is not None:
         want_bias = False
     db = torch.empty(cout, device=dev, dtype=torch.float32) if want_bias else None
@@ -421,6 +445,7 @@ class AttentionSubLayer(torch.autograd.Function):
             y, xhat, rstd = ln_fwd(proj, x, ln_w, ln_b, None, 0, lens, B, S, D, p_in=p_drop, seed_in=seed_out, emit_planes=True)
         ctx.save_for_backward(x, lens, qkv, att, lse, xhat, rstd, ln_w, ln_b, xP, attP, planes)
         hold_packs(ctx, in_wd, out_wd)
+        ctx.slots = (grad_slot(in_w), grad_slot(out_w))
         ctx.cfg = (B, S, D, nb_heads, dh, float(p_drop), seed_attn, seed_out, in_w.shape, out_w.shape)
         return y
 
@@ -439,13 +464,15 @@ class AttentionSubLayer(torch.autograd.Function):
             _call('dx_outproj_dgrad_head_planes', _p(dprojP), _p(out_wd.planes), _p(att), _p(scratch), _p(lens), B, S, D, H, dh, _st())
         else:
             datt = conv_gemm(dproj, out_wd, None, B, S, x_planes=dprojP, lens=lens)   # dproj == 0 beyond len: exact
-        d_out_w, d_out_b = conv_wgrad(att, dproj, B, S, D, D, 1, out_shape, x_planes=attP, dy_planes=dprojP, dbias=dpb, lens=lens)
+        d_out_w, d_out_b = conv_wgrad(att, dproj, B, S, D, D, 1, out_shape, x_planes=attP, dy_planes=dprojP, dbias=dpb, lens=lens,
+                                      slot=ctx.slots[1])
         dqkv = torch.empty(B, S, 3 * D, device=dy.device, dtype=torch.float32)
         _call('dx_attention_bwd', _p(qkv), _p(planes), _p(lens), _p(att), _p(lse), _p(datt), _p(dqkv), _p(scratch), B, S, H, dh, p,
               seed_attn, _st())
         dqkvP, dqb = make_planes(dqkv, B * S, 3 * D, want_colsum=True)
         dx = conv_gemm(dqkv, in_wd, None, B, S, add_src=dv, x_planes=dqkvP, lens=lens)   # dqkv == dv == 0 beyond len: exact
-        d_in_w, d_in_b = conv_wgrad(x, dqkv, B, S, D, 3 * D, 1, in_shape, x_planes=xP, dy_planes=dqkvP, dbias=dqb, lens=lens)
+        d_in_w, d_in_b = conv_wgrad(x, dqkv, B, S, D, 3 * D, 1, in_shape, x_planes=xP, dy_planes=dqkvP, dbias=dqb, lens=lens,
+                                    slot=ctx.slots[0])
         return dx, None, d_in_w, d_in_b, d_out_w, d_out_b, dln_w, dln_b, None, None
 
 
@@ -479,6 +506,7 @@ class ConvFFSubLayer(torch.autograd.Function):
             y, xhat, rstd = ln_fwd(o, x, ln_w, ln_b, film, 2 * D, lens, B, S, D, p_in=p_drop, seed_in=seed, emit_planes=True)
         ctx.save_for_backward(x, lens, h, xhat, rstd, ln_w, ln_b, film, xP, hP)
         hold_packs(ctx, w1d, w2d)
+        ctx.slots = (grad_slot(w1), grad_slot(w2))
         ctx.cfg = (B, S, D, C, float(p_drop), seed, w1.shape, w2.shape)
         return y
 
@@ -497,9 +525,10 @@ class ConvFFSubLayer(torch.autograd.Function):
         else:
             dh = conv_gemm(do, w2d, None, B, S, relu_src=h, round_out=True, x_planes=doP, lens=lens, halo=k2)   # do == 0 beyond len: exact
             dhP, dhb = make_planes(dh, B * S, C, want_colsum=True)
-        dw2, db2 = conv_wgrad(h, do, B, S, C, D, w2_shape[2], w2_shape, x_planes=hP, dy_planes=doP, dbias=dob, lens=lens)
+        dw2, db2 = conv_wgrad(h, do, B, S, C, D, w2_shape[2], w2_shape, x_planes=hP, dy_planes=doP, dbias=dob, lens=lens, slot=ctx.slots[1])
         dx = conv_gemm(dh, w1d, None, B, S, add_src=dv, x_planes=dhP, lens=lens)   # rows >= len are masked by the producer's LN bwd
-        dw1, db1 = conv_wgrad(x, dh, B, S, D, C, w1_shape[2], w1_shape, x_planes=xP, dy_planes=dhP, dbias=dhb, lens=lens, halo=k2)
+        dw1, db1 = conv_wgrad(x, dh, B, S, D, C, w1_shape[2], w1_shape, x_planes=xP, dy_planes=dhP, dbias=dhb, lens=lens, halo=k2,
+                              slot=ctx.slots[0])
         return dx, None, dw1, db1, dw2, db2, dln_w, dln_b, dfilm, None
 
 
@@ -536,6 +565,7 @@ class PreNet(torch.autograd.Function):
         ctx.save_for_backward(*saved)
         ctx.in_planes = in_planes   # bf16 planes of each layer's input (not autograd tensors of interest: plain buffers)
         hold_packs(ctx, *wds)
+        ctx.slots = (grad_slot(w0), grad_slot(w1), grad_slot(w2))
         ctx.cfg = (B, T, M, float(p_drop), seeds, (w0.shape, w1.shape, w2.shape))
         return cur
 
@@ -557,7 +587,7 @@ class PreNet(torch.autograd.Function):
                                                       seed_out=seeds[i], emit_planes=True)
             # the gradient of the masked pre-net output is zero beyond len, so dpre of layer i is exactly zero beyond len + halos[i]
             dw, db = conv_wgrad(inp, dpre, B, T, cin, cout, kw, shapes[i], x_planes=ctx.in_planes[i], dy_planes=dpreP, dbias=dpreb,
-                                lens=lens, halo=halos[i])
+                                lens=lens, halo=halos[i], slot=ctx.slots[i])
             grads[4 * i: 4 * i + 4] = [dw, db, dg, de]
             if i > 0:
                 d = conv_gemm(dpre, wd, None, B, T, x_planes=dpreP, lens=lens, halo=halos[i - 1])
