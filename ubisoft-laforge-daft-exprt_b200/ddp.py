@@ -208,13 +208,17 @@ class FlatAdam:
 
     # -- torch.optim.Adam checkpoint format ---------------------------------------------------------------------------------
     def state_dict(self):
+        """torch.optim.Adam's format.  With ddp.FusedShardedAdam attached every rank keeps the moments of its own shard only: they are
+        reassembled here (a COLLECTIVE call then — every rank must call it, like the reference's barrier around checkpoints)."""
         state = {}
+        fused = getattr(self, '_fused', None)
+        m, v = fused.full_moments() if fused is not None else (self.m, self.v)
         if self.step_count > 0:
             for i, (p, off) in enumerate(zip(self.params, self.sync.offsets)):
                 n = p.numel()
                 state[i] = {'step': torch.tensor(float(self.step_count)),
-                            'exp_avg': self.m[off:off + n].view_as(p).clone(),
-                            'exp_avg_sq': self.v[off:off + n].view_as(p).clone()}
+                            'exp_avg': m[off:off + n].view_as(p).clone(),
+                            'exp_avg_sq': v[off:off + n].view_as(p).clone()}
         group = {k: v for k, v in self.param_groups[0].items() if k != 'params'}
         group['params'] = list(range(len(self.params)))
         return {'state': state, 'param_groups': [group]}
@@ -239,6 +243,11 @@ class FlatAdam:
         if len(steps) > 1:
             raise ValueError('FlatAdam.load_state_dict: parameters with different step counts are not supported')
         self.step_count = steps.pop() if steps else 0
+        fused = getattr(self, '_fused', None)
+        if fused is not None:   # sharded moments: keep the own shard only
+            for buf in (self.m, self.v):
+                buf[:fused.begin].zero_()
+                buf[fused.begin + fused.n:].zero_()
 
 
 class FusedShardedAdam:
@@ -281,6 +290,10 @@ class FusedShardedAdam:
         self.g_peers = (ctypes.c_uint64 * self.world)(*[int(x) for x in self.hg.buffer_ptrs])
         self.p_peers = (ctypes.c_uint64 * self.world)(*[int(x) for x in self.hp.buffer_ptrs])
         self.mode = 'multimem (in-switch reduction)' if self.g_mc else 'peer loads / stores'
+        opt._fused = self
+        for buf in (opt.m, opt.v):            # moments of the other shards are not maintained on this rank
+            buf[:self.begin].zero_()
+            buf[self.begin + self.n:].zero_()
         torch.cuda.synchronize()
         dist.barrier(self.group)
 
