@@ -401,6 +401,7 @@ def main():
     ap.add_argument('--no-eager-baseline', action='store_true', help='skip the PyTorch-eager-on-GPU baseline leg')
     ap.add_argument('--eval', action='store_true', help='eval mode (dropout off)')
     ap.add_argument('--profile-step', action='store_true', help='bracket ONE extra step with cudaProfilerStart/Stop (for ncu --profile-from-start off)')
+    ap.add_argument('--accumulation-steps', type=int, default=1, help='micro-batches per optimiser step (reference hparams.py:67 default: 3); a bench step = one micro-batch')
     ap.add_argument('--nccl-allreduce', action='store_true', help='N > 1: NCCL all-reduce + Adam instead of the fused reduce-scatter + Adam + all-gather kernel')
     ap.add_argument('--no-graph', action='store_true', help='issue the launches of a step eagerly instead of replaying the captured CUDA graph')
     args = ap.parse_args()
@@ -479,7 +480,7 @@ def main():
     torch.cuda.synchronize()
     torch.cuda.reset_peak_memory_stats()
 
-    graphed = None if args.no_graph else GraphedTrainStep(model, crit, sync, opt, fused_exchange=fused)
+    graphed = None if args.no_graph else GraphedTrainStep(model, crit, sync, opt, fused_exchange=fused, accumulation_steps=args.accumulation_steps)
 
     def eager_step(inp, tgt, it, read_back=False):
         opt.zero_grad()
@@ -587,6 +588,7 @@ def main():
         'config': {'workload': workload, 'global_batch': cfg['B'] * world, 'valid_frames_per_step': total_frames,
                    'padded_frames_per_step': cfg['B'] * world * cfg['T'], 'parallelism': f'dp{world}', 'grad_exchange': exchange,
                    'per_rank_batches': 'same lengths on every rank (equal valid-frame totals), per-rank content',
+                   'accumulation_steps': args.accumulation_steps,
                    'launch': 'eager' if graphed is None else 'cuda-graph replay (graph.py); gpu_launches = kernels of libdaftexprt_b200.so executed by the replays',
                    'l2': 'per-step working set (several GB of activations) >> 126 MB L2; no explicit flush needed',
                    'peak_memory_gb': peak_mem},
