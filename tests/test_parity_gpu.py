@@ -665,6 +665,60 @@ def test_attention_tcgen05_matches_mma_sync(dev, cfg):
     assert float(c1[~valid].abs().max() if (~valid).any() else 0.0) == 0.0 and float(g1[~valid].abs().max() if (~valid).any() else 0.0) == 0.0
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize('cfg', [(2, 700, 2, 64), (2, 700, 8, 16), (1, 1000, 2, 64)])
+def test_attention_forward_moving_maximum(dev, cfg):
+    """The one-pass softmax of the tcgen05 forward keeps a lazy running maximum and corrects O in TMEM when a key tile raises it.
+    Gaussian inputs never trigger that after the first tile, so this case plants a score component that grows by 10 per 128-key
+    tile for every other query row (and falls for the rest): each tile moves the maximum of half the rows past the 8 / log2(e)
+    threshold.  Checks context and
+    log-sum-exp against an fp64 softmax, and — with dropout — against the mma.sync kernel on the same mask hash."""
+    from daft_exprt_b200 import cabi, ops
+    set_backend('bf16x3')
+    B, S, H, dh = cfg
+    D = H * dh
+    g = torch.Generator().manual_seed(7 * S + H)
+    qkv = torch.randn(B, S, 3 * D, generator=g)
+    # first coordinate of every head: q = +-sqrt(dh) (alternating rows), k = 10 * (key tile index)  ->  score = +-10 * tile + noise
+    sign = torch.where(torch.arange(S) % 2 == 0, 1.0, -1.0) * dh ** 0.5
+    qkv.view(B, S, 3, H, dh)[:, :, 0, :, 0] = sign[None, :, None]
+    qkv.view(B, S, 3, H, dh)[:, :, 1, :, 0] = (10.0 * (torch.arange(S) // 128))[None, :, None]
+    lens = torch.tensor([S] + [S - 77] * (B - 1))
+    qkv_d, lens_d = qkv.to(dev), lens.to(dev)
+
+    def run(backend, p):
+        ops._call('dx_set_attention_backend', backend, backend)
+        ctx = torch.empty(B, S, D, device=dev); lse = torch.empty(B, H, S, device=dev)
+        planes = ops.attention_planes(B, S, H, dh, dev)
+        ops._call('dx_attention_fwd', qkv_d.data_ptr(), lens_d.data_ptr(), ctx.data_ptr(), lse.data_ptr(), ops._p(planes), None, B, S, H, dh,
+                  p, 5, ops._st())
+        torch.cuda.synchronize()
+        return ctx, lse
+
+    try:
+        ctx, lse = run(cabi.DX_ATTENTION_TCGEN05, 0.0)
+        q, k, v = (t.double().view(B, S, H, dh).transpose(1, 2) for t in qkv.split(D, dim=-1))
+        s = q @ k.transpose(-1, -2) / dh ** 0.5
+        valid = torch.arange(S)[None, :] < lens[:, None]
+        s = s.masked_fill(~valid[:, None, None, :], float('-inf'))
+        ref_lse = torch.logsumexp(s, -1)
+        ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, S, D) * valid[:, :, None]
+        # how often a tile moves the reference maximum in the fp64 scores (sanity: the case does exercise the correction)
+        tile_max = torch.stack([s[..., j:j + 128].max(-1).values for j in range(0, S, 128)], -1)
+        run_max = torch.cummax(tile_max, -1).values
+        moves = (tile_max[..., 1:] > run_max[..., :-1] + 8 / 1.4426950408889634).double().mean()
+        assert moves > 0.2, float(moves)
+        assert torch.isfinite(ctx).all()
+        assert scale_rel_err(ctx.cpu().double(), ref) < 2e-3
+        lse_v = (lse.cpu().double() - ref_lse) * valid[:, None, :]
+        assert float(lse_v.abs().max()) < 2e-3 * float(ref_lse.abs().max())
+        c1, l1 = run(cabi.DX_ATTENTION_TCGEN05, 0.2)
+        c0, l0 = run(cabi.DX_ATTENTION_MMA_SYNC, 0.2)
+        assert scale_rel_err(c1, c0) < 1e-3 and scale_rel_err(l1, l0) < 1e-4
+    finally:
+        ops._call('dx_set_attention_backend', cabi.DX_ATTENTION_TCGEN05, cabi.DX_ATTENTION_TCGEN05)
+
+
 def test_batch_prefetcher_matches_parse_batch(dev):
     """data.BatchPrefetcher (parse_batch one step ahead on a side stream) hands over exactly what parse_batch returns."""
     from daft_exprt_b200.data import BatchPrefetcher

@@ -9,7 +9,11 @@ VARIANTS = {
     'no_fused_inproj': {'DX_AB_FUSED_INPROJ': '0'},
     'no_pipe64': {'DX_ATTN_BWD_PIPE64': '0'},
     'all_off': {'DX_AB_FUSED_LN': '0', 'DX_AB_FUSED_INPROJ': '0', 'DX_ATTN_BWD_PIPE64': '0'},
+    'two_pass_softmax': {'DX_ATTN_FWD_ONLINE': '0'},
+    'fwd64_2cta': {'DX_ATTN_FWD64_2CTA': '1'},
 }
+if os.environ.get('DX_AB_ONLY'):   # comma list of variant names
+    VARIANTS = {k: v for k, v in VARIANTS.items() if k in os.environ['DX_AB_ONLY'].split(',')}
 if len(sys.argv) > 1 and sys.argv[1] == 'child':
     import torch
     import bench

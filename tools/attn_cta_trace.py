@@ -8,7 +8,7 @@ import bench
 ops.set_backend('bf16x3')
 dev = torch.device('cuda', 0)
 B, S = 32, 1000
-lens = bench.make_host_batch(0)[9].to(dev)
+lens = bench.rank_batch(bench.CONFIGS['train'], 0)[9].to(dev)
 for (H, dh, p) in [(2, 64, 0.1), (8, 16, 0.1)]:
     D = H * dh
     qkv = torch.randn(B, S, 3 * D, device=dev)

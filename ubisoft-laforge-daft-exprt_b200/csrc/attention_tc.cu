@@ -15,9 +15,14 @@
 //               in the first 16 columns of the quarter, lo pairs in the last 16)
 // The score buffers ping-pong: the MMAs of key tile t+1 run while the softmax warps work on tile t.
 //
-// Exact two-pass softmax instead of online rescaling: pass A forms S tile by tile and only keeps the row maxima, pass B forms S
-// again, exponentiates against the FINAL maximum and accumulates O in TMEM with no correction step and no accumulator
-// registers (1.5x the Q K^T flops; the kernel is bound by the per-score ALU work, not by the tensor pipe).
+// Softmax, default (ONLINE): ONE pass over the key tiles with a LAZY running maximum.  Row r keeps a reference maximum M_r; a tile
+// whose row maximum exceeds M_r by more than 8 / log2(e) raises it and rescales the row sum and the O row in TMEM, otherwise the tile
+// is exponentiated against the old M_r (weights <= 2^8, cancelled by the normalisation).  After the first tile hardly any tile moves
+// M_r, so the O correction (TMEM load / scale / store behind the P V of the previous tile) runs a few times per CTA.
+// DX_ATTN_FWD_ONLINE=0 selects the exact two-pass form of round 1 (pass A forms S and keeps the row maxima, pass B forms S again and
+// exponentiates against the final maximum: 1.5x the Q K^T flops and a second TMEM read).  Measured at the bench shapes: head_dim 64
+// 105.5 -> 96.4 us per layer call, head_dim 16 199.6 -> 195.4 us; the kernel is bound by the ~13 ALU instructions per score of the
+// exp / row sum / dropout / hi|lo split (issue slots 65 % busy), so dropping the max pass buys less than its share of the tiles.
 // TMEM columns: [0,128) and [128,256) the two S/P buffers, [256, 256+dh) O.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -43,7 +48,7 @@ template <int NSW> constexpr int atc_threads() { return 64 + 32 * NSW; }   // + 
 template <int NBUF> constexpr int atc_tmem_cols() { return NBUF == 2 ? 512 : 256; }
 constexpr float kLog2e = 1.4426950408889634f;
 
-template <int DH>
+template <int DH, int NBUF = 2>
 struct AtcCfg {
     static_assert(DH == 64 || DH == 16, "tcgen05 attention: head_dim 64 (128-byte rows) or 16 (32-byte rows)");
     static constexpr int ROW_BYTES = DH * 2;
@@ -52,9 +57,11 @@ struct AtcCfg {
     static constexpr uint32_t SBO = 8 * ROW_BYTES;                    // 8-row groups
     static constexpr int KS = DH / 16;                                // K-steps of Q K^T
     static constexpr uint32_t V_KSTEP = (16 * ROW_BYTES) >> 4;        // 16 key rows per K-step of P V (MN-major B)
-    static constexpr int K_STAGES = DH == 64 ? 3 : 6, V_STAGES = DH == 64 ? 2 : 4;
+    // head_dim 64 with one score buffer (two CTAs per SM): one K and one V stage are enough — S(t+1) cannot be issued before
+    // P V(t) anyway, K(t+1) lands during the softmax of tile t and V(t+1) during S(t+1) and its softmax
+    static constexpr int K_STAGES = DH == 64 ? (NBUF == 2 ? 3 : 1) : 6, V_STAGES = DH == 64 ? (NBUF == 2 ? 2 : 1) : 4;
     static constexpr int SMEM_TILES = 2 + 2 * K_STAGES + 2 * V_STAGES;   // Q, K ring, V ring; hi|lo planes each
-    static constexpr int SMEM_BYTES = SMEM_TILES * TILE_BYTES + 256 + 4 * TQ * 4 + 64 + 1024;   // + barriers + max/sum exchange
+    static constexpr int SMEM_BYTES = SMEM_TILES * TILE_BYTES + 256 + 2 * 4 * TQ * 4 + 64 + 1024;   // + barriers + max/sum exchange (x2)
 };
 // K-major tile (rows x dh): 8-row groups SBO apart
 template <int DH>
@@ -86,16 +93,16 @@ struct AtcParams {
     long long* trace;        // optional [4][256] clock64 trace of block (0,0,0): softmax warp 2 lane 0 (rows 0-2), MMA thread (row 3)
 };
 
-template <int DH, int NBUF, int NSW>
+template <int DH, int NBUF, int NSW, bool ONLINE>
 __global__ void __launch_bounds__(atc_threads<NSW>(), NBUF == 1 ? 2 : 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_r, AtcParams p) {
-    using C = AtcCfg<DH>;
+    using C = AtcCfg<DH, NBUF>;
     constexpr int NCG = NSW / 4;             // column groups of a 128-key tile
     constexpr int CPT = 4 / NCG;             // 32-column chunks per thread
+    constexpr int OC = DH == 64 ? DH / NCG : 16;   // O columns per thread in the correction step and the epilogue (head_dim 16: column group 0 takes all)
     constexpr int O_COL0 = NBUF * TKEY;      // O accumulator behind the score buffer(s)
     constexpr int ATC_TMEM_COLS = atc_tmem_cols<NBUF>();
     constexpr int ATC_SOFTMAX_WARPS = NSW;
-    static_assert(NBUF == 2 || DH == 16, "the single-buffer / two-CTA shape is sized for head_dim 16");
     constexpr int TB = C::TILE_BYTES, KST = C::K_STAGES, VST = C::V_STAGES;
     extern __shared__ uint8_t atc_smem_raw[];
     const uint32_t base = (smem_u32(atc_smem_raw) + 1023u) & ~1023u;
@@ -106,8 +113,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_r, AtcParams p) {
     // barriers (8 bytes each): q_full | k_full[8] k_empty[8] | v_full[4] v_empty[4] | s_full[2] s_free[2] p_full[2] | o_full
     const uint32_t q_full = bars, k_full0 = bars + 8, k_empty0 = bars + 72, v_full0 = bars + 136, v_empty0 = bars + 168;
     const uint32_t s_full0 = bars + 200, s_free0 = bars + 216, p_full0 = bars + 232, o_full = bars + 248;
-    const uint32_t red0 = bars + 256;               // float [4 column quarters][128 rows]
-    const uint32_t tmem_slot = red0 + 4 * TQ * 4;
+    const uint32_t red0 = bars + 256;               // float [2][4 column quarters][128 rows]
+    const uint32_t tmem_slot = red0 + 2 * 4 * TQ * 4;
+    const uint32_t o_ready = s_free0;               // ONLINE: P V of tile t retired (count 1); the max pass and its barrier do not exist
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(atc_smem_raw + (tmem_slot - smem_u32(atc_smem_raw)));
     float* xch = reinterpret_cast<float*>(atc_smem_raw + (red0 - smem_u32(atc_smem_raw)));
 
@@ -156,7 +164,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_r, AtcParams p) {
         for (int i = 0; i < KST; ++i) { mbar_init(k_full0 + 8 * i, 1); mbar_init(k_empty0 + 8 * i, 1); }
         for (int i = 0; i < VST; ++i) { mbar_init(v_full0 + 8 * i, 1); mbar_init(v_empty0 + 8 * i, 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(s_full0 + 8 * i, 1); mbar_init(s_free0 + 8 * i, ATC_SOFTMAX_WARPS); mbar_init(p_full0 + 8 * i, ATC_SOFTMAX_WARPS);
+            mbar_init(s_full0 + 8 * i, 1); mbar_init(s_free0 + 8 * i, ONLINE ? 1 : ATC_SOFTMAX_WARPS); mbar_init(p_full0 + 8 * i, ATC_SOFTMAX_WARPS);
         }
         mbar_init(o_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -171,7 +179,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_r, AtcParams p) {
     const uint32_t tmem_base = *tmem_slot_ptr;
     if (tr0) p.trace[3 * 256 + 201] = clock64();
     const int n_tiles = (len + TKEY - 1) / TKEY;
-    const int n_steps = 2 * n_tiles;   // step t: key tile t % n_tiles; t < n_tiles = pass A (maxima), else pass B (P V); score buffer t & 1
+    // step t: key tile t % n_tiles, score buffer t % NBUF.  Two-pass: t < n_tiles = pass A (maxima), else pass B (P V).  ONLINE: one pass
+    const int n_steps = ONLINE ? n_tiles : 2 * n_tiles;
+    const int t_b0 = ONLINE ? 0 : n_tiles;   // first P V step
     // plane-head slices of R: (plane, b, which, h) -> index ((plane * B + b) * 3H + which * H + h)
     const int sl_q = b * NH + h, sl_k = b * NH + p.H + h, sl_v = b * NH + 2 * p.H + h, sl_lo = p.B * NH;
 
@@ -188,7 +198,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_r, AtcParams p) {
                 tma_load_3d(sK + (ks * 2 + 0) * TB, &map_r, k_full0 + 8 * ks, 0, j * TKEY, sl_k);
                 tma_load_3d(sK + (ks * 2 + 1) * TB, &map_r, k_full0 + 8 * ks, 0, j * TKEY, sl_lo + sl_k);
                 if (++ks == KST) { ks = 0; kph ^= 1; }
-                if (t >= n_tiles) {
+                if (t >= t_b0) {
                     mbar_wait(v_empty0 + 8 * vs, vph ^ 1);
                     mbar_expect_tx(v_full0 + 8 * vs, 2 * TB);
                     tma_load_3d(sV + (vs * 2 + 0) * TB, &map_r, v_full0 + 8 * vs, 0, j * TKEY, sl_v);
@@ -231,7 +241,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_r, AtcParams p) {
         uint32_t sfree_cnt0 = 0, sfree_cnt1 = 0, pfull_cnt0 = 0, pfull_cnt1 = 0;
         for (int t = 0; t < n_steps; ++t) {
             const int buf = t % NBUF;
-            if (t < n_tiles) {   // pass A: the softmax warps have read S(t): its buffer may take S(t + 2)
+            if (t < t_b0) {      // pass A: the softmax warps have read S(t): its buffer may take S(t + 2)
                 const uint32_t par = (buf ? sfree_cnt1 : sfree_cnt0) & 1;
                 if (buf) ++sfree_cnt1; else ++sfree_cnt0;
                 mbar_wait(s_free0 + 8 * buf, par);
@@ -244,7 +254,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_r, AtcParams p) {
                 tc_fence_after();
                 const uint64_t vh = desc_mn<DH>(sV + (vs * 2 + 0) * TB), vl = desc_mn<DH>(sV + (vs * 2 + 1) * TB);
                 const uint32_t tmem_o = tmem_base + O_COL0, tmem_p = tmem_base + buf * TKEY;
-                const uint32_t acc0 = t > n_tiles ? 1u : 0u;
+                const uint32_t acc0 = t > t_b0 ? 1u : 0u;
                 if (elect_one()) {
 #pragma unroll
                     for (int kk = 0; kk < TKEY / 16; ++kk) {
@@ -254,6 +264,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_r, AtcParams p) {
                         umma_ts(tmem_o, ph, vl + C::V_KSTEP * kk, idesc_o, 1u);
                     }
                     umma_commit(v_empty0 + 8 * vs);
+                    if (ONLINE) umma_commit(o_ready);   // phase t: O holds the sum over tiles 0..t
                 }
                 __syncwarp();
                 if (++vs == VST) { vs = 0; vph ^= 1; }
@@ -269,8 +280,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_r, AtcParams p) {
         const int rl = quad * 32 + lane;                         // row within the tile = TMEM lane
         const int r = q0 + rl;                                   // this thread's query row
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-        // ---- pass A: row maximum over all valid keys ----
         const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
+        const unsigned long long seed = dyn_seed(p.seed, p.dyn);
+        const bool drop = p.dropout_p > 0.f;
+        const uint32_t thresh = drop_threshold(p.dropout_p);
+        const uint32_t rk = hash_u32(seed, ((unsigned long long)b * p.H + h) * (unsigned long long)p.S + r);   // same keys as the backward
+        float m, l;
+        if constexpr (!ONLINE) {
+        // ---- pass A: row maximum over all valid keys ----
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         for (int t = 0; t < n_tiles; ++t) {
             const int buf = t % NBUF;
@@ -296,17 +313,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_r, AtcParams p) {
             }
             if (tr) p.trace[512 + t] = clock64();
         }
-        float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         xch[cq * TQ + rl] = m;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * NSW) : "memory");
 #pragma unroll
         for (int c = 0; c < NCG; ++c) m = fmaxf(m, xch[c * TQ + rl]);   // finite: key 0 is always valid
         asm volatile("bar.sync 1, %0;" ::"n"(32 * NSW) : "memory");
         // ---- pass B: P = exp(S - m) in place, row sums ----
-        const unsigned long long seed = dyn_seed(p.seed, p.dyn);
-        const bool drop = p.dropout_p > 0.f;
-        const uint32_t thresh = drop_threshold(p.dropout_p);
-        const uint32_t rk = hash_u32(seed, ((unsigned long long)b * p.H + h) * (unsigned long long)p.S + r);   // same keys as the backward
         const float m2 = m * kLog2e;
         float l0 = 0.f, l1 = 0.f;
         for (int t = n_tiles; t < n_steps; ++t) {
@@ -348,17 +361,112 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_r, AtcParams p) {
         }
         xch[cq * TQ + rl] = l0 + l1;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * NSW) : "memory");
-        float l = 0.f;
+        l = 0.f;
 #pragma unroll
         for (int c = 0; c < NCG; ++c) l += xch[c * TQ + rl];
+        } else {
+        // ---- ONE pass, online softmax with a LAZY reference maximum: row r keeps M_r; a key tile whose row maximum exceeds
+        // M_r by more than kTau raises M_r (and rescales the row sum and the O row in TMEM by exp(M_old - M_new)); otherwise the
+        // tile is exponentiated against the old M_r (P <= 2^8: harmless in fp32 / bf16x3, and the normalisation cancels it).
+        // After the first tile almost no tile moves M_r, so the O correction (TMEM load, scale, store, ordered behind the P V
+        // of the previous tile) runs for a few tiles per CTA only.  The threads sharing a row exchange their tile maxima
+        // through shared memory with one named barrier per TMEM lane quarter.
+        constexpr float kTau = 8.f / kLog2e;
+        m = -INFINITY;
+        float l0 = 0.f, l1 = 0.f;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int buf = t % NBUF;
+            mbar_wait(s_full0 + 8 * buf, (t / NBUF) & 1);
+            if (tr) p.trace[t] = clock64();
+            tc_fence_after();
+            // thread's scores: kept in registers between the max and the exp for one 32-column chunk per thread; with two
+            // chunks per thread (two CTAs per SM, 96 registers) the chunks are read from TMEM again instead of spilling
+            const int key0 = t * TKEY + 32 * cq * CPT;
+            const bool last = (t + 1) * TKEY > len;
+            auto load_chunk = [&](int cc, uint32_t* d) {
+                tmem_ld32(t_lane + buf * TKEY + 32 * (cq * CPT + cc), d);
+                tmem_ld_wait32(d);
+                if (last) {   // keys >= len score -inf
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (key0 + 32 * cc + i >= len) d[i] = 0xff800000u;
+                }
+            };
+            uint32_t v[32];
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int cc = 0; cc < CPT; ++cc) {
+                load_chunk(cc, v);
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) m4[(i >> 1) & 3] = fmaxf(m4[(i >> 1) & 3], fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+            }
+            if (tr) p.trace[256 + t] = clock64();
+            float* x = xch + (t & 1) * 4 * TQ;
+            x[cq * TQ + rl] = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * NCG) : "memory");
+            float tm = x[rl];
+#pragma unroll
+            for (int c = 1; c < NCG; ++c) tm = fmaxf(tm, x[c * TQ + rl]);
+            const bool need = tm > m + kTau;                       // first tile: m = -inf, tm finite or -inf (row of a dead tile part)
+            const float mn = need ? tm : m;
+            const float alpha = need ? ex2((m - mn) * kLog2e) : 1.f;   // first tile: 0
+            l0 *= alpha; l1 *= alpha;
+            if (t > 0 && __any_sync(0xffffffffu, need)) {         // warp-uniform: the O rows of this warp take their factors
+                if (DH == 64 || cq == 0) {
+                    mbar_wait(o_ready, (t - 1) & 1);               // P V of tile t-1 has retired (at most one phase behind: P V(t) waits for us)
+                    tc_fence_after();
+#pragma unroll
+                    for (int c0 = cq * OC; c0 < cq * OC + OC; c0 += 16) {
+                        uint32_t ov[16];
+                        tmem_ld16(t_lane + O_COL0 + c0, ov);
+                        tmem_ld_wait16(ov);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+                        tmem_st16(t_lane + O_COL0 + c0, ov);
+                    }
+                }
+            }
+            m = mn;
+            const float m2 = m * kLog2e;
+#pragma unroll
+            for (int cc = 0; cc < CPT; ++cc) {
+                uint32_t o[32];
+                if (CPT > 1) load_chunk(cc, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float p0 = ex2(fmaf(__uint_as_float(v[2 * i]), kLog2e, -m2));
+                    float p1 = ex2(fmaf(__uint_as_float(v[2 * i + 1]), kLog2e, -m2));
+                    l0 += p0; l1 += p1;
+                    if (drop) {
+                        p0 = drop_keep(rk, drop_col_term((uint32_t)(key0 + 32 * cc + 2 * i)), thresh) ? p0 : 0.f;
+                        p1 = drop_keep(rk, drop_col_term((uint32_t)(key0 + 32 * cc + 2 * i + 1)), thresh) ? p1 : 0.f;
+                    }
+                    split_pair(p0, p1, o[i], o[16 + i]);
+                }
+                tmem_st32(t_lane + buf * TKEY + 32 * (cq * CPT + cc), o);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full0 + 8 * buf);
+            if (tr) p.trace[512 + t] = clock64();
+        }
+        float* x = xch + (n_tiles & 1) * 4 * TQ;
+        x[cq * TQ + rl] = l0 + l1;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * NCG) : "memory");
+        l = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCG; ++c) l += x[c * TQ + rl];
+        }
         // ---- epilogue: O / l -> ctx (+ operand planes), lse; the column quarters split the head dimension ----
         mbar_wait(o_full, 0);
         tc_fence_after();
         const bool valid = r < len;
         const float inv_keep = drop ? 1.f / (1.f - p.dropout_p) : 1.f;
         const float sc = valid ? inv_keep / l : 0.f;
-        if (DH == 64 || cq == 0) {
-            const int c0 = DH == 64 ? cq * 16 : 0;
+        if (DH == 64 || cq == 0)
+#pragma unroll
+        for (int c0 = cq * OC; c0 < cq * OC + OC; c0 += 16) {
             uint32_t v[16];
             tmem_ld16(t_lane + O_COL0 + c0, v);
             tmem_ld_wait16(v);
@@ -400,16 +508,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_r, AtcParams p) {
     }
 }
 
-template <int DH, int NBUF, int NSW>
+template <int DH, int NBUF, int NSW, bool ONLINE>
 int launch_fwd_tc(const AttnArgs& a, cudaStream_t st) {
-    using C = AtcCfg<DH>;
+    using C = AtcCfg<DH, NBUF>;
     // NBUF = 2: one CTA per SM (the kernel owns all 512 TMEM columns): request more than half of the shared memory.
     // NBUF = 1: two CTAs per SM (256 TMEM columns each): request what is needed (< half).
     const int smem = NBUF == 2 ? (C::SMEM_BYTES > 120 * 1024 ? C::SMEM_BYTES : 120 * 1024) : C::SMEM_BYTES;
     static_assert(NBUF == 2 || C::SMEM_BYTES <= 110 * 1024, "two CTAs per SM need at most half of the shared memory each");
     static bool configured = false;
     if (!configured) {
-        DX_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, NBUF, NSW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DX_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, NBUF, NSW, ONLINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     CUtensorMap map;
@@ -423,7 +531,7 @@ int launch_fwd_tc(const AttnArgs& a, cudaStream_t st) {
     p.trace = tc_trace_buffer();
     p.cta_trace = getenv("DX_ATTN_CTA_TRACE") != nullptr;
     dim3 grid(ceil_div(a.S, TQ), a.H, a.B);
-    attn_fwd_tc_kernel<DH, NBUF, NSW><<<grid, atc_threads<NSW>(), smem, st>>>(map, p);
+    attn_fwd_tc_kernel<DH, NBUF, NSW, ONLINE><<<grid, atc_threads<NSW>(), smem, st>>>(map, p);
     return check_launch("attn_fwd_tc");
 }
 
@@ -435,11 +543,19 @@ bool attention_fwd_tc_supported(const AttnArgs& a) {
 
 // a.R / a.Sp must be bound (attention_mma.cu: bind_planes + prep)
 int attention_fwd_tc(const AttnArgs& a, cudaStream_t st) {
-    if (a.dh == 64) return launch_fwd_tc<64, 2, 16>(a, st);
+    static int online = -1;   // DX_ATTN_FWD_ONLINE=0: the exact two-pass softmax (max pass + P V pass) instead of the one-pass lazy-maximum form
+    if (online < 0) { const char* e = getenv("DX_ATTN_FWD_ONLINE"); online = (e && atoi(e) == 0) ? 0 : 1; }
+    if (a.dh == 64) {
+        static int two64 = -1;   // DX_ATTN_FWD64_2CTA=1: head_dim 64 as two single-buffer CTAs per SM (A/B timing)
+        if (two64 < 0) { const char* e = getenv("DX_ATTN_FWD64_2CTA"); two64 = (e && atoi(e) != 0) ? 1 : 0; }
+        if (two64) return online ? launch_fwd_tc<64, 1, 8, true>(a, st) : launch_fwd_tc<64, 1, 8, false>(a, st);
+        return online ? launch_fwd_tc<64, 2, 16, true>(a, st) : launch_fwd_tc<64, 2, 16, false>(a, st);
+    }
     if (a.dh == 16) {
         static int two = -1;   // DX_ATTN_FWD_2CTA=0: the one-CTA-per-SM shape for head_dim 16 as well (A/B timing)
         if (two < 0) { const char* e = getenv("DX_ATTN_FWD_2CTA"); two = (e && atoi(e) == 0) ? 0 : 1; }
-        return two ? launch_fwd_tc<16, 1, 8>(a, st) : launch_fwd_tc<16, 2, 16>(a, st);
+        if (online) return two ? launch_fwd_tc<16, 1, 8, true>(a, st) : launch_fwd_tc<16, 2, 16, true>(a, st);
+        return two ? launch_fwd_tc<16, 1, 8, false>(a, st) : launch_fwd_tc<16, 2, 16, false>(a, st);
     }
     set_last_error("attention_fwd_tc: unsupported head_dim %d", a.dh);
     return DX_ERR_UNSUPPORTED;
