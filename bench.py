@@ -546,7 +546,7 @@ def main():
         sampler.start()
     ms_step, launches = timed(step_resident, args.steps, max(args.warmup, 3))
     # e2e, fixed shape (the same host batch every step)
-    ms_e2e_fixed, _ = timed(make_e2e([host_batch]), max(2, args.steps // 2), 1)
+    ms_e2e_fixed, _ = timed(make_e2e([host_batch]), max(2, args.steps // 2), 3)
     # e2e, varied shapes: warm-up covers every bucket shape once (graph captures), the timed region cycles all host batches
     nv = len(varied)
     h0, m0 = (graphed.hits, graphed.misses) if graphed is not None else (0, 0)
