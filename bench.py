@@ -582,7 +582,8 @@ def main():
     line = {
         'metric': cfg['metric'], 'value': total_frames / (ms_step * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': {'bf16x3': 'bf16x3 (bf16 hi/lo split operands on tcgen05, fp32 accumulate; fp32 state/LN/softmax)',
+        'dtype': {'bf16x3': 'bf16x3 (bf16 hi/lo split operands on tcgen05, 3 passes, fp32 accumulate; weight-gradient sums over >= 4096 rows: 1 pass; '
+                            'fp32 state/LN/softmax)',
                   'tf32': 'tf32', 'fp32': 'f32'}[args.backend],
         'data': 'synthetic',
         'config': {'workload': workload, 'global_batch': cfg['B'] * world, 'valid_frames_per_step': total_frames,

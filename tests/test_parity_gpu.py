@@ -105,6 +105,34 @@ def test_conv_gemm_forward_dgrad_wgrad(dev, backend, shape):
     assert scale_rel_err(db, br.grad) < 2e-5, f'bias grad {shape}'
 
 
+def test_wgrad_pass_policy(dev):
+    """dx_conv_wgrad on the bf16x3 backend, default wgrad_passes = 0: ONE tensor-core pass when the sum runs over >= 4096 rows, three
+    below.  On white-noise operands (the worst case: nothing but rounding noise survives the sum) the one-pass result is bf16-grade
+    (< 5e-3 of the tensor's scale), the three-pass result fp32-grade (< 5e-5); on the model's gradients the two agree to three digits
+    (profiles/r2_pass_ablation.md, test_full_length_parity_vs_oracle runs with the default)."""
+    from daft_exprt_b200 import ops
+    set_backend('bf16x3')
+    Cin, Cout, KW = 128, 256, 3
+    try:
+        for B, S, single in ((4, 1000, False), (5, 1000, True)):          # 4000 and 5000 rows
+            g = torch.Generator().manual_seed(B)
+            x, dy = torch.randn(B, S, Cin, generator=g), torch.randn(B, S, Cout, generator=g)
+            xd, dyd = x.to(dev), dy.to(dev)
+            res = {}
+            for w in (0, 1, 3):
+                ops.set_gemm_passes(3, w)
+                res[w] = ops.conv_wgrad(xd, dyd, B, S, Cin, Cout, KW, (Cout, Cin, KW), want_bias=False)[0].clone()
+            wr = torch.zeros(Cout, Cin, KW, dtype=torch.float64, requires_grad=True)
+            torch.nn.functional.conv1d(x.double().transpose(1, 2), wr, None, padding=1).transpose(1, 2).backward(dy.double())
+            assert torch.equal(res[0], res[1] if single else res[3]), (B, S)
+            assert not torch.equal(res[1], res[3])
+            assert scale_rel_err(res[3], wr.grad) < 5e-5 and 5e-5 < scale_rel_err(res[1], wr.grad) < 5e-3
+    finally:
+        ops.set_gemm_passes()
+    with pytest.raises(RuntimeError):
+        ops.set_gemm_passes(0, 0)
+
+
 @pytest.mark.parametrize('backend', ['fp32', 'bf16x3'])
 @pytest.mark.parametrize('cfg', [(3, 70, 2, 64), (2, 150, 8, 16), (4, 64, 2, 64), (1, 257, 8, 16), (2, 40, 4, 32)])
 def test_attention_forward_backward(dev, cfg, backend):

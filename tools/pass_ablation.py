@@ -21,7 +21,9 @@ from helpers import l2_rel_err, scale_rel_err, targets_of
 dev = torch.device('cuda', 0)
 ops.set_backend('bf16x3')
 N_IDS = 11
-COMBOS = [(3, 3, 3), (3, 3, 2), (3, 3, 1), (3, 2, 3), (3, 1, 3), (3, 2, 2), (3, 1, 1), (2, 2, 2), (2, 1, 1), (1, 1, 1)]
+COMBOS = [(3, 3, 3), (3, 3, 0), (3, 3, 2), (3, 3, 1), (3, 2, 3), (3, 1, 3), (3, 2, 2), (3, 1, 1), (2, 2, 2), (2, 1, 1), (1, 1, 1)]   # wgrad 0 = by reduction length
+if os.environ.get('DX_PA_COMBOS'):   # e.g. "3,3,3;3,3,0"
+    COMBOS = [tuple(int(x) for x in c.split(',')) for c in os.environ['DX_PA_COMBOS'].split(';')]
 
 
 def build(train):
@@ -57,7 +59,8 @@ for f, d, w in COMBOS:
     rows.append({'passes_fwd_dgrad_wgrad': [f, d, w],
                  'mel_scale_rel': scale_rel_err(out[3][0].detach(), ref[3][0].detach()), 'mel_l2_rel': l2_rel_err(out[3][0].detach(), ref[3][0].detach()),
                  'loss_rel': abs(total.item() - tot_o.item()) / abs(tot_o.item()),
-                 'grad_l2_rel_max': errs[-1][0], 'grad_l2_rel_median': errs[len(errs) // 2][0], 'grad_worst_tensor': errs[-1][1]})
+                 'grad_l2_rel_max': errs[-1][0], 'grad_l2_rel_median': errs[len(errs) // 2][0], 'grad_worst_tensor': errs[-1][1],
+                 'grad_l2_rel_top5': [(round(e, 5), n) for e, n in errs[-5:]], 'grads_above_2e-3': sum(e > 2e-3 for e, _ in errs)})
     print(rows[-1], flush=True)
 
 # ---- step time: the bench workload (B=32, train mode) as a captured graph per combination ---------------------------------------

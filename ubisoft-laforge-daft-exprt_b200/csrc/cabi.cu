@@ -69,8 +69,8 @@ int dx_set_gemm_backend(int backend) {
 }
 int dx_get_gemm_backend(void) { return g_backend; }
 int dx_set_gemm_passes(int conv_passes, int wgrad_passes) {
-    DX_REQUIRE(conv_passes >= 1 && conv_passes <= 3 && wgrad_passes >= 1 && wgrad_passes <= 3, "dx_set_gemm_passes: 1..3 (got %d, %d)", conv_passes,
-               wgrad_passes);
+    DX_REQUIRE(conv_passes >= 1 && conv_passes <= 3 && wgrad_passes >= 0 && wgrad_passes <= 3,
+               "dx_set_gemm_passes: conv 1..3, wgrad 0 (by reduction length) or 1..3 (got %d, %d)", conv_passes, wgrad_passes);
     set_tc_passes(conv_passes, wgrad_passes);
     return DX_OK;
 }

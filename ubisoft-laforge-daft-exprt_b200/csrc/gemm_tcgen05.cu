@@ -983,7 +983,10 @@ int make_map_3d(CUtensorMap* map, const void* ptr, int esz, uint64_t d0, uint64_
 int g_num_sms = 0;
 int g_prec = PREC_BF16X3;
 unsigned long long g_tc_launches = 0;
-int g_passes_conv = 3, g_passes_wgrad = 3;   // BF16X3 passes issued by forward / dgrad GEMMs and by weight-gradient GEMMs
+int g_passes_conv = 3, g_passes_wgrad = 0;   // BF16X3 passes issued by forward / dgrad GEMMs and by weight-gradient GEMMs (wgrad 0 = by reduction length)
+// wgrad_passes = 0: a weight gradient sums B*S products per element in fp32; with this many rows or more the rounding of the operands
+// to bf16 (unbiased, independent from row to row) is taken as is: ONE pass on the hi planes, the lo planes are not loaded
+constexpr long long kWgradSinglePassRows = 4096;
 
 int num_sms() {
     if (g_num_sms == 0) {
@@ -1351,7 +1354,7 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
     p.hp_dh = 0; p.hp_NH = 0; p.hp_scale_cols = 0; p.hp_scale = 1.f; p.hp_dot_src = nullptr; p.hp_dot_out = nullptr;
     p.ln_res = nullptr; p.ln_w = nullptr; p.ln_b = nullptr; p.film = nullptr; p.film_stride = 0; p.ln_rstd = nullptr;
     p.ln_p_in = 0.f; p.ln_seed_in = 0; p.dyn = nullptr; p.ln_planes = 0;
-    p.passes = g_passes_wgrad;
+    p.passes = g_passes_wgrad ? g_passes_wgrad : ((long long)a.B * a.S >= kWgradSinglePassRows ? 1 : 3);
     p.B = a.B; p.S = a.S; p.Cin = a.Cin; p.Cout = a.Cout; p.KW = a.KW; p.ldy = a.Cin;
     p.tiles_m_per_b = ceil_div(a.Cout, TM);
     p.tiles_n = ceil_div(a.Cin, TN);

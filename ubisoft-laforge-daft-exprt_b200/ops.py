@@ -52,9 +52,9 @@ def set_backend(name):
     invalidate_packed_weights()
 
 
-def set_gemm_passes(conv=3, wgrad=3):
-    """bf16x3 backend: tensor-core passes per K-step of the GEMMs issued from now on (3 = parity mode; 2 / 1 = reduced precision,
-    see dx_set_gemm_passes).  `conv` applies to forward AND input-gradient GEMMs: switch it between a forward and its backward to
+def set_gemm_passes(conv=3, wgrad=0):
+    """bf16x3 backend: tensor-core passes per K-step of the GEMMs issued from now on (3 = parity mode; 2 / 1 = reduced precision;
+    wgrad 0 = the default: one pass for weight gradients summed over >= 4096 rows, three below — see dx_set_gemm_passes).  `conv` applies to forward AND input-gradient GEMMs: switch it between a forward and its backward to
     give them different pass counts (tools/pass_ablation.py does)."""
     cabi.check(lib().dx_set_gemm_passes(int(conv), int(wgrad)), 'dx_set_gemm_passes')
 
