@@ -11,6 +11,7 @@ VARIANTS = {
     'all_off': {'DX_AB_FUSED_LN': '0', 'DX_AB_FUSED_INPROJ': '0', 'DX_ATTN_BWD_PIPE64': '0'},
     'two_pass_softmax': {'DX_ATTN_FWD_ONLINE': '0'},
     'fwd64_2cta': {'DX_ATTN_FWD64_2CTA': '1'},
+    'no_wgrad_three_tap': {'DX_WGRAD_HALO3': '0'},
 }
 if os.environ.get('DX_AB_ONLY'):   # comma list of variant names
     VARIANTS = {k: v for k, v in VARIANTS.items() if k in os.environ['DX_AB_ONLY'].split(',')}

@@ -870,6 +870,196 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     }
 }
 
+// ---- weight gradient, KW = 3, ONE bf16 pass: all three taps per CTA from one x tile fetched WITH ITS HALO -----------------
+// dW[co][ci][tap] = sum_s dy[s][co] * x[s + tap - 1][ci].  The generic MODE_WGRAD kernel makes one 128 x 128 output tile per
+// (tap, K split) and streams a dy tile and an x tile for each: per 64-row chunk of the reduction 6 tile loads serve 3 taps, and at one
+// tensor-core pass the 128 x 128 x 64 MMAs (~260 cycles) finish long before L2 has delivered the next 32 KB (measured: the K = 32 k
+// row weight gradients run at 0.46 - 0.65 PFLOP/s whatever the pass count buys).  Here a CTA owns (Cout tile, Cin tile, K split) for
+// ALL taps: per chunk it loads the dy tile once and the x tile once with one halo row on each side (66 rows; rows outside the
+// utterance arrive as zeros), and the three taps read it through MN-major UMMA descriptors whose start address is advanced by
+// `tap` rows (the 128-byte swizzle is a function of the absolute shared-memory address, see umma_desc_k_sw128_rows), into three
+// TMEM accumulators.  2 tile loads per chunk instead of 6, 34 KB stages (five of them), 12 MMAs per stage.
+constexpr int WG3_STAGES = 5;
+constexpr int WG3_A_BYTES = 2 * 8192;                            // dy: two 64-channel MN chunks of [64 rows][128 B]
+constexpr int WG3_B_CHUNK = 9 * 1024;                            // x: 66 rows x 128 B, rounded up to the 1024-byte swizzle repeat
+constexpr int WG3_STAGE_BYTES = WG3_A_BYTES + 2 * WG3_B_CHUNK;   // 34816
+constexpr int WG3_TX_BYTES = WG3_A_BYTES + 2 * 66 * 128;
+constexpr int WG3_SMEM = WG3_STAGES * WG3_STAGE_BYTES + 2 * OUT_BYTES + 256 + 1024;
+constexpr int WG3_TMEM_COLS = 512;                               // three 128-column accumulators
+
+struct Wg3Params {
+    const long long* lens;
+    int B, S, Cin, Cout, halo, tiles_m, tiles_n, nsplit, k_chunks, num_tiles;
+};
+struct Wg3Tile { int co0, ci0, split, k_begin, k_end; };
+
+__device__ __forceinline__ Wg3Tile wg3_tile(const Wg3Params& p, int tile) {
+    Wg3Tile t;
+    const int tci = tile % p.tiles_n;
+    const int r = tile / p.tiles_n;
+    t.ci0 = tci * TN; t.co0 = (r % p.tiles_m) * TM; t.split = r / p.tiles_m;
+    const long long total_k = (long long)p.B * p.k_chunks;       // k -> (utterance = k / k_chunks, 64-row chunk = k % k_chunks)
+    t.k_begin = (int)((t.split * total_k) / p.nsplit);
+    t.k_end = (int)(((t.split + 1) * total_k) / p.nsplit);
+    return t;
+}
+// rows at or beyond len + halo carry dy == 0 exactly (see live_rows above): such chunks are not accumulated
+__device__ __forceinline__ int wg3_live(const Wg3Params& p, int b) { return min((int)p.lens[b], p.S) + p.halo; }
+__device__ __forceinline__ bool wg3_k_dead(const Wg3Params& p, int k) {
+    if (p.lens == nullptr) return false;
+    const int b = k / p.k_chunks;
+    return (k - b * p.k_chunks) * 64 >= wg3_live(p, b);
+}
+__device__ __forceinline__ bool wg3_tile_dead(const Wg3Params& p, const Wg3Tile& t) {
+    if (p.lens == nullptr) return false;
+    for (int b = t.k_begin / p.k_chunks; b <= (t.k_end - 1) / p.k_chunks; ++b)
+        if (max(t.k_begin - b * p.k_chunks, 0) * 64 < wg3_live(p, b)) return false;
+    return true;
+}
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_lbo(uint32_t saddr, uint32_t lbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) wgrad_halo3_kernel(const __grid_constant__ CUtensorMap map_dy,     // (co, s, b), box 64 x 64
+                                                                  const __grid_constant__ CUtensorMap map_x,      // (ci, s, b), box 64 x 66
+                                                                  const __grid_constant__ CUtensorMap map_part,   // (ci, co, split * 3 + tap) fp32
+                                                                  Wg3Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sOut = base + WG3_STAGES * WG3_STAGE_BYTES;
+    const uint32_t bars = sOut + 2 * OUT_BYTES;
+    const uint32_t full0 = bars, empty0 = bars + 8 * WG3_STAGES, tfull = bars + 16 * WG3_STAGES, tempty = tfull + 8, tmem_slot = tempty + 8;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < WG3_STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, NUM_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(WG3_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const Wg3Tile t = wg3_tile(p, tile);
+                if (wg3_tile_dead(p, t)) continue;
+                for (int k = t.k_begin; k < t.k_end; ++k) {
+                    if (wg3_k_dead(p, k)) continue;
+                    const int b = k / p.k_chunks, s0 = (k - b * p.k_chunks) * 64;
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t bar = full0 + 8 * stage;
+                    const uint32_t sa = base + stage * WG3_STAGE_BYTES, sb = sa + WG3_A_BYTES;
+                    mbar_expect_tx(bar, WG3_TX_BYTES);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        tma_load_3d(sa + j * 8192, &map_dy, bar, t.co0 + 64 * j, s0, b);
+                        tma_load_3d(sb + j * WG3_B_CHUNK, &map_x, bar, t.ci0 + 64 * j, s0 - 1, b);
+                    }
+                    if (++stage == WG3_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = umma_idesc(1, TM, TN, 1);
+        constexpr uint32_t kstep = (16 * 128) >> 4;              // 16 reduction rows of 128 bytes per K = 16 instruction
+        int stage = 0, phase = 0, it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const Wg3Tile t = wg3_tile(p, tile);
+            if (wg3_tile_dead(p, t)) continue;
+            mbar_wait(tempty, (it & 1) ^ 1);                      // the epilogue has read the three accumulators of the previous live tile
+            ++it;
+            tc_fence_after();
+            uint32_t started = 0;
+            for (int k = t.k_begin; k < t.k_end; ++k) {
+                if (wg3_k_dead(p, k)) continue;
+                mbar_wait(full0 + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t sa = base + stage * WG3_STAGE_BYTES, sb = sa + WG3_A_BYTES;
+                const uint64_t a = umma_desc_mn_sw128(sa);
+                if (elect_one()) {
+#pragma unroll
+                    for (uint32_t tap = 0; tap < 3; ++tap) {
+                        const uint64_t bd = umma_desc_mn_sw128_lbo(sb + tap * 128u, WG3_B_CHUNK);
+#pragma unroll
+                        for (uint32_t kk = 0; kk < 4; ++kk)
+                            umma<PREC_BF16X3>(tmem_base + tap * TN, a + kstep * kk, bd + kstep * kk, idesc, started | kk);
+                    }
+                    umma_commit(empty0 + 8 * stage);
+                }
+                __syncwarp();
+                started = 1;
+                if (++stage == WG3_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one()) umma_commit(tfull);
+            __syncwarp();
+        }
+    } else {
+        const int quad = warp & 3, part = (warp - 2) >> 2;
+        const uint32_t wbuf = sOut + (uint32_t)(warp - 2) * 2048u;
+        const uint32_t rbuf = wbuf + lane * 64;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const Wg3Tile t = wg3_tile(p, tile);
+            const bool dead = wg3_tile_dead(p, t);               // dead tiles are stored as zeros
+            if (!dead) {
+                mbar_wait(tfull, it & 1);
+                tc_fence_after();
+            }
+#pragma unroll 1
+            for (int tap = 0; tap < 3; ++tap) {
+                uint32_t v[32];
+                if (dead) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0u;
+                } else {
+                    tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + tap * TN + part * 32, v);
+                    tmem_ld_wait(v);
+                    if (tap == 2) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty);
+                    }
+                }
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {                  // 32 rows x 16 fp32 columns per round through the SWIZZLE_64B staging tile
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t off = (uint32_t)((c ^ ((lane >> 1) & 3)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbuf + off), "r"(v[16 * hh + 4 * c]), "r"(v[16 * hh + 4 * c + 1]),
+                                     "r"(v[16 * hh + 4 * c + 2]), "r"(v[16 * hh + 4 * c + 3]) : "memory");
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_3d(&map_part, wbuf, t.ci0 + part * 32 + 16 * hh, t.co0 + quad * 32, t.split * 3 + tap);
+                        tma_store_commit();
+                    }
+                }
+            }
+            if (!dead) ++it;
+        }
+        if (lane == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(WG3_TMEM_COLS) : "memory");
+    }
+}
+
 // ---- operand planes: fp32 [B, S, ld] -> bf16 hi/lo, row-major [B*S][C] and/or transposed [C][B][Sp] -------------------
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
     hi = __float2bfloat16_rn(x);
@@ -1238,9 +1428,35 @@ static int wgrad_nsplit(const ConvWgradArgs& a) {
     return best;
 }
 
+// the three-tap kernel (wgrad_halo3_kernel) has KW times fewer tiles per split: it splits the reduction finer to fill the SMs
+static int wgrad3_nsplit(const ConvWgradArgs& a) {
+    const int tiles = ceil_div(a.Cout, TM) * ceil_div(a.Cin, TN);
+    const int sms = 148;
+    int best = 1;
+    double best_eff = 0.0;
+    const int total_k = a.B * ceil_div(a.S, 64);
+    for (int ns = 1; ns <= total_k / 4 && ns <= 64; ++ns) {
+        const int ctas = tiles * ns, waves = ceil_div(ctas, sms);
+        const double eff = (double)ctas / ((double)waves * sms);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = ns; }
+        if (eff >= 0.9 && ctas >= sms) { best = ns; break; }
+    }
+    return best;
+}
+
+bool wgrad_halo3_enabled() {   // DX_WGRAD_HALO3=0: one tile per tap through the generic kernel (A/B timing)
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("DX_WGRAD_HALO3");
+        on = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return on != 0;
+}
+
 size_t conv_wgrad_tc_workspace(const ConvWgradArgs& a) {
     const size_t dye = (size_t)a.B * a.S * a.Cout, xe = (size_t)a.B * a.S * a.Cin;
-    const size_t part = (size_t)wgrad_nsplit(a) * a.KW * a.Cout * a.Cin * 4;
+    const int ns = a.KW == 3 ? (wgrad_nsplit(a) > wgrad3_nsplit(a) ? wgrad_nsplit(a) : wgrad3_nsplit(a)) : wgrad_nsplit(a);   // either kernel
+    const size_t part = (size_t)ns * a.KW * a.Cout * a.Cin * 4;
     return (a.dy_planes ? 0 : 2 * align256(dye * 2)) + (a.x_planes ? 0 : 2 * align256(xe * 2)) + align256(part) + 256;
 }
 
@@ -1318,7 +1534,9 @@ void wgrad_reduce_defer(bool on) {
 int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
     const size_t need = conv_wgrad_tc_workspace(a);
     DX_REQUIRE(a.workspace && a.workspace_bytes >= need, "conv_wgrad_tc: workspace %zu < %zu bytes", a.workspace_bytes, need);
-    const int nsplit = wgrad_nsplit(a);
+    const int passes = g_passes_wgrad ? g_passes_wgrad : ((long long)a.B * a.S >= kWgradSinglePassRows ? 1 : 3);
+    const bool three_tap = passes == 1 && a.KW == 3 && wgrad_halo3_enabled();
+    const int nsplit = three_tap ? wgrad3_nsplit(a) : wgrad_nsplit(a);
     const size_t dye = (size_t)a.B * a.S * a.Cout, xe = (size_t)a.B * a.S * a.Cin;
     uint8_t* ws = (uint8_t*)(((uintptr_t)a.workspace + 255) & ~(uintptr_t)255);
     const size_t dyb = a.dy_planes ? 0 : 2 * align256(dye * 2), xb = a.x_planes ? 0 : 2 * align256(xe * 2);
@@ -1354,7 +1572,7 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
     p.hp_dh = 0; p.hp_NH = 0; p.hp_scale_cols = 0; p.hp_scale = 1.f; p.hp_dot_src = nullptr; p.hp_dot_out = nullptr;
     p.ln_res = nullptr; p.ln_w = nullptr; p.ln_b = nullptr; p.film = nullptr; p.film_stride = 0; p.ln_rstd = nullptr;
     p.ln_p_in = 0.f; p.ln_seed_in = 0; p.dyn = nullptr; p.ln_planes = 0;
-    p.passes = g_passes_wgrad ? g_passes_wgrad : ((long long)a.B * a.S >= kWgradSinglePassRows ? 1 : 3);
+    p.passes = passes;
     p.B = a.B; p.S = a.S; p.Cin = a.Cin; p.Cout = a.Cout; p.KW = a.KW; p.ldy = a.Cin;
     p.tiles_m_per_b = ceil_div(a.Cout, TM);
     p.tiles_n = ceil_div(a.Cin, TN);
@@ -1374,7 +1592,25 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
     if ((rc = make_map_3d(&mbl, xl, 2, a.Cin, a.S, a.B, x1, x2, 64, 64, 1))) return rc;
     if ((rc = make_map_3d(&my, part, 4, a.Cin, a.Cout, (uint64_t)nsplit * a.KW, (uint64_t)a.Cin * 4, (uint64_t)a.Cout * a.Cin * 4, 16, 32, 1, true)))
         return rc;
-    if ((rc = launch<PREC_BF16X3, MODE_WGRAD>(mah, mal, mbh, mbl, my, p, st))) return rc;
+    if (three_tap) {
+        CUtensorMap mx66;   // x with one halo row on each side of the 64-row chunk
+        if ((rc = make_map_3d(&mx66, xh, 2, a.Cin, a.S, a.B, x1, x2, 64, 66, 1))) return rc;
+        Wg3Params q;
+        q.lens = a.lens; q.B = a.B; q.S = a.S; q.Cin = a.Cin; q.Cout = a.Cout; q.halo = a.halo;
+        q.tiles_m = p.tiles_m_per_b; q.tiles_n = p.tiles_n; q.nsplit = nsplit; q.k_chunks = p.k_chunks;
+        q.num_tiles = q.tiles_m * q.tiles_n * nsplit;
+        static bool configured = false;
+        if (!configured) {
+            DX_CUDA(cudaFuncSetAttribute(wgrad_halo3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG3_SMEM));
+            configured = true;
+        }
+        const int grid = q.num_tiles < num_sms() ? q.num_tiles : num_sms();
+        wgrad_halo3_kernel<<<grid, NTHREADS, WG3_SMEM, st>>>(mah, mx66, my, q);
+        ++g_tc_launches;
+        if ((rc = check_launch("wgrad_halo3"))) return rc;
+    } else if ((rc = launch<PREC_BF16X3, MODE_WGRAD>(mah, mal, mbh, mbl, my, p, st))) {
+        return rc;
+    }
     const size_t per = (size_t)a.KW * a.Cout * a.Cin;
     if (g_defer_reduce) {   // the caller keeps the workspace alive until dx_wgrad_flush
         if (g_reduce.n == kMaxReduce && (rc = wgrad_reduce_flush(st))) return rc;
