@@ -1495,6 +1495,19 @@ bool g_defer_reduce = false;
 ReduceBatch g_reduce = {};
 int g_reduce_blocks = 0;
 
+// One block = kReduceChunk consecutive (co, ci) positions of one weight gradient, ALL taps.  The partials are read once from DRAM
+// (~1.5 GB per backward pass at the bench shapes, the whole cost of this kernel): 16-byte streaming loads, eight split slices in
+// flight per thread; k = 3 gradients leave as twelve contiguous floats of dw[co][ci..ci+3][0..2].
+__device__ __forceinline__ float4 reduce_slices4(const float4* src, size_t stride4, int nsplit) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int k = 0; k < nsplit; ++k) {
+        const float4 a = __ldcs(src + (size_t)k * stride4);
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    }
+    return s;
+}
+
 __global__ void __launch_bounds__(256) wgrad_reduce_batched_kernel(const __grid_constant__ ReduceBatch b) {
     int lo = 0, hi = b.n - 1;
     while (lo < hi) {
@@ -1502,18 +1515,35 @@ __global__ void __launch_bounds__(256) wgrad_reduce_batched_kernel(const __grid_
         if (b.d[mid].block0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
     }
     const ReduceDesc& d = b.d[lo];
-    const size_t per = (size_t)d.KW * d.Cout * d.Cin;
+    const size_t cc = (size_t)d.Cout * d.Cin, per = (size_t)d.KW * cc;
     const size_t i0 = (size_t)((int)blockIdx.x - d.block0) * kReduceChunk;
+    const float al = d.alpha;
+    if ((d.Cin & 3) == 0 && (reinterpret_cast<uintptr_t>(d.dw) & 15) == 0 && (d.KW == 1 || d.KW == 3)) {
+        const size_t i = i0 + 4 * threadIdx.x;                    // kReduceChunk = 4 * 256
+        if (i >= cc) return;
+        const float4* src = reinterpret_cast<const float4*>(d.part + i);
+        if (d.KW == 1) {
+            const float4 s = reduce_slices4(src, per / 4, d.nsplit);
+            *reinterpret_cast<float4*>(d.dw + i) = make_float4(al * s.x, al * s.y, al * s.z, al * s.w);
+        } else {
+            const float4 s0 = reduce_slices4(src, per / 4, d.nsplit), s1 = reduce_slices4(src + cc / 4, per / 4, d.nsplit),
+                         s2 = reduce_slices4(src + cc / 2, per / 4, d.nsplit);
+            float4* dst = reinterpret_cast<float4*>(d.dw + 3 * i);
+            dst[0] = make_float4(al * s0.x, al * s1.x, al * s2.x, al * s0.y);
+            dst[1] = make_float4(al * s1.y, al * s2.y, al * s0.z, al * s1.z);
+            dst[2] = make_float4(al * s2.z, al * s0.w, al * s1.w, al * s2.w);
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < kReduceChunk / 256; ++j) {
-        const size_t i = i0 + threadIdx.x + 256 * j;
-        if (i >= per) break;
-        float s = 0.f;
-        for (int k = 0; k < d.nsplit; ++k) s += d.part[(size_t)k * per + i];
-        const int ci = (int)(i % d.Cin);
-        const size_t q = i / d.Cin;
-        const int co = (int)(q % d.Cout), tap = (int)(q / d.Cout);
-        d.dw[((size_t)co * d.Cin + ci) * d.KW + tap] = d.alpha * s;
+        const size_t i = i0 + threadIdx.x + 256 * j;              // (co, ci) position
+        if (i >= cc) break;
+        for (int tap = 0; tap < d.KW; ++tap) {
+            float s = 0.f;
+            for (int k = 0; k < d.nsplit; ++k) s += d.part[(size_t)k * per + (size_t)tap * cc + i];
+            d.dw[i * d.KW + tap] = al * s;
+        }
     }
 }
 
@@ -1617,7 +1647,7 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
         ReduceDesc& d = g_reduce.d[g_reduce.n++];
         d.part = part; d.dw = a.dw; d.nsplit = nsplit; d.KW = a.KW; d.Cout = a.Cout; d.Cin = a.Cin; d.alpha = a.alpha;
         d.block0 = g_reduce_blocks;
-        g_reduce_blocks += (int)((per + kReduceChunk - 1) / kReduceChunk);
+        g_reduce_blocks += (int)(((size_t)a.Cout * a.Cin + kReduceChunk - 1) / kReduceChunk);   // a block = 1024 (co, ci) positions, all taps
     } else {
         wgrad_reduce_tc_kernel<<<grid_1d(per, 256, 148 * 8), 256, 0, st>>>(part, a.dw, nsplit, a.KW, a.Cout, a.Cin, a.alpha);
         if ((rc = check_launch("wgrad_reduce_tc"))) return rc;
