@@ -891,31 +891,35 @@ struct Wg3Params {
     const long long* lens;
     int B, S, Cin, Cout, halo, tiles_m, tiles_n, nsplit, k_chunks, num_tiles;
 };
-struct Wg3Tile { int co0, ci0, split, k_begin, k_end; };
+// The K splits divide the LIVE 64-row chunks evenly (rows at or beyond len + halo carry dy == 0 exactly, see live_rows above, and are
+// never loaded): with the bench batch (lengths 513..1000 of 1000) equal shares of the (utterance, chunk) grid differ by up to 2x in work.
+struct Wg3Tile { int co0, ci0, split, n_begin, n_end; };        // [n_begin, n_end) in live-chunk order
 
-__device__ __forceinline__ Wg3Tile wg3_tile(const Wg3Params& p, int tile) {
+__device__ __forceinline__ int wg3_live_chunks(const Wg3Params& p, int b) {
+    if (p.lens == nullptr) return p.k_chunks;
+    return min(p.k_chunks, (min((int)p.lens[b], p.S) + p.halo + 63) >> 6);
+}
+__device__ __forceinline__ Wg3Tile wg3_tile(const Wg3Params& p, int tile, int total_live) {
     Wg3Tile t;
     const int tci = tile % p.tiles_n;
     const int r = tile / p.tiles_n;
     t.ci0 = tci * TN; t.co0 = (r % p.tiles_m) * TM; t.split = r / p.tiles_m;
-    const long long total_k = (long long)p.B * p.k_chunks;       // k -> (utterance = k / k_chunks, 64-row chunk = k % k_chunks)
-    t.k_begin = (int)((t.split * total_k) / p.nsplit);
-    t.k_end = (int)(((t.split + 1) * total_k) / p.nsplit);
+    t.n_begin = (int)(((long long)t.split * total_live) / p.nsplit);
+    t.n_end = (int)(((long long)(t.split + 1) * total_live) / p.nsplit);
     return t;
 }
-// rows at or beyond len + halo carry dy == 0 exactly (see live_rows above): such chunks are not accumulated
-__device__ __forceinline__ int wg3_live(const Wg3Params& p, int b) { return min((int)p.lens[b], p.S) + p.halo; }
-__device__ __forceinline__ bool wg3_k_dead(const Wg3Params& p, int k) {
-    if (p.lens == nullptr) return false;
-    const int b = k / p.k_chunks;
-    return (k - b * p.k_chunks) * 64 >= wg3_live(p, b);
-}
-__device__ __forceinline__ bool wg3_tile_dead(const Wg3Params& p, const Wg3Tile& t) {
-    if (p.lens == nullptr) return false;
-    for (int b = t.k_begin / p.k_chunks; b <= (t.k_end - 1) / p.k_chunks; ++b)
-        if (max(t.k_begin - b * p.k_chunks, 0) * 64 < wg3_live(p, b)) return false;
-    return true;
-}
+// walks the live chunks of a tile: (b, kc) of live chunk n_begin, then next()
+struct Wg3Walk {
+    int b, kc, lc;
+    __device__ __forceinline__ void start(const Wg3Params& p, int n) {
+        b = 0; lc = wg3_live_chunks(p, 0);
+        while (n >= lc) { n -= lc; ++b; lc = wg3_live_chunks(p, b); }
+        kc = n;
+    }
+    __device__ __forceinline__ void next(const Wg3Params& p) {
+        if (++kc == lc) { kc = 0; ++b; if (b < p.B) lc = wg3_live_chunks(p, b); }
+    }
+};
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128_lbo(uint32_t saddr, uint32_t lbo_bytes) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
@@ -931,12 +935,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_halo3_kernel(const __grid_c
     const uint32_t full0 = bars, empty0 = bars + 8 * WG3_STAGES, tfull = bars + 16 * WG3_STAGES, tempty = tfull + 8, tmem_slot = tempty + 8;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    volatile int* total_slot = reinterpret_cast<volatile int*>(smem_raw + (tmem_slot + 8 - smem_u32(smem_raw)));
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < WG3_STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
         mbar_init(tfull, 1);
         mbar_init(tempty, NUM_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        int tot = 0;
+        for (int b = 0; b < p.B; ++b) tot += wg3_live_chunks(p, b);
+        *total_slot = tot;
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(WG3_TMEM_COLS) : "memory");
@@ -946,16 +954,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_halo3_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    const int total_live = *total_slot;
 
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const Wg3Tile t = wg3_tile(p, tile);
-                if (wg3_tile_dead(p, t)) continue;
-                for (int k = t.k_begin; k < t.k_end; ++k) {
-                    if (wg3_k_dead(p, k)) continue;
-                    const int b = k / p.k_chunks, s0 = (k - b * p.k_chunks) * 64;
+                const Wg3Tile t = wg3_tile(p, tile, total_live);
+                if (t.n_begin == t.n_end) continue;
+                Wg3Walk w;
+                w.start(p, t.n_begin);
+                for (int n = t.n_begin; n < t.n_end; ++n, w.next(p)) {
+                    const int b = w.b, s0 = w.kc * 64;
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t bar = full0 + 8 * stage;
                     const uint32_t sa = base + stage * WG3_STAGE_BYTES, sb = sa + WG3_A_BYTES;
@@ -974,14 +984,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_halo3_kernel(const __grid_c
         constexpr uint32_t kstep = (16 * 128) >> 4;              // 16 reduction rows of 128 bytes per K = 16 instruction
         int stage = 0, phase = 0, it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const Wg3Tile t = wg3_tile(p, tile);
-            if (wg3_tile_dead(p, t)) continue;
+            const Wg3Tile t = wg3_tile(p, tile, total_live);
+            if (t.n_begin == t.n_end) continue;
             mbar_wait(tempty, (it & 1) ^ 1);                      // the epilogue has read the three accumulators of the previous live tile
             ++it;
             tc_fence_after();
             uint32_t started = 0;
-            for (int k = t.k_begin; k < t.k_end; ++k) {
-                if (wg3_k_dead(p, k)) continue;
+            for (int n = t.n_begin; n < t.n_end; ++n) {
                 mbar_wait(full0 + 8 * stage, phase);
                 tc_fence_after();
                 const uint32_t sa = base + stage * WG3_STAGE_BYTES, sb = sa + WG3_A_BYTES;
@@ -1009,8 +1018,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_halo3_kernel(const __grid_c
         const uint32_t rbuf = wbuf + lane * 64;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const Wg3Tile t = wg3_tile(p, tile);
-            const bool dead = wg3_tile_dead(p, t);               // dead tiles are stored as zeros
+            const Wg3Tile t = wg3_tile(p, tile, total_live);
+            const bool dead = t.n_begin == t.n_end;              // a split without live chunks stores zeros
             if (!dead) {
                 mbar_wait(tfull, it & 1);
                 tc_fence_after();
