@@ -35,7 +35,7 @@ extern "C" {
 #define DX_ABI_VERSION 1
 #define DX_GEMM_FP32_CUDA_CORES 0 /* exact fp32 (parity mode) */
 #define DX_GEMM_TCGEN05_TF32 1    /* tcgen05.mma kind::tf32 on fp32 tiles: one pass, ~1e-3 per GEMM (forward/dgrad; wgrad runs bf16x3) */
-#define DX_GEMM_TCGEN05_BF16X3 2  /* tcgen05.mma kind::f16 on bf16 hi/lo operand planes, 3 passes, fp32-grade results (default) */
+#define DX_GEMM_TCGEN05_BF16X3 2  /* tcgen05.mma kind::f16 on bf16 hi/lo operand planes, 3 passes, fp32-grade results (default; see dx_set_gemm_passes) */
 
 const char* dx_last_error(void);
 int dx_abi_version(void);

@@ -43,7 +43,8 @@ BACKENDS = {'fp32': cabi.DX_GEMM_FP32_CUDA_CORES, 'tf32': cabi.DX_GEMM_TCGEN05_T
 
 def set_backend(name):
     """GEMM backend for Conv1d/Linear forward, dgrad and wgrad:
-    'bf16x3' tcgen05 tensor cores on bf16 hi/lo operand planes, 3 passes, fp32-grade results (default);
+    'bf16x3' tcgen05 tensor cores on bf16 hi/lo operand planes, 3 passes, fp32-grade results (default; weight gradients summed
+             over >= 4096 rows take one pass, see set_gemm_passes);
     'tf32'   tcgen05 kind::tf32 on fp32 tiles, one pass, ~1e-3 per GEMM (wgrad still runs bf16x3);
     'fp32'   exact fp32 on CUDA cores (strict parity mode)."""
     be = BACKENDS[name]
