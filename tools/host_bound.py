@@ -21,7 +21,7 @@ crit = DaftExprtLoss(0, hp)
 params = list(model.parameters())
 sync = FlatGradSync(params, mode='gather')
 opt = FlatAdam(params, sync, lr=hp.initial_learning_rate, betas=hp.betas, eps=hp.epsilon, weight_decay=hp.weight_decay)
-inputs, targets, _ = model.parse_batch(0, bench.make_host_batch(0))
+inputs, targets, _ = model.parse_batch(0, bench.with_ids(bench.rank_batch(bench.CONFIGS['train'], 0)))
 
 def step(it):
     opt.zero_grad()
