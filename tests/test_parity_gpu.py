@@ -133,16 +133,18 @@ def test_wgrad_pass_policy(dev):
         ops.set_gemm_passes(0, 0)
 
 
-@pytest.mark.parametrize('shape', [(5, 1000, 128, 256), (3, 1500, 80, 1024), (9, 500, 1024, 128), (40, 120, 200, 96), (2, 2100, 256, 256)])
+@pytest.mark.parametrize('shape', [(5, 1000, 128, 256, 3), (3, 1500, 80, 1024, 3), (9, 500, 1024, 128, 3), (40, 120, 200, 96, 3), (2, 2100, 256, 256, 3),
+                                   (5, 1000, 128, 384, 1), (33, 200, 128, 128, 1), (7, 700, 1024, 80, 1)])
 @pytest.mark.parametrize('ragged', [False, True])
 def test_wgrad_three_tap_kernel(dev, shape, ragged):
     """k=3 weight gradients with a long reduction run in `wgrad_halo3_kernel` (one dy tile and ONE x tile with its halo per 64-row
     chunk, three row-shifted MN-major descriptors, three TMEM accumulators).  One bf16 pass computes exactly the sum of products of
     the bf16-rounded operands (fp32 accumulation), so that fp64 sum is the oracle here (1e-5 of the tensor's scale): channel counts
-    off the 64 / 128 tile grid, row counts off the 64-row chunk grid, and — ragged — padding skipped through lens + halo."""
+    off the 64 / 128 tile grid, row counts off the 64-row chunk grid, and — ragged — padding skipped through lens + halo.  k = 1
+    weight gradients with a long reduction run in the same kernel (one tap, no halo)."""
     from daft_exprt_b200 import ops
     set_backend('bf16x3')
-    B, S, Cin, Cout = shape
+    B, S, Cin, Cout, KW = shape
     assert B * S >= 4096
     g = torch.Generator().manual_seed(sum(shape))
     x, dy = torch.randn(B, S, Cin, generator=g), torch.randn(B, S, Cout, generator=g)
@@ -152,11 +154,11 @@ def test_wgrad_three_tap_kernel(dev, shape, ragged):
         lens[0] = S
         halo = 1
         dy = dy * (torch.arange(S)[None, :] < (lens[:, None] + halo))[:, :, None]     # the caller's contract: dy == 0 beyond len + halo
-    dw = ops.conv_wgrad(x.to(dev), dy.to(dev), B, S, Cin, Cout, 3, (Cout, Cin, 3), want_bias=False,
+    dw = ops.conv_wgrad(x.to(dev), dy.to(dev), B, S, Cin, Cout, KW, (Cout, Cin, KW), want_bias=False,
                         lens=None if lens is None else lens.to(dev), halo=halo)[0]
     xr, dyr = x.bfloat16().double(), dy.bfloat16().double()
-    wr = torch.zeros(Cout, Cin, 3, dtype=torch.float64, requires_grad=True)
-    torch.nn.functional.conv1d(xr.transpose(1, 2), wr, None, padding=1).transpose(1, 2).backward(dyr)
+    wr = torch.zeros(Cout, Cin, KW, dtype=torch.float64, requires_grad=True)
+    torch.nn.functional.conv1d(xr.transpose(1, 2), wr, None, padding=(KW - 1) // 2).transpose(1, 2).backward(dyr)
     assert scale_rel_err(dw, wr.grad) < 1e-5
 
 

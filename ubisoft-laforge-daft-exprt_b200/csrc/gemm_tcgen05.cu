@@ -883,8 +883,9 @@ constexpr int WG3_STAGES = 5;
 constexpr int WG3_A_BYTES = 2 * 8192;                            // dy: two 64-channel MN chunks of [64 rows][128 B]
 constexpr int WG3_B_CHUNK = 9 * 1024;                            // x: 66 rows x 128 B, rounded up to the 1024-byte swizzle repeat
 constexpr int WG3_STAGE_BYTES = WG3_A_BYTES + 2 * WG3_B_CHUNK;   // 34816
-constexpr int WG3_TX_BYTES = WG3_A_BYTES + 2 * 66 * 128;
 constexpr int WG3_SMEM = WG3_STAGES * WG3_STAGE_BYTES + 2 * OUT_BYTES + 256 + 1024;
+// The same kernel serves k = 1 (KW = 1: a 64-row x box, one accumulator): five 32 KB stages in flight and K splits over live chunks
+// instead of the generic kernel's three 64 KB stages, half of each unused at one pass.
 constexpr int WG3_TMEM_COLS = 512;                               // three 128-column accumulators
 
 struct Wg3Params {
@@ -924,6 +925,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128_lbo(uint32_t saddr, uint3
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+template <int KW>
 __global__ void __launch_bounds__(NTHREADS, 1) wgrad_halo3_kernel(const __grid_constant__ CUtensorMap map_dy,     // (co, s, b), box 64 x 64
                                                                   const __grid_constant__ CUtensorMap map_x,      // (ci, s, b), box 64 x 66
                                                                   const __grid_constant__ CUtensorMap map_part,   // (ci, co, split * 3 + tap) fp32
@@ -969,11 +971,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_halo3_kernel(const __grid_c
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t bar = full0 + 8 * stage;
                     const uint32_t sa = base + stage * WG3_STAGE_BYTES, sb = sa + WG3_A_BYTES;
-                    mbar_expect_tx(bar, WG3_TX_BYTES);
+                    mbar_expect_tx(bar, WG3_A_BYTES + 2 * (64 + KW - 1) * 128);
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         tma_load_3d(sa + j * 8192, &map_dy, bar, t.co0 + 64 * j, s0, b);
-                        tma_load_3d(sb + j * WG3_B_CHUNK, &map_x, bar, t.ci0 + 64 * j, s0 - 1, b);
+                        tma_load_3d(sb + j * WG3_B_CHUNK, &map_x, bar, t.ci0 + 64 * j, s0 - (KW - 1) / 2, b);
                     }
                     if (++stage == WG3_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -997,7 +999,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_halo3_kernel(const __grid_c
                 const uint64_t a = umma_desc_mn_sw128(sa);
                 if (elect_one()) {
 #pragma unroll
-                    for (uint32_t tap = 0; tap < 3; ++tap) {
+                    for (uint32_t tap = 0; tap < (uint32_t)KW; ++tap) {
                         const uint64_t bd = umma_desc_mn_sw128_lbo(sb + tap * 128u, WG3_B_CHUNK);
 #pragma unroll
                         for (uint32_t kk = 0; kk < 4; ++kk)
@@ -1025,7 +1027,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_halo3_kernel(const __grid_c
                 tc_fence_after();
             }
 #pragma unroll 1
-            for (int tap = 0; tap < 3; ++tap) {
+            for (int tap = 0; tap < KW; ++tap) {
                 uint32_t v[32];
                 if (dead) {
 #pragma unroll
@@ -1033,7 +1035,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_halo3_kernel(const __grid_c
                 } else {
                     tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + tap * TN + part * 32, v);
                     tmem_ld_wait(v);
-                    if (tap == 2) {
+                    if (tap == KW - 1) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty);
@@ -1052,7 +1054,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_halo3_kernel(const __grid_c
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_3d(&map_part, wbuf, t.ci0 + part * 32 + 16 * hh, t.co0 + quad * 32, t.split * 3 + tap);
+                        tma_store_3d(&map_part, wbuf, t.ci0 + part * 32 + 16 * hh, t.co0 + quad * 32, t.split * KW + tap);
                         tma_store_commit();
                     }
                 }
@@ -1464,7 +1466,7 @@ bool wgrad_halo3_enabled() {   // DX_WGRAD_HALO3=0: one tile per tap through the
 
 size_t conv_wgrad_tc_workspace(const ConvWgradArgs& a) {
     const size_t dye = (size_t)a.B * a.S * a.Cout, xe = (size_t)a.B * a.S * a.Cin;
-    const int ns = a.KW == 3 ? (wgrad_nsplit(a) > wgrad3_nsplit(a) ? wgrad_nsplit(a) : wgrad3_nsplit(a)) : wgrad_nsplit(a);   // either kernel
+    const int ns = wgrad_nsplit(a) > wgrad3_nsplit(a) ? wgrad_nsplit(a) : wgrad3_nsplit(a);   // either kernel
     const size_t part = (size_t)ns * a.KW * a.Cout * a.Cin * 4;
     return (a.dy_planes ? 0 : 2 * align256(dye * 2)) + (a.x_planes ? 0 : 2 * align256(xe * 2)) + align256(part) + 256;
 }
@@ -1574,7 +1576,7 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
     const size_t need = conv_wgrad_tc_workspace(a);
     DX_REQUIRE(a.workspace && a.workspace_bytes >= need, "conv_wgrad_tc: workspace %zu < %zu bytes", a.workspace_bytes, need);
     const int passes = g_passes_wgrad ? g_passes_wgrad : ((long long)a.B * a.S >= kWgradSinglePassRows ? 1 : 3);
-    const bool three_tap = passes == 1 && a.KW == 3 && wgrad_halo3_enabled();
+    const bool three_tap = passes == 1 && (a.KW == 3 || a.KW == 1) && wgrad_halo3_enabled();   // all taps per CTA (wgrad_halo3_kernel<KW>)
     const int nsplit = three_tap ? wgrad3_nsplit(a) : wgrad_nsplit(a);
     const size_t dye = (size_t)a.B * a.S * a.Cout, xe = (size_t)a.B * a.S * a.Cin;
     uint8_t* ws = (uint8_t*)(((uintptr_t)a.workspace + 255) & ~(uintptr_t)255);
@@ -1632,19 +1634,21 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t st) {
     if ((rc = make_map_3d(&my, part, 4, a.Cin, a.Cout, (uint64_t)nsplit * a.KW, (uint64_t)a.Cin * 4, (uint64_t)a.Cout * a.Cin * 4, 16, 32, 1, true)))
         return rc;
     if (three_tap) {
-        CUtensorMap mx66;   // x with one halo row on each side of the 64-row chunk
-        if ((rc = make_map_3d(&mx66, xh, 2, a.Cin, a.S, a.B, x1, x2, 64, 66, 1))) return rc;
+        CUtensorMap mx66;   // x with one halo row on each side of the 64-row chunk (k = 3)
+        if ((rc = make_map_3d(&mx66, xh, 2, a.Cin, a.S, a.B, x1, x2, 64, 64 + a.KW - 1, 1))) return rc;
         Wg3Params q;
         q.lens = a.lens; q.B = a.B; q.S = a.S; q.Cin = a.Cin; q.Cout = a.Cout; q.halo = a.halo;
         q.tiles_m = p.tiles_m_per_b; q.tiles_n = p.tiles_n; q.nsplit = nsplit; q.k_chunks = p.k_chunks;
         q.num_tiles = q.tiles_m * q.tiles_n * nsplit;
         static bool configured = false;
         if (!configured) {
-            DX_CUDA(cudaFuncSetAttribute(wgrad_halo3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG3_SMEM));
+            DX_CUDA(cudaFuncSetAttribute(wgrad_halo3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG3_SMEM));
+            DX_CUDA(cudaFuncSetAttribute(wgrad_halo3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG3_SMEM));
             configured = true;
         }
         const int grid = q.num_tiles < num_sms() ? q.num_tiles : num_sms();
-        wgrad_halo3_kernel<<<grid, NTHREADS, WG3_SMEM, st>>>(mah, mx66, my, q);
+        if (a.KW == 3) wgrad_halo3_kernel<3><<<grid, NTHREADS, WG3_SMEM, st>>>(mah, mx66, my, q);
+        else wgrad_halo3_kernel<1><<<grid, NTHREADS, WG3_SMEM, st>>>(mah, mx66, my, q);
         ++g_tc_launches;
         if ((rc = check_launch("wgrad_halo3"))) return rc;
     } else if ((rc = launch<PREC_BF16X3, MODE_WGRAD>(mah, mal, mbh, mbl, my, p, st))) {
